@@ -1,0 +1,73 @@
+// chain.h -- per-chain persistent state and the K-iteration chain runner shared by the sm_100a
+// kernel (one thread = one chain) and the host twin used as the bit-level oracle.
+//
+// Reference: the body of the ParallelFor lambda, src/mlt.cpp:60-196 (RNG(chainId + seedOffset)
+// :61-62; currentState = initStates[chainId], valid = false :68, src/mlt.h:124; loop :91-170).
+#pragma once
+#include "mutation.h"
+
+namespace lmc {
+
+template <int MAXD>
+struct ChainState {
+    MarkovState<MAXD> st[2];
+    ChainVars<MAXD> ch;
+    int curIdx;
+    unsigned long long rngState;
+    unsigned int rngEpoch;
+    unsigned int seeded;
+    long long sampleIdx;
+    // counters (lmc_stats)
+    unsigned int nAccept[4];     // per MutationType
+    unsigned int nPropose[4];
+    unsigned int gradStats[2];   // gradient evaluations, non-finite gradients
+};
+
+template <int MAXD>
+LMC_HD void chain_state_init(ChainState<MAXD> &cs, float initLsScore) {
+    for (int k = 0; k < 2; k++) {
+        MarkovState<MAXD> &s = cs.st[k];
+        s.valid = 0; s.gaussianInitialized = 0; s.nSplat = 0; s.scoreSum = 0.0f;
+        s.sp.camDepth = 0; s.sp.lightDepth = 0; s.sp.screenPos = mk2(0, 0); s.sp.contrib = mk3s(0.0f);
+        s.sp.lsScore = 0.0f; s.sp.ssScore = 0.0f;
+        path_clear(s.path);
+        s.path.camDepth = 0; s.path.lgtDepth = 0; s.path.time = 0.0f;
+        s.gaussian.dim = 0; s.gaussian.logDet = 0.0f;
+    }
+    cs.st[0].sp.lsScore = initLsScore;   // initStates[chainId].spContrib.lsScore
+    chain_vars_init(cs.ch);
+    cs.curIdx = 0; cs.rngState = 0ULL; cs.rngEpoch = 0u; cs.seeded = 0u; cs.sampleIdx = 0;
+    for (int i = 0; i < 4; i++) { cs.nAccept[i] = 0; cs.nPropose[i] = 0; }
+    cs.gradStats[0] = 0; cs.gradStats[1] = 0;
+}
+
+// Runs `numSteps` iterations of chain `globalChainId`.  `tab`/`stride` is scratch for the
+// 64-entry PCG extension table (regenerated from the seed, never stored with the chain).
+// trace (optional): one byte per step = mutationType | accepted << 2 | (a > 0) << 3;
+// aTrace (optional): the acceptance probability of each step.
+template <int MAXD, class FILM>
+LMC_HD void chain_run(const Scene &sc, const RunParams &rp, int globalChainId, ChainState<MAXD> &cs,
+                      long long numSteps, uint32_t *tab, int stride, FILM &film,
+                      unsigned char *trace, float *aTrace, long long traceStride) {
+    Rng rng; rng.tab = tab; rng.stride = stride;
+    const uint64_t seed = (uint64_t)(long long)(globalChainId + sc.opt.seedOffset);
+    if (!cs.seeded) {
+        rng_seed(rng, seed);
+        cs.seeded = 1u;
+    } else {
+        rng_restore(rng, seed, cs.rngState, cs.rngEpoch);
+    }
+    for (long long k = 0; k < numSteps; k++) {
+        const StepInfo info = chain_step(sc, rp, globalChainId, cs.sampleIdx, cs.st, cs.curIdx, cs.ch, rng, film,
+                                         cs.gradStats);
+        cs.nPropose[info.mutationType] += 1u;
+        cs.nAccept[info.mutationType] += (unsigned int)info.accepted;
+        if (trace) trace[k * traceStride] = (unsigned char)(info.mutationType | (info.accepted << 2) | ((info.a > 0.0f) ? 8 : 0));
+        if (aTrace) aTrace[k * traceStride] = info.a;
+        cs.sampleIdx += 1;
+    }
+    cs.rngState = rng.state;
+    cs.rngEpoch = rng.epoch;
+}
+
+}  // namespace lmc

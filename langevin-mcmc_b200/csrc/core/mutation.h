@@ -1,0 +1,371 @@
+// mutation.h -- Gaussian proposals, the three mutation kernels and one iteration of the MLT
+// chain loop.  The reference's virtual `Mutation::Mutate` (src/mutation.h:16-26) becomes the
+// enum-dispatched `chain_step`; one call == one iteration of the loop at src/mlt.cpp:91-170.
+//
+//   Gaussian / IsotropicGaussian / GaussianLogPdf / GenerateSample   src/gaussian.{h,cpp}
+//   ComputeGaussian (LMC, diagonal)                                  src/mala.cpp:7-51
+//   SmallStep::Mutate                                                src/mutation_small.h:16-55
+//   MALASmallStep::Mutate                                            src/mutation_mala.h:35-278
+//   LargeStep::Mutate                                                src/mutation_large.h:31-127
+//   chain loop body (step choice, splat, accept, moment commit, outlier reset)  src/mlt.cpp:91-170
+//   Splat                                                            src/image.h:66-77
+//
+// The global KD-tree cache is out of scope: `isReady(dim)` is constant
+// false, so every eligible MALA step evaluates a gradient.
+#pragma once
+#include "path.h"
+#include "pathgrad.h"
+
+namespace lmc {
+
+enum MutationType { MUT_LARGE = 0, MUT_SMALL = 1, MUT_H2MC_SMALL = 2, MUT_MALA_SMALL = 3 };  // src/mutation.h:11
+
+#define LMC_PCD_MIN 0.01f
+#define LMC_PCD_MAX 100.0f
+#define LMC_MTM_MIN (-5.0f)
+#define LMC_MTM_MAX 5.0f
+#define LMC_OUTLIER_WEAK_REJECT_CNT 10000
+#define LMC_OUTLIER_STRONG_REJECT_CNT 1000
+#define LMC_OUTLIER_RATIO_THRESHOLD 30.0f
+
+template <int DIM>
+struct Gaussian {                // src/gaussian.h:9-19 (diagonal members only; dense = H2MC)
+    int dim;
+    float logDet;
+    float mean[DIM], covL_d[DIM], invCov_d[DIM];
+};
+
+template <int DIM>
+LMC_HD void isotropic_gaussian(int dim, float sigma, Gaussian<DIM> &g) {
+    g.dim = dim;
+    const float inv = 1.0f / (sigma * sigma);
+    for (int i = 0; i < dim; i++) { g.mean[i] = 0.0f; g.covL_d[i] = sigma; g.invCov_d[i] = inv; }
+    g.logDet = (float)dim * dm_fastlog(inverse(sigma * sigma));
+}
+
+template <int DIM>
+LMC_HD float gaussian_log_pdf(const float *offset, float sign, const Gaussian<DIM> &g) {
+    float logPdf = (float)g.dim * (-0.9189385332046727f);
+    logPdf += 0.5f * g.logDet;
+    float q = 0.0f;
+    for (int i = 0; i < g.dim; i++) {
+        const float d = sign * offset[i] - g.mean[i];
+        q += d * (g.invCov_d[i] * d);
+    }
+    logPdf -= 0.5f * q;
+    return logPdf;
+}
+
+template <int DIM>
+LMC_HD void generate_sample(const Gaussian<DIM> &g, float *x, Rng &rng) {
+    NormalDist nd = normal_make(0.0f, 1.0f);
+    for (int i = 0; i < g.dim; i++) x[i] = normal_draw(nd, rng);
+    for (int i = 0; i < g.dim; i++) x[i] = g.covL_d[i] * x[i] + g.mean[i];
+}
+
+// ComputeGaussian (src/mala.cpp:7-51)
+template <int DIM>
+LMC_HD void compute_gaussian_lmc(int dim, const float *v1, const float *M, float ss, float shk, float sc,
+                                 Gaussian<DIM> &g) {
+    g.dim = dim;
+    g.logDet = 0.0f;
+    const float shrk = inverse(shk * shk);
+    if (sc <= 1e-10f) {
+        for (int i = 0; i < dim; i++) { g.mean[i] = 0.0f; g.invCov_d[i] = shrk; g.covL_d[i] = shk; }
+        g.logDet = (float)dim * dm_fastlog(inverse(shk * shk));
+    } else {
+        for (int i = 0; i < dim; i++) {
+            const float cov_t = ss * ss * (M[i] + 1.0f);
+            const float invcov = inverse(cov_t) + shrk;
+            const float cov = inverse(invcov);
+            g.invCov_d[i] = invcov;
+            g.covL_d[i] = dm_sqrt(cov);
+            g.mean[i] = dm_clamp(v1[i], LMC_MTM_MIN, LMC_MTM_MAX) * cov / 2.0f;
+            g.logDet += dm_fastlog(invcov);
+        }
+    }
+}
+
+struct SplatSample { V2 screenPos; V3 contrib; };
+
+template <int MAXD>
+struct Limits {
+    static const int DIM = 2 * MAXD;
+    // upper bound on the contributions of one GeneratePathBidir call (path.h derivation)
+    static const int MAXC = (MAXD - 1) + 1 + (MAXD - 1) + ((MAXD - 2) * (MAXD - 1)) / 2 + 2;
+};
+
+template <int MAXD>
+struct MarkovState {             // src/mlt.h:30-39
+    int valid;
+    SubpathContrib sp;
+    Path<MAXD> path;
+    float scoreSum;
+    int gaussianInitialized;
+    Gaussian<Limits<MAXD>::DIM> gaussian;
+    int nSplat;
+    SplatSample splat[Limits<MAXD>::MAXC];
+};
+
+template <int MAXD>
+struct ChainVars {               // Chain (src/mutation.h:28-43) + per-chain loop locals (src/mlt.cpp:61-90)
+    float v1[Limits<MAXD>::DIM], v2[Limits<MAXD>::DIM];
+    float curr_new_v1[Limits<MAXD>::DIM], curr_new_v2[Limits<MAXD>::DIM];
+    float prop_new_v1[Limits<MAXD>::DIM], prop_new_v2[Limits<MAXD>::DIM];
+    int buffered;
+    int t;
+    float lastScoreSum, lastScore;    // LargeStep members (src/mutation_large.h:16-17)
+    int adjacentReject;
+    int lastMutationType;
+};
+
+template <int MAXD>
+LMC_HD void chain_vars_init(ChainVars<MAXD> &c) {
+    for (int i = 0; i < Limits<MAXD>::DIM; i++) {
+        c.v1[i] = 0; c.v2[i] = 0; c.curr_new_v1[i] = 0; c.curr_new_v2[i] = 0; c.prop_new_v1[i] = 0; c.prop_new_v2[i] = 0;
+    }
+    c.buffered = 0; c.t = 0; c.lastScoreSum = 1.0f; c.lastScore = 1.0f; c.adjacentReject = 0; c.lastMutationType = MUT_LARGE;
+}
+
+// Film accumulation (src/image.h:66-77).  FILM is a functor add(pixelIndex, channel, value)
+// so the device can use red.global.add.f32 and the host twin a plain +=.
+template <class FILM>
+LMC_HD void splat(FILM &film, int width, int height, V2 screenPos, V3 contrib) {
+    const int ix = dm_clampi((int)(screenPos.x * (float)width), 0, width - 1);
+    const int iy = dm_clampi((int)(screenPos.y * (float)height), 0, height - 1);
+    if (all_finite(contrib)) {
+        const int pix = iy * width + ix;
+        film.add(pix, 0, contrib.x); film.add(pix, 1, contrib.y); film.add(pix, 2, contrib.z);
+    }
+}
+
+// --- gradient + Adam-style moments + Gaussian for one state (src/mutation_mala.h:83-166 / :178-260) ---
+template <int MAXD>
+LMC_HD void mala_build_gaussian(const Scene &sc, const MarkovState<MAXD> &st, ChainVars<MAXD> &ch,
+                                float *new_v1, float *new_v2, Gaussian<Limits<MAXD>::DIM> &out,
+                                unsigned int *gradStats) {
+    const int dim = path_dimension(st.path);
+    const SubpathContrib &csp = st.sp;
+    const bool haveFunc = (csp.camDepth + csp.lightDepth - 1) <= sc.opt.maxDervDepth &&
+                          grad_supported(sc, st.path);
+    if (dim >= sc.opt.pssMinLength && dim <= sc.opt.pssMaxLength && haveFunc) {
+        float vGrad[Limits<MAXD>::DIM];
+        for (int i = 0; i < dim; i++) vGrad[i] = 0.0f;
+        if (csp.ssScore > 1e-10f) {
+            path_gradient(sc, st.path, vGrad);
+            bool finite = true;
+            for (int i = 0; i < dim; i++) if (!dm_isfinite(vGrad[i])) finite = false;
+            if (!finite) {
+                for (int i = 0; i < dim; i++) vGrad[i] = 0.0f;
+                if (gradStats) gradStats[1]++;
+            }
+            if (gradStats) gradStats[0]++;
+        }
+        float norm = 0.0f;
+        const float drift = sc.opt.malaGN;
+        for (int i = 0; i < dim; i++) norm += vGrad[i] * vGrad[i];
+        norm = dm_sqrt(norm);
+        for (int i = 0; i < dim; i++) vGrad[i] *= drift / dm_max(drift, norm);
+        bool first = true;
+        for (int i = 0; i < dim; i++) if (new_v2[i] > 1e-10f) { first = false; break; }
+        float M[Limits<MAXD>::DIM];
+        for (int i = 0; i < dim; i++) {
+            const float g = vGrad[i];
+            new_v1[i] = first ? g : 0.9f * ch.v1[i] + 0.1f * g;
+            new_v2[i] = first ? g * g : 0.999f * ch.v2[i] + 0.001f * g * g;
+            M[i] = dm_clamp(1.0f / (1e-3f + dm_sqrt(new_v2[i])), LMC_PCD_MIN, LMC_PCD_MAX);
+        }
+        compute_gaussian_lmc(dim, new_v1, M, sc.opt.malaStepsize, sc.opt.malaStdDev, csp.ssScore, out);
+    } else {
+        isotropic_gaussian(dim, sc.opt.malaStdDev, out);
+    }
+}
+
+// SmallStep::Mutate
+template <int MAXD>
+LMC_HD float small_step_mutate(const Scene &sc, float normalization, MarkovState<MAXD> &cur,
+                               MarkovState<MAXD> &prop, Rng &rng, ChainVars<MAXD> &ch) {
+    ContribList<2> contribs; contribs.clear();
+    float a = 1.0f;
+    path_copy(prop.path, cur.path);
+    NormalDist nd = normal_make(0.0f, sc.opt.perturbStdDev);
+    ch.lastMutationType = MUT_SMALL;
+    const int dim = path_dimension(cur.path);
+    float offset[Limits<MAXD>::DIM];
+    for (int i = 0; i < dim; i++) offset[i] = normal_draw(nd, rng);
+    perturb_path_bidir(sc, offset, prop.path, contribs, rng);
+    prop.gaussianInitialized = 0;
+    if (contribs.n > 0) {
+        prop.sp = contribs.c[0];
+        a = dm_clamp(prop.sp.ssScore / cur.sp.ssScore, 0.0f, 1.0f);
+        prop.nSplat = 1;
+        prop.splat[0].screenPos = prop.sp.screenPos;
+        prop.splat[0].contrib = prop.sp.contrib * (normalization / prop.sp.lsScore);
+    } else {
+        a = 0.0f;
+    }
+    return a;
+}
+
+// MALASmallStep::Mutate
+template <int MAXD>
+LMC_HD float mala_small_step_mutate(const Scene &sc, float normalization, MarkovState<MAXD> &cur,
+                                    MarkovState<MAXD> &prop, Rng &rng, ChainVars<MAXD> &ch,
+                                    unsigned int *gradStats) {
+    if (rng_uniform(rng) < sc.opt.uniformMixingProbability) {
+        return small_step_mutate(sc, normalization, cur, prop, rng, ch);
+    }
+    ContribList<2> contribs; contribs.clear();
+    float a = 1.0f;
+    ch.lastMutationType = MUT_MALA_SMALL;
+    const int dim = path_dimension(cur.path);
+    if (!ch.buffered) {
+        for (int i = 0; i < Limits<MAXD>::DIM; i++) {
+            ch.v1[i] = 0; ch.v2[i] = 0; ch.curr_new_v1[i] = 0; ch.curr_new_v2[i] = 0;
+            ch.prop_new_v1[i] = 0; ch.prop_new_v2[i] = 0;
+        }
+        ch.buffered = 1;
+    }
+    if (!cur.gaussianInitialized) {
+        mala_build_gaussian(sc, cur, ch, ch.curr_new_v1, ch.curr_new_v2, cur.gaussian, gradStats);
+        cur.gaussianInitialized = 1;
+    }
+    float offset[Limits<MAXD>::DIM];
+    generate_sample(cur.gaussian, offset, rng);
+    path_copy(prop.path, cur.path);
+    perturb_path_bidir(sc, offset, prop.path, contribs, rng);
+    if (contribs.n > 0) {
+        prop.sp = contribs.c[0];
+        mala_build_gaussian(sc, prop, ch, ch.prop_new_v1, ch.prop_new_v2, prop.gaussian, gradStats);
+        prop.gaussianInitialized = 1;
+        const float py = gaussian_log_pdf(offset, 1.0f, cur.gaussian);
+        const float px = gaussian_log_pdf(offset, -1.0f, prop.gaussian);
+        a = dm_clamp(dm_exp(px - py) * prop.sp.ssScore / cur.sp.ssScore, 0.0f, 1.0f);
+        prop.nSplat = 1;
+        prop.splat[0].screenPos = prop.sp.screenPos;
+        prop.splat[0].contrib = prop.sp.contrib * normalization / prop.sp.lsScore;
+    } else {
+        a = 0.0f;
+    }
+    return a;
+}
+
+// LargeStep::Mutate (largeStepMultiplexed == false)
+template <int MAXD>
+LMC_HD float large_step_mutate(const Scene &sc, float normalization, MarkovState<MAXD> &cur,
+                               MarkovState<MAXD> &prop, Rng &rng, ChainVars<MAXD> &ch) {
+    ch.lastMutationType = MUT_LARGE;
+    float a = 1.0f;
+    ContribList<Limits<MAXD>::MAXC> contribs; contribs.clear();
+    path_clear(prop.path);
+    const int minDepth = sc.opt.minDepth > 3 ? sc.opt.minDepth : 3;
+    generate_path_bidir(sc, minDepth, sc.opt.maxDepth, prop.path, contribs, rng);
+    prop.gaussianInitialized = 0;
+    if (contribs.n > 0) {
+        float cdf[Limits<MAXD>::MAXC + 1];
+        cdf[0] = 0.0f;
+        for (int i = 0; i < contribs.n; i++) cdf[i + 1] = cdf[i] + contribs.c[i].lsScore;
+        const float scoreSum = cdf[contribs.n];
+        const float invSc = inverse(scoreSum);
+        for (int i = 0; i <= contribs.n; i++) cdf[i] *= invSc;
+        const int it = upper_bound_f(cdf, contribs.n + 1, rng_uniform(rng));
+        const int contribId = dm_clampi(it - 1, 0, contribs.n - 1);
+        prop.sp = contribs.c[contribId];
+        prop.scoreSum = scoreSum;
+        if (cur.valid) {
+            const float probProposal = prop.sp.lsScore / prop.scoreSum;
+            const float probLast = ch.lastScore / ch.lastScoreSum;
+            a = dm_clamp((prop.sp.lsScore * probLast) / (cur.sp.lsScore * probProposal), 0.0f, 1.0f);
+        }
+        prop.nSplat = contribs.n;
+        for (int i = 0; i < contribs.n; i++) {
+            prop.splat[i].screenPos = contribs.c[i].screenPos;
+            prop.splat[i].contrib = contribs.c[i].contrib * (normalization / scoreSum);
+        }
+    } else {
+        a = 0.0f;
+    }
+    return a;
+}
+
+struct StepInfo {          // what one iteration did (parity traces / stats)
+    int mutationType;
+    int accepted;
+    float a;
+};
+
+// Per-run constants of the chain loop
+struct RunParams {
+    float normalization;
+    int numChains;
+    long long numSamplesThisChain;   // for the LS_RATIO large-step schedule (src/mlt.cpp:96)
+    const float *initLsScore;        // initStates[i].spContrib.lsScore (outlier reset, src/mlt.cpp:152-158)
+};
+
+// One iteration of the loop at src/mlt.cpp:91-170.  `cur` and `prop` are swapped by index:
+// the caller owns two MarkovState slots and `curIdx` says which one is current.
+template <int MAXD, class FILM>
+LMC_HD StepInfo chain_step(const Scene &sc, const RunParams &rp, int chainId, long long sampleIdx,
+                           MarkovState<MAXD> *states, int &curIdx, ChainVars<MAXD> &ch, Rng &rng, FILM &film,
+                           unsigned int *gradStats) {
+    MarkovState<MAXD> &cur = states[curIdx];
+    MarkovState<MAXD> &prop = states[curIdx ^ 1];
+    float a = 1.0f;
+    bool isLargeStep = false;
+    const float lsScale = ((float)sampleIdx > (float)rp.numSamplesThisChain * sc.opt.lsRatio)
+                              ? sc.opt.largeStepProbScale : 1.0f;
+    if (!cur.valid || rng_uniform(rng) < sc.opt.largeStepProbability * lsScale) {
+        isLargeStep = true;
+        a = large_step_mutate(sc, rp.normalization, cur, prop, rng, ch);
+    } else {
+        if (sc.opt.mala) a = mala_small_step_mutate(sc, rp.normalization, cur, prop, rng, ch, gradStats);
+        else a = small_step_mutate(sc, rp.normalization, cur, prop, rng, ch);
+    }
+    const int W = sc.cam.width, H = sc.cam.height;
+    if (cur.valid && a < 1.0f) {
+        for (int i = 0; i < cur.nSplat; i++) splat(film, W, H, cur.splat[i].screenPos, (1.0f - a) * cur.splat[i].contrib);
+    }
+    if (a > 0.0f) {
+        for (int i = 0; i < prop.nSplat; i++) splat(film, W, H, prop.splat[i].screenPos, a * prop.splat[i].contrib);
+    }
+    StepInfo info; info.mutationType = ch.lastMutationType; info.accepted = 0; info.a = a;
+    if (a > 0.0f && rng_uniform(rng) <= a) {
+        info.accepted = 1;
+        to_subpath(prop.sp.camDepth, prop.sp.lightDepth, prop.path);
+        curIdx ^= 1;
+        MarkovState<MAXD> &ncur = states[curIdx];
+        ncur.valid = 1;
+        ch.adjacentReject = 0;
+        if (isLargeStep) {
+            ch.lastScoreSum = ncur.scoreSum;
+            ch.lastScore = ncur.sp.lsScore;
+            ncur.gaussianInitialized = 0;
+            ch.buffered = 0;
+        } else if (ch.lastMutationType == MUT_MALA_SMALL) {
+            for (int i = 0; i < Limits<MAXD>::DIM; i++) { ch.v1[i] = ch.prop_new_v1[i]; ch.v2[i] = ch.prop_new_v2[i]; }
+            ch.t += 1;
+            ch.buffered = 1;
+            ncur.gaussianInitialized = 1;
+        }
+    } else {
+        ch.adjacentReject += 1;
+        const bool strongReject = cur.sp.lsScore > LMC_OUTLIER_RATIO_THRESHOLD * rp.normalization;
+        if (ch.adjacentReject > LMC_OUTLIER_WEAK_REJECT_CNT ||
+            (strongReject && ch.adjacentReject > LMC_OUTLIER_STRONG_REJECT_CNT)) {
+            int cid = chainId, cnt = 0;
+            for (;;) {
+                cur.sp.lsScore = rp.initLsScore[cid];
+                if (cur.sp.lsScore < LMC_OUTLIER_RATIO_THRESHOLD * rp.normalization) break;
+                cid = (int)(((long long)cid + sampleIdx + (long long)(cnt++)) % (long long)rp.numChains);
+                if (cnt > rp.numChains) break;   // guard: the reference would spin forever
+            }
+            cur.valid = 0; cur.gaussianInitialized = 0; cur.nSplat = 0;
+            prop.valid = 0; prop.gaussianInitialized = 0; prop.nSplat = 0;
+            path_clear(prop.path);
+            ch.buffered = 0;
+        }
+    }
+    return info;
+}
+
+}  // namespace lmc

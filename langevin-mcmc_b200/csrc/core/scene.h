@@ -1,0 +1,154 @@
+// scene.h -- flattened, pointer-based scene view shared by host twin and device kernels.
+//
+// This is the HBM layout of everything the chain kernel reads (DESIGN.md "Data layout"):
+// triangles are stored in BVH order ("tid" = position in that order) so a leaf is a
+// contiguous run and the id a ray query returns indexes every per-triangle array directly.
+// It replaces the reference's pointer graph Scene -> Shape -> TriMeshData / BSDF / Light
+// (src/scene.h:23-45, src/trianglemesh.h:22-31, src/bsdf.h:10-68, src/light.h:14-59).
+#pragma once
+#include "vec.h"
+
+namespace lmc {
+
+enum BsdfType { BSDF_LAMBERTIAN = 0, BSDF_PHONG = 1, BSDF_ROUGHDIELECTRIC = 2 };  // src/bsdf.h:6
+enum LightType { LIGHT_POINT = 0, LIGHT_AREA = 1, LIGHT_ENV = 2 };                // src/light.h:7
+
+// 48 B, read as 3 x float4 during traversal
+struct TriGeom {
+    float p0[3]; int geom;      // geom = shape index (the reference's geomID)
+    float e1[3]; int prim;      // prim = index inside that shape (the reference's primID)
+    float e2[3]; int pad;
+};
+// 64 B, read once per accepted hit
+struct TriShade {
+    float n0[3], n1[3], n2[3];
+    float st0[2], st1[2], st2[2];
+    int pad;
+};
+// 64 B BVH2 node: both child boxes inline.  child >= 0: inner node index;
+// child < 0: leaf, ~child = (first << 3) | (count - 1).
+struct BvhNode {
+    float lmin[3], lmax[3];
+    float rmin[3], rmax[3];
+    int left, right;
+    int pad[2];
+};
+
+struct Material {
+    int type;          // BsdfType
+    int twoSided;
+    int kdTex;         // texture index for Kd (Lambertian/Phong diffuse) or -1
+    int areaLight;     // light index if the shape is an emitter, else -1
+    float Kd[3];
+    float Ks[3];
+    float Kt[3];
+    float exponent;
+    float KsWeight;    // src/phong.cpp:159-169
+    float eta, invEta;
+    float alpha;
+    int hasST;         // mesh has texture coordinates (else st = barycentric uv)
+    float invTotalArea;
+    int firstTid;      // not used by traversal; kept for diagnostics
+};
+
+struct Texture {
+    int width, height;
+    int offset;        // float offset into texData (RGB interleaved)
+    float gamma;       // 2.2 for 8-bit sources, 1 otherwise (src/bitmaptexture.h:136-144)
+    float sScale, tScale;
+};
+
+struct Light {
+    int type;          // LightType
+    float samplingWeight;
+    // area light
+    int geom;          // shape index
+    int numPrims;
+    int primCdfOffset; // offset into lightCdf: numPrims+1 floats (PiecewiseConstant1D cdf)
+    int primTidOffset; // offset into lightPrimTid: numPrims ints (prim -> tid)
+    float emission[3];
+    float invTotalArea;
+    // point light
+    float pos[3];
+};
+
+struct EnvMap {
+    int present;
+    int lightIndex;
+    int width, height;
+    const float *image;      // width*height*3
+    const float *cdfRows;    // height+1
+    const float *cdfCols;    // (width+1)*height
+    const float *rowWeights; // height
+    float normalization;
+    float pixelSize[2];
+    M44 toWorld, toLight;    // static transforms (Interpolate(...) of a non-moving transform)
+    float toWorldSer[15], toLightSer[15];  // AnimatedTransform serialisation (for the reference ABI)
+};
+
+struct Camera {
+    M44 sampleToCam, camToSample;
+    M44 camToWorld, worldToCam;
+    float nearClip, farClip;
+    float dist;
+    int width, height;
+    float camToWorldSer[15];
+};
+
+struct Options {                 // src/dptoptions.h:7-34 + compile-time constants
+    int minDepth, maxDepth;
+    int bidirectional;
+    int h2mc, mala;
+    int numChains;
+    int seedOffset;
+    int useLightCoordinateSampling;
+    int largeStepMultiplexed;
+    int cacheEnabled;            // always 0 here (GlobalCache out of scope)
+    int maxDervDepth;            // 8
+    int pssMinLength, pssMaxLength;   // 2, 12
+    int adjointCompat;           // 1: reproduce the reference's reverse-mode merge semantics
+    float perturbStdDev;         // 0.01
+    float roughnessThreshold;    // 0.05
+    float largeStepProbability;  // 0.05
+    float largeStepProbScale;    // 1 (4 in the shipped LMC xml)
+    float malaGN;                // 100
+    float malaStepsize;          // 0.005
+    float malaStdDev;            // 0.005
+    float discreteStdDev;        // 0.01
+    float uniformMixingProbability;  // 0.1
+    float lsRatio;               // LS_RATIO 0.1
+};
+
+struct Scene {
+    // geometry
+    int numTris, numNodes, numGeoms;
+    const TriGeom *tris;
+    const TriShade *shade;
+    const BvhNode *nodes;
+    const Material *mats;        // per geom
+    // textures
+    int numTextures;
+    const Texture *textures;
+    const float *texData;
+    // lights
+    int numLights;
+    const Light *lights;
+    const float *lightPickCdf;   // numLights+1 (PiecewiseConstant1D over samplingWeight)
+    float lightWeightSum;
+    const float *lightCdf;
+    const int *lightPrimTid;
+    EnvMap env;
+    Camera cam;
+    float bsphereCenter[3];
+    float bsphereRadius;         // already x1000 (src/scene.cpp:40)
+    float sceneSer[38];          // Serialize(scene) for the reference ABI (src/scene.cpp:164-169)
+    Options opt;
+};
+
+#define LMC_ISECT_EPS 5e-4f   // c_IsectEpsilon, src/commondef.h:53
+#define LMC_SHADOW_EPS 5e-4f  // c_ShadowEpsilon, src/commondef.h:54
+#define LMC_COS_EPS 1e-4f     // c_CosEpsilon, src/commondef.h:60
+
+LMC_HD V3 ld3(const float *p) { return mk3(p[0], p[1], p[2]); }
+
+}  // namespace lmc
