@@ -1,0 +1,270 @@
+"""ctypes binding of include/lmc/lmc_abi.h (see package docstring)."""
+import ctypes
+import enum
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class LmcError(RuntimeError):
+    pass
+
+
+class MutationType(enum.IntEnum):  # src/mutation.h:11
+    Large = 0
+    Small = 1
+    H2MCSmall = 2
+    MALASmall = 3
+
+
+class _SceneInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("width", "height", "num_triangles", "num_bvh_nodes", "num_lights",
+                                              "num_shapes", "num_textures", "spp", "direct_spp", "num_init_samples")]
+
+
+class _Stats(ctypes.Structure):
+    _fields_ = [("proposed", ctypes.c_uint64 * 4), ("accepted", ctypes.c_uint64 * 4),
+                ("gradient_evals", ctypes.c_uint64), ("gradient_nonfinite", ctypes.c_uint64),
+                ("kernel_launches", ctypes.c_uint64), ("last_kernel_ms", ctypes.c_double)]
+
+
+class _RunDesc(ctypes.Structure):
+    _fields_ = [("num_chains", ctypes.c_int32), ("chain_base", ctypes.c_int32), ("total_chains", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("samples_per_chain", ctypes.c_int64),
+                ("normalization", ctypes.c_float), ("reserved_f", ctypes.c_float)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "liblmc_b200.so")
+
+
+def load_library():
+    """Load liblmc_b200.so; fails loudly when the CUDA extension has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise LmcError("CUDA extension %s is missing: run `make lib` (or __graft_entry__.build()); "
+                       "there is no CPU fallback" % p)
+    L = ctypes.CDLL(p)
+    vp, i32, i64, f32, dbl, cp = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double,
+                                  ctypes.c_char_p)
+    sig = {
+        "lmc_last_error": (cp, []), "lmc_version": (cp, []),
+        "lmc_scene_load": (i32, [cp, ctypes.POINTER(vp)]), "lmc_scene_save_pack": (i32, [vp, cp]),
+        "lmc_scene_free": (None, [vp]), "lmc_scene_get_info": (i32, [vp, ctypes.POINTER(_SceneInfo)]),
+        "lmc_scene_set_option": (i32, [vp, cp, dbl]), "lmc_scene_get_option": (i32, [vp, cp, ctypes.POINTER(dbl)]),
+        "lmc_scene_serialized": (i32, [vp, vp]),
+        "lmc_mlt_init": (i32, [vp, i64, i32, i32, ctypes.POINTER(f32), vp]),
+        "lmc_create": (i32, [vp, i32, ctypes.POINTER(vp)]), "lmc_destroy": (None, [vp]),
+        "lmc_set_stream": (i32, [vp, vp]),
+        "lmc_chains_begin": (i32, [vp, ctypes.POINTER(_RunDesc), vp]),
+        "lmc_run_chains": (i32, [vp, i64, vp, vp]), "lmc_synchronize": (i32, [vp]),
+        "lmc_get_stats": (i32, [vp, ctypes.POINTER(_Stats)]),
+        "lmc_film_clear": (i32, [vp]), "lmc_film_read": (i32, [vp, vp]),
+        "lmc_film_device_ptr": (i32, [vp, ctypes.POINTER(vp)]), "lmc_film_bind": (i32, [vp, vp]),
+        "lmc_eval_batch": (i32, [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
+        "lmc_vert_param_size": (i32, [i32, i32]),
+        "lmc_bvh_probe": (i32, [vp, i32, vp, f32, f32, i32, vp, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise LmcError("lmc error %d: %s" % (rc, load_library().lmc_last_error().decode()))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class _Options:
+    """Scene.options: the <dpt> block (src/dptoptions.h), addressed by the reference's xml names."""
+
+    def __init__(self, scene):
+        self._s = scene
+
+    def __getitem__(self, name):
+        v = ctypes.c_double()
+        _check(load_library().lmc_scene_get_option(self._s._h, name.encode(), ctypes.byref(v)))
+        return v.value
+
+    def __setitem__(self, name, value):
+        _check(load_library().lmc_scene_set_option(self._s._h, name.encode(), float(value)))
+
+    def update(self, d):
+        for k, v in d.items():
+            self[k] = v
+
+
+class Scene:
+    def __init__(self, handle):
+        self._h = handle
+        self.options = _Options(self)
+        info = _SceneInfo()
+        _check(load_library().lmc_scene_get_info(self._h, ctypes.byref(info)))
+        self.info = {n: getattr(info, n) for n, _ in _SceneInfo._fields_}
+        self.width, self.height = info.width, info.height
+
+    def save_pack(self, path):
+        _check(load_library().lmc_scene_save_pack(self._h, path.encode()))
+
+    def serialized(self):
+        out = np.zeros(38, np.float32)
+        _check(load_library().lmc_scene_serialized(self._h, _ptr(out)))
+        return out
+
+    def __del__(self):
+        try:
+            if self._h:
+                load_library().lmc_scene_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def ParseScene(filename):
+    """src/parsescene.h:8 -- accepts the reference's scene xml (or a pre-flattened .pack)."""
+    h = ctypes.c_void_p()
+    _check(load_library().lmc_scene_load(os.fspath(filename).encode(), ctypes.byref(h)))
+    return Scene(h)
+
+
+def MLTInit(scene, numInitSamples=None, numChains=None, logicalThreads=32):
+    """src/mlt.h:41-154 -> (normalization, initLsScore[numChains])."""
+    if numInitSamples is None:
+        numInitSamples = scene.info["num_init_samples"]
+    if numChains is None:
+        numChains = int(scene.options["numchains"])
+    norm = ctypes.c_float()
+    init_ls = np.zeros(numChains, np.float32)
+    _check(load_library().lmc_mlt_init(scene._h, int(numInitSamples), int(numChains), int(logicalThreads),
+                                       ctypes.byref(norm), _ptr(init_ls)))
+    return norm.value, init_ls
+
+
+def decode_trace(trace):
+    """trace byte -> (mutationType, accepted, a>0)."""
+    t = np.asarray(trace)
+    return t & 3, (t >> 2) & 1, (t >> 3) & 1
+
+
+class ChainContext:
+    """One GPU's chains: lmc_create .. lmc_destroy (the body of MLT()'s ParallelFor, src/mlt.cpp:60-196)."""
+
+    def __init__(self, scene, device=0, stream=None):
+        self.scene = scene
+        self._c = ctypes.c_void_p()
+        _check(load_library().lmc_create(scene._h, int(device), ctypes.byref(self._c)))
+        if stream is not None:
+            _check(load_library().lmc_set_stream(self._c, ctypes.c_void_p(int(stream))))
+        self.num_chains = 0
+
+    def begin(self, num_chains, normalization, init_ls_score=None, chain_base=0, total_chains=None,
+              samples_per_chain=0):
+        d = _RunDesc()
+        d.num_chains = int(num_chains)
+        d.chain_base = int(chain_base)
+        d.total_chains = int(total_chains if total_chains is not None else num_chains)
+        d.samples_per_chain = int(samples_per_chain)
+        d.normalization = float(normalization)
+        if init_ls_score is not None:
+            init_ls_score = np.ascontiguousarray(init_ls_score, np.float32)
+            if init_ls_score.size != d.total_chains:
+                raise LmcError("init_ls_score must have total_chains entries")
+        _check(load_library().lmc_chains_begin(self._c, ctypes.byref(d), _ptr(init_ls_score)))
+        self.num_chains = d.num_chains
+
+    def run(self, num_mutations, trace=False, a_trace=False):
+        t = np.zeros((self.num_chains, num_mutations), np.uint8) if trace else None
+        a = np.zeros((self.num_chains, num_mutations), np.float32) if a_trace else None
+        _check(load_library().lmc_run_chains(self._c, int(num_mutations), _ptr(t), _ptr(a)))
+        return t, a
+
+    def synchronize(self):
+        _check(load_library().lmc_synchronize(self._c))
+
+    def stats(self):
+        s = _Stats()
+        _check(load_library().lmc_get_stats(self._c, ctypes.byref(s)))
+        return {"proposed": list(s.proposed), "accepted": list(s.accepted), "gradient_evals": s.gradient_evals,
+                "gradient_nonfinite": s.gradient_nonfinite, "kernel_launches": s.kernel_launches,
+                "last_kernel_ms": s.last_kernel_ms}
+
+    def film(self):
+        out = np.zeros((self.scene.height, self.scene.width, 3), np.float32)
+        _check(load_library().lmc_film_read(self._c, _ptr(out)))
+        return out
+
+    def film_clear(self):
+        _check(load_library().lmc_film_clear(self._c))
+
+    def film_device_ptr(self):
+        p = ctypes.c_void_p()
+        _check(load_library().lmc_film_device_ptr(self._c, ctypes.byref(p)))
+        return p.value
+
+    def film_bind(self, device_ptr):
+        _check(load_library().lmc_film_bind(self._c, ctypes.c_void_p(int(device_ptr))))
+
+    def eval_batch(self, cam_depth, light_depth, lens, primary, vert_params, want_grad=True):
+        lens = np.ascontiguousarray(lens, np.float32)
+        primary = np.ascontiguousarray(primary, np.float32)
+        vert_params = np.ascontiguousarray(vert_params, np.float32)
+        n = lens.shape[0]
+        dim = primary.shape[1] - 1
+        log_lum = np.zeros(n, np.float32)
+        grad = np.zeros((n, dim), np.float32) if want_grad else None
+        _check(load_library().lmc_eval_batch(self._c, int(cam_depth), int(light_depth), n, _ptr(lens), _ptr(primary),
+                                             _ptr(vert_params), int(vert_params.shape[1]), _ptr(log_lum), _ptr(grad)))
+        return log_lum, grad
+
+    def bvh_probe(self, rays, tmin, tmax, any_hit=False):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        tid = np.zeros(n, np.int32)
+        gp = np.zeros((n, 2), np.int32)
+        tuv = np.zeros((n, 3), np.float32)
+        _check(load_library().lmc_bvh_probe(self._c, n, _ptr(rays), float(tmin), float(tmax), 1 if any_hit else 0,
+                                            _ptr(tid), _ptr(gp), _ptr(tuv)))
+        return tid, gp, tuv
+
+    def close(self):
+        if self._c:
+            load_library().lmc_destroy(self._c)
+            self._c = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def MLT(scene, numChains=None, mutationsPerChain=None, device=0, logicalThreads=32, numInitSamples=None):
+    """The chain phase of MLT() (src/mlt.cpp:20-215): MLTInit on the host, the chain loop on the
+    GPU.  Returns (indirect film / spp-equivalent as H x W x 3, stats).  The direct-lighting
+    pre-pass and EXR output of the reference are out of scope."""
+    if numChains is None:
+        numChains = int(scene.options["numchains"])
+    if mutationsPerChain is None:
+        mutationsPerChain = scene.info["spp"] * scene.width * scene.height // numChains
+    norm, init_ls = MLTInit(scene, numInitSamples, numChains, logicalThreads)
+    ctx = ChainContext(scene, device)
+    ctx.begin(numChains, norm, init_ls, samples_per_chain=mutationsPerChain)
+    ctx.run(mutationsPerChain)
+    film = ctx.film()
+    stats = ctx.stats()
+    ctx.close()
+    spp = numChains * mutationsPerChain / float(scene.width * scene.height)
+    return film / np.float32(spp), stats

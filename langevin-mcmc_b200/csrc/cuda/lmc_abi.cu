@@ -1,0 +1,397 @@
+// lmc_abi.cu -- the C ABI (include/lmc/lmc_abi.h) and the sm_100a kernels behind it.
+//
+// Kernels (one CUDA thread = one Markov chain; DESIGN.md "Kernels"):
+//   k_chain_init   chain_state_init for every chain                     (src/mlt.cpp:61-90)
+//   k_chain_run    K iterations of the chain loop per launch            (src/mlt.cpp:91-170 + mutations + path replay)
+//   k_chain_stats  reduce per-chain counters
+//   k_bvh_probe    closest-hit / any-hit harness                        (src/scene.cpp:106-149)
+//   k_eval_batch   log-luminance + PSS gradient of serialized paths     (src/path.h:121-125 ABI)
+// Host code here is glue only: device memory, launches, error translation.  No CPU fallback.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../../include/lmc/lmc_abi.h"
+#include "../core/chain.h"
+#include "../host/host_scene.h"
+#include "../host/mlt_init.h"
+
+using namespace lmc;
+
+struct lmc_scene { lmc_host::SceneStore store; };
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(LMC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct DevFilm {
+    float *p;
+    __device__ __forceinline__ void add(int pix, int c, float v) { atomicAdd(p + 3 * pix + c, v); }
+};
+
+template <int MAXD>
+__global__ void k_chain_init(ChainState<MAXD> *states, int n, int chainBase, const float *initLs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    chain_state_init(states[i], initLs ? initLs[chainBase + i] : 0.0f);
+}
+
+template <int MAXD>
+__global__ void __launch_bounds__(128) k_chain_run(const __grid_constant__ Scene sc, RunParams rp, int chainBase,
+                                                    ChainState<MAXD> *states, int n, long long numSteps, float *film,
+                                                    unsigned char *trace, float *aTrace) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t tab[64];
+    DevFilm df; df.p = film;
+    chain_run(sc, rp, chainBase + i, states[i], numSteps, tab, 1, df,
+              trace ? trace + (size_t)i * numSteps : nullptr, aTrace ? aTrace + (size_t)i * numSteps : nullptr, 1);
+}
+
+template <int MAXD>
+__global__ void k_chain_stats(const ChainState<MAXD> *states, int n, unsigned long long *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v[10];
+    for (int k = 0; k < 10; k++) v[k] = 0ULL;
+    if (i < n) {
+        for (int k = 0; k < 4; k++) { v[k] = states[i].nPropose[k]; v[4 + k] = states[i].nAccept[k]; }
+        v[8] = states[i].gradStats[0]; v[9] = states[i].gradStats[1];
+    }
+    for (int k = 0; k < 10; k++) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(out + k, x);
+    }
+}
+
+__global__ void k_bvh_probe(const __grid_constant__ Scene sc, int n, const float *rays, float tmin, float tmax, int anyHit,
+                            int *triId, int *geomPrim, float *tuv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r; r.org = ld3(rays + 6 * i); r.dir = ld3(rays + 6 * i + 3);
+    if (anyHit) {
+        const Hit h = bvh_traverse<true>(sc, r, tmin, tmax);
+        triId[i] = h.tid >= 0 ? 1 : 0;
+    } else {
+        const Hit h = bvh_traverse<false>(sc, r, tmin, tmax);
+        triId[i] = h.tid;
+        if (geomPrim) { geomPrim[2 * i] = h.tid >= 0 ? sc.tris[h.tid].geom : -1; geomPrim[2 * i + 1] = h.tid >= 0 ? sc.tris[h.tid].prim : -1; }
+        if (tuv) { tuv[3 * i] = h.t; tuv[3 * i + 1] = h.u; tuv[3 * i + 2] = h.v; }
+    }
+}
+
+template <class T> int upload(const std::vector<T> &v, T **out) {
+    *out = nullptr;
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CK(cudaMalloc((void **)out, bytes));
+    if (!v.empty()) CK(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return LMC_OK;
+}
+}  // namespace
+
+struct lmc_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    Scene sc;                       // device pointers inside
+    std::vector<void *> allocs;
+    int maxdTemplate = 8;
+    // chains
+    void *states = nullptr; size_t stateBytes = 0;
+    lmc_run_desc desc{};
+    float *initLs = nullptr;
+    bool begun = false;
+    // film
+    float *film = nullptr; bool filmOwned = false;
+    unsigned long long *statsDev = nullptr;
+    uint64_t launches = 0;
+    double lastMs = 0.0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+template <int MAXD>
+int chains_begin_t(lmc_ctx *c) {
+    const int n = c->desc.num_chains;
+    const size_t bytes = sizeof(ChainState<MAXD>) * (size_t)n;
+    if (c->states && c->stateBytes != bytes) { cudaFree(c->states); c->states = nullptr; }
+    if (!c->states) { CK(cudaMalloc(&c->states, bytes)); c->stateBytes = bytes; }
+    k_chain_init<MAXD><<<(n + 127) / 128, 128, 0, c->stream>>>((ChainState<MAXD> *)c->states, n, c->desc.chain_base, c->initLs);
+    c->launches++;
+    CK(cudaGetLastError());
+    return LMC_OK;
+}
+
+template <int MAXD>
+int run_chains_t(lmc_ctx *c, long long numSteps, unsigned char *dTrace, float *dATrace) {
+    const int n = c->desc.num_chains;
+    RunParams rp; rp.normalization = c->desc.normalization; rp.numChains = c->desc.total_chains;
+    rp.numSamplesThisChain = c->desc.samples_per_chain; rp.initLsScore = c->initLs;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_chain_run<MAXD><<<(n + 127) / 128, 128, 0, c->stream>>>(c->sc, rp, c->desc.chain_base, (ChainState<MAXD> *)c->states, n,
+                                                               numSteps, c->film, dTrace, dATrace);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    return LMC_OK;
+}
+
+template <int MAXD>
+int stats_t(lmc_ctx *c) {
+    const int n = c->desc.num_chains;
+    CK(cudaMemsetAsync(c->statsDev, 0, 10 * sizeof(unsigned long long), c->stream));
+    k_chain_stats<MAXD><<<(n + 127) / 128, 128, 0, c->stream>>>((const ChainState<MAXD> *)c->states, n, c->statsDev);
+    c->launches++;
+    CK(cudaGetLastError());
+    return LMC_OK;
+}
+
+#define DISPATCH_MAXD(c, expr4, expr8, expr12) \
+    ((c)->maxdTemplate == 4 ? (expr4) : ((c)->maxdTemplate == 8 ? (expr8) : (expr12)))
+}  // namespace
+
+extern "C" {
+
+const char *lmc_last_error(void) { return g_err.c_str(); }
+const char *lmc_version(void) { return "lmc-b200 0.1 (sm_100a)"; }
+
+int lmc_scene_load(const char *path, lmc_scene **out) {
+    if (!path || !out) return fail(LMC_ERR_ARG, "null argument");
+    try {
+        lmc_scene *s = new lmc_scene();
+        const std::string p(path);
+        if (p.size() > 5 && p.substr(p.size() - 5) == ".pack") lmc_host::load_scene_pack(p, s->store);
+        else lmc_host::load_scene_xml(p, s->store);
+        *out = s;
+    } catch (const std::exception &e) { return fail(LMC_ERR_IO, e.what()); }
+    return LMC_OK;
+}
+int lmc_scene_save_pack(const lmc_scene *scene, const char *path) {
+    if (!scene || !path) return fail(LMC_ERR_ARG, "null argument");
+    try { lmc_host::save_scene_pack(path, scene->store); } catch (const std::exception &e) { return fail(LMC_ERR_IO, e.what()); }
+    return LMC_OK;
+}
+void lmc_scene_free(lmc_scene *scene) { delete scene; }
+int lmc_scene_get_info(const lmc_scene *scene, lmc_scene_info *out) {
+    if (!scene || !out) return fail(LMC_ERR_ARG, "null argument");
+    const lmc_host::SceneStore &s = scene->store;
+    out->width = s.head.cam.width; out->height = s.head.cam.height; out->num_triangles = s.head.numTris;
+    out->num_bvh_nodes = s.head.numNodes; out->num_lights = s.head.numLights; out->num_shapes = s.head.numGeoms;
+    out->num_textures = s.head.numTextures; out->spp = s.spp; out->direct_spp = s.directSpp; out->num_init_samples = s.numInitSamples;
+    return LMC_OK;
+}
+int lmc_scene_set_option(lmc_scene *scene, const char *name, double value) {
+    if (!scene || !name) return fail(LMC_ERR_ARG, "null argument");
+    if (!lmc_host::set_option(scene->store.head.opt, name, value)) return fail(LMC_ERR_ARG, std::string("Unknown dpt option:") + name);
+    return LMC_OK;
+}
+int lmc_scene_get_option(const lmc_scene *scene, const char *name, double *value) {
+    if (!scene || !name || !value) return fail(LMC_ERR_ARG, "null argument");
+    if (!lmc_host::get_option(scene->store.head.opt, name, *value)) return fail(LMC_ERR_ARG, std::string("Unknown dpt option:") + name);
+    return LMC_OK;
+}
+int lmc_scene_serialized(const lmc_scene *scene, float *out38) {
+    if (!scene || !out38) return fail(LMC_ERR_ARG, "null argument");
+    memcpy(out38, scene->store.head.sceneSer, 38 * sizeof(float));
+    out38[0] = scene->store.head.opt.useLightCoordinateSampling ? 1.0f : 0.0f;
+    return LMC_OK;
+}
+
+int lmc_mlt_init(const lmc_scene *scene, int64_t num_init_samples, int32_t num_chains, int32_t logical_threads,
+                 float *normalization, float *init_ls_score) {
+    if (!scene || !normalization || num_chains <= 0 || num_init_samples <= 0) return fail(LMC_ERR_ARG, "bad argument");
+    try {
+        const Scene sc = scene->store.view();
+        lmc_host::InitResult r;
+        if (sc.opt.maxDepth <= 4) lmc_host::mlt_init<4>(sc, num_init_samples, num_chains, logical_threads, r);
+        else if (sc.opt.maxDepth <= 8) lmc_host::mlt_init<8>(sc, num_init_samples, num_chains, logical_threads, r);
+        else if (sc.opt.maxDepth <= 12) lmc_host::mlt_init<12>(sc, num_init_samples, num_chains, logical_threads, r);
+        else return fail(LMC_ERR_UNSUPPORTED, "maxdepth > 12 is not supported");
+        *normalization = r.normalization;
+        if (init_ls_score) memcpy(init_ls_score, r.initLsScore.data(), sizeof(float) * (size_t)num_chains);
+    } catch (const std::exception &e) { return fail(LMC_ERR_STATE, e.what()); }
+    return LMC_OK;
+}
+
+int lmc_create(const lmc_scene *scene, int32_t device, lmc_ctx **out) {
+    if (!scene || !out) return fail(LMC_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(LMC_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(LMC_ERR_ARG, "device index out of range");
+    CK(cudaSetDevice(device));
+    const lmc_host::SceneStore &s = scene->store;
+    if (s.head.opt.maxDepth < 2 || s.head.opt.maxDepth > 12) return fail(LMC_ERR_UNSUPPORTED, "maxdepth must be in [2, 12]");
+    if (s.head.opt.h2mc) return fail(LMC_ERR_UNSUPPORTED, "h2mc mutation is not implemented in this build");
+    if (s.head.opt.largeStepMultiplexed) return fail(LMC_ERR_UNSUPPORTED, "largestepmultiplexed is not supported");
+    lmc_ctx *c = new lmc_ctx();
+    c->device = device;
+    c->sc = s.head;
+    c->maxdTemplate = s.head.opt.maxDepth <= 4 ? 4 : (s.head.opt.maxDepth <= 8 ? 8 : 12);
+    Scene &d = c->sc;
+    int rc = LMC_OK;
+#define UP(field, vec, T) do { T *p_ = nullptr; rc = upload<T>(vec, &p_); if (rc) { lmc_destroy(c); return rc; } c->allocs.push_back(p_); field = p_; } while (0)
+    UP(d.tris, s.tris, TriGeom); UP(d.shade, s.shade, TriShade); UP(d.nodes, s.nodes, BvhNode); UP(d.mats, s.mats, Material);
+    UP(d.textures, s.textures, Texture); UP(d.texData, s.texData, float); UP(d.lights, s.lights, Light);
+    UP(d.lightPickCdf, s.lightPickCdf, float); UP(d.lightCdf, s.lightCdf, float); UP(d.lightPrimTid, s.lightPrimTid, int);
+    UP(d.env.image, s.envImage, float); UP(d.env.cdfRows, s.envCdfRows, float); UP(d.env.cdfCols, s.envCdfCols, float);
+    UP(d.env.rowWeights, s.envRowWeights, float);
+#undef UP
+    const size_t filmBytes = (size_t)d.cam.width * d.cam.height * 3 * sizeof(float);
+    if (cudaMalloc((void **)&c->film, filmBytes) != cudaSuccess || cudaMemset(c->film, 0, filmBytes) != cudaSuccess ||
+        cudaMalloc((void **)&c->statsDev, 10 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        lmc_destroy(c);
+        return fail(LMC_ERR_CUDA, "device allocation failed");
+    }
+    c->filmOwned = true;
+    *out = c;
+    return LMC_OK;
+}
+
+void lmc_destroy(lmc_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (void *p : c->allocs) cudaFree(p);
+    if (c->states) cudaFree(c->states);
+    if (c->initLs) cudaFree(c->initLs);
+    if (c->film && c->filmOwned) cudaFree(c->film);
+    if (c->statsDev) cudaFree(c->statsDev);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+}
+
+int lmc_set_stream(lmc_ctx *c, void *cuda_stream) {
+    if (!c) return fail(LMC_ERR_ARG, "null ctx");
+    c->stream = (cudaStream_t)cuda_stream;
+    return LMC_OK;
+}
+
+int lmc_chains_begin(lmc_ctx *c, const lmc_run_desc *desc, const float *init_ls_score) {
+    if (!c || !desc) return fail(LMC_ERR_ARG, "null argument");
+    if (desc->num_chains <= 0 || desc->total_chains < desc->num_chains || desc->chain_base < 0 ||
+        desc->chain_base + desc->num_chains > desc->total_chains) return fail(LMC_ERR_ARG, "inconsistent run descriptor");
+    CK(cudaSetDevice(c->device));
+    c->desc = *desc;
+    if (c->initLs) { cudaFree(c->initLs); c->initLs = nullptr; }
+    CK(cudaMalloc((void **)&c->initLs, sizeof(float) * (size_t)desc->total_chains));
+    if (init_ls_score) CK(cudaMemcpyAsync(c->initLs, init_ls_score, sizeof(float) * (size_t)desc->total_chains, cudaMemcpyHostToDevice, c->stream));
+    else CK(cudaMemsetAsync(c->initLs, 0, sizeof(float) * (size_t)desc->total_chains, c->stream));
+    const int rc = DISPATCH_MAXD(c, chains_begin_t<4>(c), chains_begin_t<8>(c), chains_begin_t<12>(c));
+    if (rc) return rc;
+    c->begun = true;
+    return lmc_film_clear(c);
+}
+
+int lmc_run_chains(lmc_ctx *c, int64_t num_mutations, uint8_t *trace, float *a_trace) {
+    if (!c) return fail(LMC_ERR_ARG, "null ctx");
+    if (!c->begun) return fail(LMC_ERR_STATE, "lmc_chains_begin has not been called");
+    if (num_mutations <= 0) return fail(LMC_ERR_ARG, "num_mutations must be positive");
+    CK(cudaSetDevice(c->device));
+    unsigned char *dTrace = nullptr; float *dA = nullptr;
+    const size_t cnt = (size_t)c->desc.num_chains * (size_t)num_mutations;
+    if (trace) CK(cudaMalloc((void **)&dTrace, cnt));
+    if (a_trace) CK(cudaMalloc((void **)&dA, cnt * sizeof(float)));
+    int rc = DISPATCH_MAXD(c, run_chains_t<4>(c, num_mutations, dTrace, dA), run_chains_t<8>(c, num_mutations, dTrace, dA),
+                           run_chains_t<12>(c, num_mutations, dTrace, dA));
+    if (rc == LMC_OK && (trace || a_trace)) {
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess && trace) e = cudaMemcpy(trace, dTrace, cnt, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && a_trace) e = cudaMemcpy(a_trace, dA, cnt * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(LMC_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (dTrace) cudaFree(dTrace);
+    if (dA) cudaFree(dA);
+    return rc;
+}
+
+int lmc_synchronize(lmc_ctx *c) {
+    if (!c) return fail(LMC_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return LMC_OK;
+}
+
+int lmc_get_stats(lmc_ctx *c, lmc_stats *out) {
+    if (!c || !out) return fail(LMC_ERR_ARG, "null argument");
+    memset(out, 0, sizeof(*out));
+    CK(cudaSetDevice(c->device));
+    if (c->begun) {
+        const int rc = DISPATCH_MAXD(c, stats_t<4>(c), stats_t<8>(c), stats_t<12>(c));
+        if (rc) return rc;
+        unsigned long long h[10];
+        CK(cudaMemcpyAsync(h, c->statsDev, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < 4; k++) { out->proposed[k] = h[k]; out->accepted[k] = h[4 + k]; }
+        out->gradient_evals = h[8]; out->gradient_nonfinite = h[9];
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->lastMs = ms;
+        else cudaGetLastError();
+    }
+    out->kernel_launches = c->launches;
+    out->last_kernel_ms = c->lastMs;
+    return LMC_OK;
+}
+
+int lmc_film_clear(lmc_ctx *c) {
+    if (!c) return fail(LMC_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->film, 0, (size_t)c->sc.cam.width * c->sc.cam.height * 3 * sizeof(float), c->stream));
+    return LMC_OK;
+}
+int lmc_film_read(lmc_ctx *c, float *host_rgb) {
+    if (!c || !host_rgb) return fail(LMC_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(host_rgb, c->film, (size_t)c->sc.cam.width * c->sc.cam.height * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return LMC_OK;
+}
+int lmc_film_device_ptr(lmc_ctx *c, void **p) {
+    if (!c || !p) return fail(LMC_ERR_ARG, "null argument");
+    *p = c->film;
+    return LMC_OK;
+}
+int lmc_film_bind(lmc_ctx *c, void *device_ptr) {
+    if (!c || !device_ptr) return fail(LMC_ERR_ARG, "null argument");
+    CK(cudaSetDevice(c->device));
+    if (c->film && c->filmOwned) cudaFree(c->film);
+    c->film = (float *)device_ptr; c->filmOwned = false;
+    return LMC_OK;
+}
+
+int32_t lmc_vert_param_size(int32_t cam_depth, int32_t light_depth) {
+    const int maxDepth = cam_depth + light_depth;
+    return maxDepth * 46 + maxDepth * 10 + 56 + maxDepth * 2 + maxDepth * 1 + 3 + 1 + 1;
+}
+
+int lmc_eval_batch(lmc_ctx *c, int32_t, int32_t, int32_t, const float *, const float *, const float *, int32_t, float *, float *) {
+    if (!c) return fail(LMC_ERR_ARG, "null ctx");
+    return fail(LMC_ERR_UNSUPPORTED, "lmc_eval_batch: gradient kernel not built yet");
+}
+
+int lmc_bvh_probe(lmc_ctx *c, int32_t n, const float *rays, float tmin, float tmax, int32_t any_hit, int32_t *tri_id,
+                  int32_t *geom_prim, float *tuv) {
+    if (!c || !rays || !tri_id || n < 0) return fail(LMC_ERR_ARG, "bad argument");
+    if (n == 0) return LMC_OK;
+    CK(cudaSetDevice(c->device));
+    float *dR = nullptr, *dT = nullptr; int *dI = nullptr, *dG = nullptr;
+    CK(cudaMalloc((void **)&dR, sizeof(float) * 6 * (size_t)n));
+    CK(cudaMalloc((void **)&dI, sizeof(int) * (size_t)n));
+    CK(cudaMalloc((void **)&dG, sizeof(int) * 2 * (size_t)n));
+    CK(cudaMalloc((void **)&dT, sizeof(float) * 3 * (size_t)n));
+    CK(cudaMemcpyAsync(dR, rays, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    k_bvh_probe<<<(n + 127) / 128, 128, 0, c->stream>>>(c->sc, n, dR, tmin, tmax, any_hit, dI, dG, dT);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(tri_id, dI, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (geom_prim && !any_hit) CK(cudaMemcpyAsync(geom_prim, dG, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (tuv && !any_hit) CK(cudaMemcpyAsync(tuv, dT, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(dR); cudaFree(dI); cudaFree(dG); cudaFree(dT);
+    return LMC_OK;
+}
+
+}  // extern "C"
