@@ -21,7 +21,7 @@ LMC_HD int imod(int a, int b) { const int r = a % b; return (r < 0) ? r + b : r;
 // Bilinear, periodic wrap, texel centres at (i + 0.5)/W; then the reference's
 // fastpow(max(v, 0), gamma) (src/bitmaptexture.h:93-96).  OIIO's own filter is unpinned
 // (SURVEY.md App. B#9); this is the restatement's definition.
-LMC_HD V3 texture_eval(const Scene &sc, int texId, V2 st) {
+LMC_HD_NOINLINE V3 texture_eval(const Scene &sc, int texId, V2 st) {
     const Texture &tx = sc.textures[texId];
     const float s = tx.sScale * st.x, t = tx.tScale * st.y;
     const float x = s * (float)tx.width - 0.5f, y = t * (float)tx.height - 0.5f;
@@ -396,13 +396,13 @@ LMC_HD bool roughdielectric_sample(bool adjoint, const BsdfParams &p, V3 wi, V3 
 }
 
 // ---- dispatch (replaces the virtual calls of src/bsdf.h:10-68) ------------------------------
-LMC_HD void bsdf_eval(bool adjoint, const BsdfParams &p, V3 wi, V3 normal, V3 wo,
+LMC_HD_NOINLINE void bsdf_eval(bool adjoint, const BsdfParams &p, V3 wi, V3 normal, V3 wo,
                       V3 &contrib, float &cosWo, float &pdf, float &revPdf) {
     if (p.type == BSDF_LAMBERTIAN) lambertian_eval(p, wi, normal, wo, contrib, cosWo, pdf, revPdf);
     else if (p.type == BSDF_PHONG) phong_eval(p, wi, normal, wo, contrib, cosWo, pdf, revPdf);
     else roughdielectric_eval(adjoint, p, wi, normal, wo, contrib, cosWo, pdf, revPdf);
 }
-LMC_HD bool bsdf_sample(bool adjoint, const BsdfParams &p, V3 wi, V3 normal, V2 rnd, float uDiscrete,
+LMC_HD_NOINLINE bool bsdf_sample(bool adjoint, const BsdfParams &p, V3 wi, V3 normal, V2 rnd, float uDiscrete,
                         V3 &wo, V3 &contrib, float &cosWo, float &pdf, float &revPdf) {
     if (p.type == BSDF_LAMBERTIAN) return lambertian_sample(p, wi, normal, rnd, wo, contrib, cosWo, pdf, revPdf);
     if (p.type == BSDF_PHONG) return phong_sample(p, wi, normal, rnd, wo, contrib, cosWo, pdf, revPdf);

@@ -52,7 +52,7 @@ LMC_HD bool box_test(const float *bmin, const float *bmax, const V3 &org, const 
 #define LMC_BVH_STACK 48
 
 template <bool ANY_HIT>
-LMC_HD Hit bvh_traverse(const Scene &sc, const Ray &ray, float minT, float maxT) {
+LMC_HD_NOINLINE Hit bvh_traverse(const Scene &sc, const Ray &ray, float minT, float maxT) {
     Hit best; best.tid = -1; best.t = maxT; best.u = 0.0f; best.v = 0.0f;
     if (sc.numNodes == 0) return best;
     const V3 invDir = mk3(inverse(ray.dir.x), inverse(ray.dir.y), inverse(ray.dir.z));

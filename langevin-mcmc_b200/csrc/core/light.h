@@ -133,7 +133,7 @@ LMC_HD int light_prim_tid(const Scene &sc, const Light &l, int lPrimID) {
 }
 
 // Light::SampleDirect
-LMC_HD bool light_sample_direct(const Scene &sc, int lightId, V3 pos, V2 rnd, int &lPrimID,
+LMC_HD_NOINLINE bool light_sample_direct(const Scene &sc, int lightId, V3 pos, V2 rnd, int &lPrimID,
                                 V3 &dirToLight, float &dist, V3 &contrib, float &cosAtLight,
                                 float &directPdf, float &emissionPdf) {
     const Light &l = sc.lights[lightId];
@@ -177,7 +177,7 @@ LMC_HD bool light_sample_direct(const Scene &sc, int lightId, V3 pos, V2 rnd, in
 }
 
 // Light::Emission (env: src/envlight.cpp:195-226; area: src/arealight.cpp:62-79)
-LMC_HD void light_emission(const Scene &sc, int lightId, V3 dirToLight, V3 normalOnLight, int &lPrimID,
+LMC_HD_NOINLINE void light_emission(const Scene &sc, int lightId, V3 dirToLight, V3 normalOnLight, int &lPrimID,
                            V3 &emission, float &directPdf, float &emissionPdf) {
     const Light &l = sc.lights[lightId];
     if (l.type == LIGHT_ENV) {
@@ -214,7 +214,7 @@ LMC_HD void light_emission(const Scene &sc, int lightId, V3 dirToLight, V3 norma
 }
 
 // Light::Emit (env: src/envlight.cpp:228-248; area: src/arealight.cpp:81-104; point: src/pointlight.cpp:58-72)
-LMC_HD void light_emit(const Scene &sc, int lightId, V2 rndPos, V2 rndDir, int &lPrimID, Ray &ray,
+LMC_HD_NOINLINE void light_emit(const Scene &sc, int lightId, V2 rndPos, V2 rndDir, int &lPrimID, Ray &ray,
                        V3 &emission, float &cosAtLight, float &emissionPdf, float &directPdf) {
     const Light &l = sc.lights[lightId];
     if (l.type == LIGHT_ENV) {

@@ -14,7 +14,7 @@
 // false, so every eligible MALA step evaluates a gradient.
 #pragma once
 #include "path.h"
-#include "pathgrad.h"
+#include "serialize.h"
 
 namespace lmc {
 

@@ -412,7 +412,7 @@ LMC_HD int get_hit_light(const Scene &sc, bool hitSurface, int tid) {
 
 // GeneratePathBidir(scene, (-1,-1), minDepth, maxDepth, path, contribs, rng)
 template <int MAXD, class CL>
-LMC_HD void generate_path_bidir(const Scene &sc, int minDepth, int maxDepth, Path<MAXD> &path,
+LMC_HD_NOINLINE void generate_path_bidir(const Scene &sc, int minDepth, int maxDepth, Path<MAXD> &path,
                                 CL &contribs, Rng &rng) {
     path.time = rng_uniform(rng);
     BidirPathState lightStates[MAXD];
@@ -511,7 +511,7 @@ LMC_HD void perturb(float &value, const float *offset, int &offsetId) {
 
 // PerturbPathBidir(scene, offset, path, contribs, rng): contribs gets 0 or 1 entries.
 template <int MAXD, class CL>
-LMC_HD void perturb_path_bidir(const Scene &sc, const float *offset, Path<MAXD> &path, CL &contribs, Rng &rng) {
+LMC_HD_NOINLINE void perturb_path_bidir(const Scene &sc, const float *offset, Path<MAXD> &path, CL &contribs, Rng &rng) {
     NormalDist normDist = normal_make(0.0f, sc.opt.discreteStdDev);
     int offsetId = 0;
     path.time = modulo1(path.time + normal_draw(normDist, rng));

@@ -83,6 +83,16 @@ __global__ void k_bvh_probe(const __grid_constant__ Scene sc, int n, const float
     }
 }
 
+// one thread = one serialized path (reference ABI: PathFunc / PathFuncDerv, src/path.h:121-125)
+__global__ void k_eval_batch(int camDepth, int lightDepth, int n, const float *sceneSer, const float *primary, int primaryStride,
+                             const float *vertParams, int vertStride, float *logLum, float *grad, int dim) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = primary + (size_t)i * primaryStride, *v = vertParams + (size_t)i * vertStride;
+    if (grad) logLum[i] = path_loglum_grad(camDepth, lightDepth, sceneSer, p, v, grad + (size_t)i * dim);
+    else logLum[i] = path_loglum(camDepth, lightDepth, sceneSer, p, v);
+}
+
 template <class T> int upload(const std::vector<T> &v, T **out) {
     *out = nullptr;
     const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
@@ -367,9 +377,34 @@ int32_t lmc_vert_param_size(int32_t cam_depth, int32_t light_depth) {
     return maxDepth * 46 + maxDepth * 10 + 56 + maxDepth * 2 + maxDepth * 1 + 3 + 1 + 1;
 }
 
-int lmc_eval_batch(lmc_ctx *c, int32_t, int32_t, int32_t, const float *, const float *, const float *, int32_t, float *, float *) {
-    if (!c) return fail(LMC_ERR_ARG, "null ctx");
-    return fail(LMC_ERR_UNSUPPORTED, "lmc_eval_batch: gradient kernel not built yet");
+int lmc_eval_batch(lmc_ctx *c, int32_t cam_depth, int32_t light_depth, int32_t n, const float *lens, const float *primary,
+                   const float *vert_params, int32_t vert_stride, float *log_lum, float *grad) {
+    (void)lens;   // Static mode: the screen position is primary[..], `lens` is unused by the generated code too
+    if (!c || !primary || !vert_params || !log_lum || n < 0) return fail(LMC_ERR_ARG, "bad argument");
+    if (cam_depth < 1 || light_depth < 0 || cam_depth + light_depth < 3) return fail(LMC_ERR_ARG, "no path function for this (camDepth, lightDepth)");
+    const int len = cam_depth + light_depth - 1;
+    if (len > 8) return fail(LMC_ERR_UNSUPPORTED, "path functions exist for camDepth + lightDepth - 1 <= 8 (maxDervDepth)");
+    if (vert_stride < lmc::serialized_vert_size(cam_depth, light_depth)) return fail(LMC_ERR_ARG, "vert_stride too small for this path class");
+    if (n == 0) return LMC_OK;
+    CK(cudaSetDevice(c->device));
+    const int dim = 2 * (len > 2 ? len : 2);
+    float *dS = nullptr, *dP = nullptr, *dV = nullptr, *dL = nullptr, *dG = nullptr;
+    CK(cudaMalloc((void **)&dS, 38 * sizeof(float)));
+    CK(cudaMalloc((void **)&dP, sizeof(float) * (size_t)n * (dim + 1)));
+    CK(cudaMalloc((void **)&dV, sizeof(float) * (size_t)n * vert_stride));
+    CK(cudaMalloc((void **)&dL, sizeof(float) * (size_t)n));
+    if (grad) CK(cudaMalloc((void **)&dG, sizeof(float) * (size_t)n * dim));
+    CK(cudaMemcpyAsync(dS, c->sc.sceneSer, 38 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(dP, primary, sizeof(float) * (size_t)n * (dim + 1), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(dV, vert_params, sizeof(float) * (size_t)n * vert_stride, cudaMemcpyHostToDevice, c->stream));
+    k_eval_batch<<<(n + 63) / 64, 64, 0, c->stream>>>(cam_depth, light_depth, n, dS, dP, dim + 1, dV, vert_stride, dL, dG, dim);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(log_lum, dL, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (grad) CK(cudaMemcpyAsync(grad, dG, sizeof(float) * (size_t)n * dim, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(dS); cudaFree(dP); cudaFree(dV); cudaFree(dL); if (dG) cudaFree(dG);
+    return LMC_OK;
 }
 
 int lmc_bvh_probe(lmc_ctx *c, int32_t n, const float *rays, float tmin, float tmax, int32_t any_hit, int32_t *tri_id,

@@ -163,6 +163,102 @@ int lmco_bdpt(void *h, int spp, int minDepth, float *film, int threads) {
     LMCO_CATCH
 }
 
+// Path recorder for the fine-grained parity tests: draws `numLargeSteps` bidirectional paths
+// (GeneratePathBidir), turns every contribution into its (c, l) subpath (ToSubpath), optionally
+// applies one small-step perturbation (PerturbPathBidir, sigma = perturbstddev) and serializes
+// the result in the reference's buffer layout.  Record = LMCO_REC_HEAD + 25 + vstride floats:
+//   [c, l, screenX, screenY, lsScore, ssScore, contribRGB(3), perturbed, nVertFloats, dim, pad(4)]
+//   primary[25] (time first), vertParams[vstride].   Returns the number of records written.
+#define LMCO_REC_HEAD 16
+int lmco_sample_paths(void *h, unsigned long long seed, int numLargeSteps, int perturb, int maxLen, int vstride,
+                      int maxRecords, float *out) {
+    const Scene sc = ((OScene *)h)->store.view();
+    const int MAXD = 8;
+    uint32_t tab[64]; Rng rng; rng.tab = tab; rng.stride = 1; rng_seed(rng, seed);
+    Path<MAXD> *path = new Path<MAXD>(), *sub = new Path<MAXD>(), *pp = new Path<MAXD>();
+    ContribList<Limits<MAXD>::MAXC> contribs;
+    const int recSize = LMCO_REC_HEAD + 25 + vstride;
+    int n = 0;
+    const int minDepth = sc.opt.minDepth > 3 ? sc.opt.minDepth : 3;
+    auto emit = [&](const Path<MAXD> &p, const SubpathContrib &c, int perturbed) {
+        if (n >= maxRecords) return;
+        if (c.camDepth + c.lightDepth - 1 > maxLen) return;
+        if (serialized_vert_size(c.camDepth, c.lightDepth) > vstride) return;
+        float *r = out + (size_t)n * recSize;
+        for (int i = 0; i < recSize; i++) r[i] = 0.0f;
+        r[0] = (float)c.camDepth; r[1] = (float)c.lightDepth; r[2] = c.screenPos.x; r[3] = c.screenPos.y;
+        r[4] = c.lsScore; r[5] = c.ssScore; r[6] = c.contrib.x; r[7] = c.contrib.y; r[8] = c.contrib.z;
+        r[9] = (float)perturbed;
+        r[10] = (float)serialize_path(sc, p, r + LMCO_REC_HEAD, r + LMCO_REC_HEAD + 25);
+        r[11] = (float)path_dimension(p);
+        n++;
+    };
+    for (int s = 0; s < numLargeSteps && n < maxRecords; s++) {
+        contribs.clear(); path_clear(*path);
+        generate_path_bidir(sc, minDepth, sc.opt.maxDepth, *path, contribs, rng);
+        for (int i = 0; i < contribs.n; i++) {
+            path_copy(*sub, *path);
+            to_subpath(contribs.c[i].camDepth, contribs.c[i].lightDepth, *sub);
+            emit(*sub, contribs.c[i], 0);
+            if (perturb) {
+                float offset[2 * MAXD];
+                NormalDist nd = normal_make(0.0f, sc.opt.perturbStdDev);
+                const int dim = path_dimension(*sub);
+                for (int k = 0; k < dim; k++) offset[k] = normal_draw(nd, rng);
+                ContribList<2> pc; pc.clear();
+                path_copy(*pp, *sub);
+                perturb_path_bidir(sc, offset, *pp, pc, rng);
+                if (pc.n > 0) emit(*pp, pc.c[0], 1);
+            }
+        }
+    }
+    delete path; delete sub; delete pp;
+    return n;
+}
+
+// Host twin of lmc_eval_batch: same templated evaluator the kernel compiles (core/pathgrad.h)
+int lmco_eval_batch(void *h, int camDepth, int lightDepth, int n, const float *primary, int primaryStride,
+                    const float *vertParams, int vertStride, float *logLum, float *grad) {
+    const lmc_host::SceneStore &st = ((OScene *)h)->store;
+    float sceneSer[38]; memcpy(sceneSer, st.head.sceneSer, sizeof(sceneSer));
+    const int dim = primary_param_size(camDepth, lightDepth) - 1;
+    for (int i = 0; i < n; i++) {
+        const float *p = primary + (size_t)i * primaryStride, *v = vertParams + (size_t)i * vertStride;
+        if (grad) logLum[i] = path_loglum_grad(camDepth, lightDepth, sceneSer, p, v, grad + (size_t)i * dim);
+        else logLum[i] = path_loglum(camDepth, lightDepth, sceneSer, p, v);
+    }
+    return 0;
+}
+int lmco_scene_serialized(void *h, float *out38) { memcpy(out38, ((OScene *)h)->store.head.sceneSer, 38 * sizeof(float)); return 0; }
+
+// RNG streams from a fresh RNG(seed) each: raw 32-bit draws, uniform_real_distribution<float>(0,1),
+// normal_distribution<float>(0,1) (core/rng.h restatement; golden vectors come from the reference header)
+int lmco_rng_stream(unsigned long long seed, int n, unsigned int *raw, float *uni, float *nrm) {
+    uint32_t tab[64]; Rng r; r.tab = tab; r.stride = 1;
+    if (raw) { rng_seed(r, seed); for (int i = 0; i < n; i++) raw[i] = rng_next(r); }
+    if (uni) { rng_seed(r, seed); for (int i = 0; i < n; i++) uni[i] = rng_uniform(r); }
+    if (nrm) { rng_seed(r, seed); NormalDist d = normal_make(0.0f, 1.0f); for (int i = 0; i < n; i++) nrm[i] = normal_draw(d, r); }
+    return 0;
+}
+// deterministic math header probes: fn 0 sin, 1 cos, 2 exp, 3 log, 4 pow(x,y), 5 atan2(x,y), 6 acos, 7 fastlog, 8 fastpow(x,y)
+int lmco_math(int fn, int n, const float *x, const float *y, float *out) {
+    for (int i = 0; i < n; i++) {
+        switch (fn) {
+            case 0: out[i] = dm_sin(x[i]); break;
+            case 1: out[i] = dm_cos(x[i]); break;
+            case 2: out[i] = dm_exp(x[i]); break;
+            case 3: out[i] = dm_log(x[i]); break;
+            case 4: out[i] = dm_pow(x[i], y[i]); break;
+            case 5: out[i] = dm_atan2(x[i], y[i]); break;
+            case 6: out[i] = dm_acos(x[i]); break;
+            case 7: out[i] = dm_fastlog(x[i]); break;
+            case 8: out[i] = dm_fastpow(x[i], y[i]); break;
+            default: return -1;
+        }
+    }
+    return 0;
+}
+
 // rays: n x 6 (org, dir); out: tid[n], tuv[n x 3].  brute != 0 -> O(N) closest hit
 int lmco_intersect(void *h, int n, const float *rays, float tmin, float tmax, int brute, int *tid, float *tuv) {
     const Scene sc = ((OScene *)h)->store.view();
