@@ -15,14 +15,22 @@ oracle: oracle/liblmc_oracle.so
 oracle/liblmc_oracle.so: oracle/oracle_api.cpp $(PKG)/csrc/host/host_scene.cpp $(CORE_H)
 	$(CXX) $(CXXFLAGS) -shared -o $@ oracle/oracle_api.cpp $(PKG)/csrc/host/host_scene.cpp -lz
 
+CUDA_SRC := $(PKG)/csrc/cuda
+CUDA_OBJ := $(PKG)/build/lmc_abi.o $(PKG)/build/chain_inst_4.o $(PKG)/build/chain_inst_8.o $(PKG)/build/chain_inst_12.o
 lib: $(PKG)/liblmc_b200.so
-$(PKG)/liblmc_b200.so: $(PKG)/csrc/cuda/lmc_abi.cu $(PKG)/csrc/host/host_scene.cpp $(CORE_H) include/lmc/lmc_abi.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(PKG)/csrc/cuda/lmc_abi.cu $(PKG)/csrc/host/host_scene.cpp -lz 2> $(PKG)/ptxas.log || (cat $(PKG)/ptxas.log; false)
+$(PKG)/build/%.o: $(CUDA_SRC)/%.cu $(CORE_H) $(CUDA_SRC)/chain_kernels.cuh include/lmc/lmc_abi.h
+	@mkdir -p $(PKG)/build
+	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $(PKG)/build/$*.ptxas.log || (cat $(PKG)/build/$*.ptxas.log; false)
+$(PKG)/build/host_scene.o: $(PKG)/csrc/host/host_scene.cpp $(CORE_H)
+	@mkdir -p $(PKG)/build
+	$(CXX) $(CXXFLAGS) -c -o $@ $<
+$(PKG)/liblmc_b200.so: $(CUDA_OBJ) $(PKG)/build/host_scene.o
+	$(NVCC) -ccbin /usr/bin/g++ -shared -o $@ $^ -lz -lpthread
 
 ref:
 	bash oracle/build_ref.sh
 
 clean:
-	rm -f oracle/liblmc_oracle.so $(PKG)/liblmc_b200.so
+	rm -rf oracle/liblmc_oracle.so $(PKG)/liblmc_b200.so $(PKG)/build
 
 .PHONY: all oracle lib ref clean

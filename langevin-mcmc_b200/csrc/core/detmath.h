@@ -20,7 +20,7 @@
 
 #if defined(__CUDACC__)
 #define LMC_HD __host__ __device__ __forceinline__
-#define LMC_HD_NOINLINE __host__ __device__ __noinline__
+#define LMC_HD_NOINLINE __host__ __device__ __noinline__ inline
 #else
 #define LMC_HD inline
 #define LMC_HD_NOINLINE inline

@@ -9,16 +9,18 @@
 // Host code here is glue only: device memory, launches, error translation.  No CPU fallback.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstddef>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../../include/lmc/lmc_abi.h"
-#include "../core/chain.h"
+#include "chain_kernels.cuh"
 #include "../host/host_scene.h"
 #include "../host/mlt_init.h"
 
 using namespace lmc;
+using namespace lmc_cuda;
 
 struct lmc_scene { lmc_host::SceneStore store; };
 
@@ -26,46 +28,6 @@ namespace {
 thread_local std::string g_err;
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(LMC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
-
-struct DevFilm {
-    float *p;
-    __device__ __forceinline__ void add(int pix, int c, float v) { atomicAdd(p + 3 * pix + c, v); }
-};
-
-template <int MAXD>
-__global__ void k_chain_init(ChainState<MAXD> *states, int n, int chainBase, const float *initLs) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    chain_state_init(states[i], initLs ? initLs[chainBase + i] : 0.0f);
-}
-
-template <int MAXD>
-__global__ void __launch_bounds__(128) k_chain_run(const __grid_constant__ Scene sc, RunParams rp, int chainBase,
-                                                    ChainState<MAXD> *states, int n, long long numSteps, float *film,
-                                                    unsigned char *trace, float *aTrace) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t tab[64];
-    DevFilm df; df.p = film;
-    chain_run(sc, rp, chainBase + i, states[i], numSteps, tab, 1, df,
-              trace ? trace + (size_t)i * numSteps : nullptr, aTrace ? aTrace + (size_t)i * numSteps : nullptr, 1);
-}
-
-template <int MAXD>
-__global__ void k_chain_stats(const ChainState<MAXD> *states, int n, unsigned long long *out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long v[10];
-    for (int k = 0; k < 10; k++) v[k] = 0ULL;
-    if (i < n) {
-        for (int k = 0; k < 4; k++) { v[k] = states[i].nPropose[k]; v[4 + k] = states[i].nAccept[k]; }
-        v[8] = states[i].gradStats[0]; v[9] = states[i].gradStats[1];
-    }
-    for (int k = 0; k < 10; k++) {
-        unsigned long long x = v[k];
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if ((threadIdx.x & 31) == 0 && x) atomicAdd(out + k, x);
-    }
-}
 
 __global__ void k_bvh_probe(const __grid_constant__ Scene sc, int n, const float *rays, float tmin, float tmax, int anyHit,
                             int *triId, int *geomPrim, float *tuv) {
@@ -122,44 +84,45 @@ struct lmc_ctx {
 };
 
 namespace {
-template <int MAXD>
-int chains_begin_t(lmc_ctx *c) {
+int chains_begin(lmc_ctx *c) {
     const int n = c->desc.num_chains;
-    const size_t bytes = sizeof(ChainState<MAXD>) * (size_t)n;
+    const int d = c->maxdTemplate;
+    const size_t bytes = (d == 4 ? chain_state_bytes_4() : (d == 8 ? chain_state_bytes_8() : chain_state_bytes_12())) * (size_t)n;
     if (c->states && c->stateBytes != bytes) { cudaFree(c->states); c->states = nullptr; }
     if (!c->states) { CK(cudaMalloc(&c->states, bytes)); c->stateBytes = bytes; }
-    k_chain_init<MAXD><<<(n + 127) / 128, 128, 0, c->stream>>>((ChainState<MAXD> *)c->states, n, c->desc.chain_base, c->initLs);
+    uint32_t *st = (uint32_t *)c->states;
     c->launches++;
-    CK(cudaGetLastError());
+    CK(d == 4 ? launch_chain_init_4(c->stream, st, n, c->desc.chain_base, c->initLs)
+              : (d == 8 ? launch_chain_init_8(c->stream, st, n, c->desc.chain_base, c->initLs)
+                        : launch_chain_init_12(c->stream, st, n, c->desc.chain_base, c->initLs)));
     return LMC_OK;
 }
 
-template <int MAXD>
-int run_chains_t(lmc_ctx *c, long long numSteps, unsigned char *dTrace, float *dATrace) {
+int run_chains(lmc_ctx *c, long long numSteps, unsigned char *dTrace, float *dATrace) {
     const int n = c->desc.num_chains;
+    const int d = c->maxdTemplate;
     RunParams rp; rp.normalization = c->desc.normalization; rp.numChains = c->desc.total_chains;
     rp.numSamplesThisChain = c->desc.samples_per_chain; rp.initLsScore = c->initLs;
+    uint32_t *st = (uint32_t *)c->states;
     CK(cudaEventRecord(c->ev0, c->stream));
-    k_chain_run<MAXD><<<(n + 127) / 128, 128, 0, c->stream>>>(c->sc, rp, c->desc.chain_base, (ChainState<MAXD> *)c->states, n,
-                                                               numSteps, c->film, dTrace, dATrace);
     c->launches++;
-    CK(cudaGetLastError());
+    CK(d == 4 ? launch_chain_run_4(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace)
+              : (d == 8 ? launch_chain_run_8(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace)
+                        : launch_chain_run_12(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace)));
     CK(cudaEventRecord(c->ev1, c->stream));
     return LMC_OK;
 }
 
-template <int MAXD>
-int stats_t(lmc_ctx *c) {
+int chain_stats(lmc_ctx *c) {
     const int n = c->desc.num_chains;
+    const int d = c->maxdTemplate;
+    const uint32_t *st = (const uint32_t *)c->states;
     CK(cudaMemsetAsync(c->statsDev, 0, 10 * sizeof(unsigned long long), c->stream));
-    k_chain_stats<MAXD><<<(n + 127) / 128, 128, 0, c->stream>>>((const ChainState<MAXD> *)c->states, n, c->statsDev);
     c->launches++;
-    CK(cudaGetLastError());
+    CK(d == 4 ? launch_chain_stats_4(c->stream, st, n, c->statsDev)
+              : (d == 8 ? launch_chain_stats_8(c->stream, st, n, c->statsDev) : launch_chain_stats_12(c->stream, st, n, c->statsDev)));
     return LMC_OK;
 }
-
-#define DISPATCH_MAXD(c, expr4, expr8, expr12) \
-    ((c)->maxdTemplate == 4 ? (expr4) : ((c)->maxdTemplate == 8 ? (expr8) : (expr12)))
 }  // namespace
 
 extern "C" {
@@ -290,7 +253,7 @@ int lmc_chains_begin(lmc_ctx *c, const lmc_run_desc *desc, const float *init_ls_
     CK(cudaMalloc((void **)&c->initLs, sizeof(float) * (size_t)desc->total_chains));
     if (init_ls_score) CK(cudaMemcpyAsync(c->initLs, init_ls_score, sizeof(float) * (size_t)desc->total_chains, cudaMemcpyHostToDevice, c->stream));
     else CK(cudaMemsetAsync(c->initLs, 0, sizeof(float) * (size_t)desc->total_chains, c->stream));
-    const int rc = DISPATCH_MAXD(c, chains_begin_t<4>(c), chains_begin_t<8>(c), chains_begin_t<12>(c));
+    const int rc = chains_begin(c);
     if (rc) return rc;
     c->begun = true;
     return lmc_film_clear(c);
@@ -305,8 +268,7 @@ int lmc_run_chains(lmc_ctx *c, int64_t num_mutations, uint8_t *trace, float *a_t
     const size_t cnt = (size_t)c->desc.num_chains * (size_t)num_mutations;
     if (trace) CK(cudaMalloc((void **)&dTrace, cnt));
     if (a_trace) CK(cudaMalloc((void **)&dA, cnt * sizeof(float)));
-    int rc = DISPATCH_MAXD(c, run_chains_t<4>(c, num_mutations, dTrace, dA), run_chains_t<8>(c, num_mutations, dTrace, dA),
-                           run_chains_t<12>(c, num_mutations, dTrace, dA));
+    int rc = run_chains(c, num_mutations, dTrace, dA);
     if (rc == LMC_OK && (trace || a_trace)) {
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e == cudaSuccess && trace) e = cudaMemcpy(trace, dTrace, cnt, cudaMemcpyDeviceToHost);
@@ -330,7 +292,7 @@ int lmc_get_stats(lmc_ctx *c, lmc_stats *out) {
     memset(out, 0, sizeof(*out));
     CK(cudaSetDevice(c->device));
     if (c->begun) {
-        const int rc = DISPATCH_MAXD(c, stats_t<4>(c), stats_t<8>(c), stats_t<12>(c));
+        const int rc = chain_stats(c);
         if (rc) return rc;
         unsigned long long h[10];
         CK(cudaMemcpyAsync(h, c->statsDev, sizeof(h), cudaMemcpyDeviceToHost, c->stream));

@@ -1,0 +1,121 @@
+"""Chain-loop parity: the CUDA persistent-chain kernel vs the CPU oracle (bit-level twin).
+
+BASELINE.json configs[0]: torus, LMC, path length 4, 1024 chains x 100 mutations, fixed PCG
+seeds (chain id + seedoffset): accept/reject + step-type sequence and acceptance probabilities
+must be BIT-identical; the film equal up to fp32 atomic summation order."""
+import numpy as np
+import pytest
+
+
+def oracle_run(oracle, xml, opts, chains, steps, norm, init_ls, **kw):
+    h = oracle.load(xml)
+    for k, v in opts.items():
+        oracle.set_option(h, k, v)
+    return oracle.run_chains(h, chains, steps, norm, init_ls, **kw)
+
+
+def test_oracle_chain_loop_properties(oracle, torus_xml):
+    """CPU-only sanity of the oracle itself: determinism, sharding invariance, step mix."""
+    h = oracle.load(torus_xml)
+    oracle.set_option(h, "maxdepth", 4)
+    norm, init_ls = oracle.mlt_init(h, 40000, 256, 32)
+    f1, t1, a1, s1 = oracle.run_chains(h, 256, 40, norm, init_ls, threads=4)
+    f2, t2, a2, s2 = oracle.run_chains(h, 256, 40, norm, init_ls, threads=2)
+    assert np.array_equal(t1, t2) and np.array_equal(a1.view(np.uint32), a2.view(np.uint32))
+    # a shard [128, 256) of the same job reproduces the same chains (seed = global chain id)
+    f3, t3, a3, s3 = oracle.run_chains(h, 128, 40, norm, init_ls, chain_base=128, total_chains=256, threads=2)
+    assert np.array_equal(t3, t1[128:])
+    # every chain starts with a large step (init states are invalid, src/mlt.h:124)
+    assert ((t1[:, 0] & 3) == 0).all()
+    assert int(s1[:4].sum()) == 256 * 40
+    types = t1 & 3
+    assert (types == 3).mean() > 0.5          # MALA small steps dominate
+    assert s1[8] > 0                          # gradients were evaluated
+    assert np.isfinite(f1).all() and f1.sum() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("maxdepth,chains,steps", [(4, 1024, 100), (8, 512, 48), (12, 256, 24)])
+def test_cuda_trace_bit_identical_to_oracle(lmc, oracle, torus_xml, maxdepth, chains, steps):
+    sc = lmc.ParseScene(torus_xml)
+    sc.options["maxdepth"] = maxdepth
+    norm, init_ls = lmc.MLTInit(sc, 300000, chains, 32)
+    ctx = lmc.ChainContext(sc, 0)
+    ctx.begin(chains, norm, init_ls, samples_per_chain=steps)
+    trace, a = ctx.run(steps, trace=True, a_trace=True)
+    film = ctx.film()
+    st = ctx.stats()
+    ofilm, otrace, oa, ostats = oracle_run(oracle, torus_xml, {"maxdepth": maxdepth}, chains, steps, norm, init_ls,
+                                           samples_per_chain=steps)
+    assert np.array_equal(trace, otrace), "%d chains diverge" % int((trace != otrace).any(axis=1).sum())
+    assert np.array_equal(a.view(np.uint32), oa.view(np.uint32))
+    assert st["proposed"] == [int(x) for x in ostats[:4]] and st["accepted"] == [int(x) for x in ostats[4:8]]
+    assert st["gradient_evals"] == int(ostats[8]) and st["gradient_nonfinite"] == int(ostats[9])
+    assert np.allclose(film, ofilm, rtol=1e-4, atol=1e-5 * max(1.0, float(ofilm.max())))
+    assert abs(float(film.sum()) - float(ofilm.sum())) <= 1e-4 * float(ofilm.sum())
+
+
+@pytest.mark.gpu
+def test_cuda_door_scene_and_isotropic_kernel(lmc, oracle, door_xml):
+    """veach-door (area light, connections, light tracing, textures) and mala=false (SmallStep)."""
+    for mala in (1, 0):
+        sc = lmc.ParseScene(door_xml)
+        sc.options.update({"maxdepth": 6, "mala": mala})
+        chains, steps = 512, 40
+        norm, init_ls = lmc.MLTInit(sc, 100000, chains, 32)
+        ctx = lmc.ChainContext(sc, 0)
+        ctx.begin(chains, norm, init_ls, samples_per_chain=steps)
+        trace, a = ctx.run(steps, trace=True, a_trace=True)
+        ofilm, otrace, oa, ostats = oracle_run(oracle, door_xml, {"maxdepth": 6, "mala": mala}, chains, steps, norm, init_ls,
+                                               samples_per_chain=steps)
+        assert np.array_equal(trace, otrace) and np.array_equal(a.view(np.uint32), oa.view(np.uint32))
+        if not mala:
+            assert ((trace & 3) != 3).all()
+
+
+@pytest.mark.gpu
+def test_cuda_launch_split_and_sharding_invariance(lmc, torus_xml):
+    """100 mutations in one launch == 4 launches of 25 (state round-trips through HBM bit-exactly),
+    and a shard of the chain range reproduces the same chains."""
+    sc = lmc.ParseScene(torus_xml)
+    sc.options["maxdepth"] = 8
+    chains, steps = 512, 100
+    norm, init_ls = lmc.MLTInit(sc, 300000, chains, 32)
+    ctx = lmc.ChainContext(sc, 0)
+    ctx.begin(chains, norm, init_ls, samples_per_chain=steps)
+    t_one, a_one = ctx.run(steps, trace=True, a_trace=True)
+    film_one = ctx.film()
+    ctx.begin(chains, norm, init_ls, samples_per_chain=steps)
+    parts = [ctx.run(25, trace=True, a_trace=True) for _ in range(4)]
+    t_split = np.concatenate([p[0] for p in parts], axis=1)
+    assert np.array_equal(t_one, t_split)
+    assert np.allclose(ctx.film(), film_one, rtol=1e-4, atol=1e-5)
+    ctx.begin(128, norm, init_ls, chain_base=256, total_chains=chains, samples_per_chain=steps)
+    t_shard, _ = ctx.run(steps, trace=True)
+    assert np.array_equal(t_shard, t_one[256:384])
+
+
+@pytest.mark.gpu
+def test_cuda_full_size_properties(lmc, torus_xml):
+    """BASELINE configs[1] size (2^20 chains, maxdepth 8): size-independent invariants."""
+    sc = lmc.ParseScene(torus_xml)
+    sc.options["maxdepth"] = 8
+    chains, steps = 1 << 20, 8
+    norm, init_small = lmc.MLTInit(sc, 300000, 4096, 32)
+    init_ls = np.resize(init_small, chains)
+    ctx = lmc.ChainContext(sc, 0)
+    ctx.begin(chains, norm, init_ls, samples_per_chain=steps)
+    ctx.run(steps)
+    st = ctx.stats()
+    assert sum(st["proposed"]) == chains * steps
+    assert st["proposed"][0] >= chains                 # every chain opens with a large step
+    assert all(a <= p for a, p in zip(st["accepted"], st["proposed"]))
+    film = ctx.film()
+    assert np.isfinite(film).all() and film.min() >= 0.0
+    # energy check: sum of splats / mutations estimates the image mean (normalization = b)
+    mean = float(film.sum()) / (chains * steps) / 3.0
+    assert 0.2 * norm < mean < 5.0 * norm
+    # the first 1024 chains of the big job are the chains of a 1024-chain job (seed = chain id)
+    ctx.begin(1024, norm, init_ls[:1024], total_chains=chains, samples_per_chain=steps)
+    t_small, _ = ctx.run(steps, trace=True)
+    assert ((t_small[:, 0] & 3) == 0).all()
