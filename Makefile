@@ -25,7 +25,7 @@ $(PKG)/build/host_scene.o: $(PKG)/csrc/host/host_scene.cpp $(CORE_H)
 	@mkdir -p $(PKG)/build
 	$(CXX) $(CXXFLAGS) -c -o $@ $<
 $(PKG)/liblmc_b200.so: $(CUDA_OBJ) $(PKG)/build/host_scene.o
-	$(NVCC) -ccbin /usr/bin/g++ -shared -o $@ $^ -lz -lpthread
+	$(NVCC) -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -shared -o $@ $^ -lz -lpthread
 
 ref:
 	bash oracle/build_ref.sh

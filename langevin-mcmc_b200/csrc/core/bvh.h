@@ -115,7 +115,7 @@ struct Isect {
 
 // Fill the intersection record for triangle `tid` hit at (t,u,v)
 // (reference: TriangleIntersect + TriangleMesh::Intersect, src/trianglemesh.cpp:58-79,189-236).
-LMC_HD void fill_isect(const Scene &sc, const Ray &ray, const Hit &h, Isect &isect, V2 &st) {
+LMC_HD_NOINLINE void fill_isect(const Scene &sc, const Ray &ray, const Hit &h, Isect &isect, V2 &st) {
     const TriGeom &tg = sc.tris[h.tid];
     const TriShade &ts = sc.shade[h.tid];
     const V3 e1 = ld3(tg.e1), e2 = ld3(tg.e2);

@@ -12,6 +12,7 @@ template <int MAXD>
 struct ChainState {
     MarkovState<MAXD> st[2];
     ChainVars<MAXD> ch;
+    StepScratch<MAXD> ss;
     int curIdx;
     unsigned long long rngState;
     unsigned int rngEpoch;
@@ -36,6 +37,8 @@ LMC_HD void chain_state_init(ChainState<MAXD> &cs, float initLsScore) {
     }
     cs.st[0].sp.lsScore = initLsScore;   // initStates[chainId].spContrib.lsScore
     chain_vars_init(cs.ch);
+    cs.ss.kind = STEP_LARGE; cs.ss.needCurGrad = 0; cs.ss.needPropGrad = 0; cs.ss.hasContrib = 0; cs.ss.a = 0.0f;
+    for (int i = 0; i < Limits<MAXD>::DIM; i++) { cs.ss.offset[i] = 0.0f; cs.ss.grad[i] = 0.0f; }
     cs.curIdx = 0; cs.rngState = 0ULL; cs.rngEpoch = 0u; cs.seeded = 0u; cs.sampleIdx = 0;
     for (int i = 0; i < 4; i++) { cs.nAccept[i] = 0; cs.nPropose[i] = 0; }
     cs.gradStats[0] = 0; cs.gradStats[1] = 0;
@@ -59,7 +62,7 @@ LMC_HD void chain_run(const Scene &sc, const RunParams &rp, int globalChainId, C
     }
     for (long long k = 0; k < numSteps; k++) {
         const StepInfo info = chain_step(sc, rp, globalChainId, cs.sampleIdx, cs.st, cs.curIdx, cs.ch, rng, film,
-                                         cs.gradStats);
+                                         cs.gradStats, cs.ss);
         cs.nPropose[info.mutationType] += 1u;
         cs.nAccept[info.mutationType] += (unsigned int)info.accepted;
         if (trace) trace[k * traceStride] = (unsigned char)(info.mutationType | (info.accepted << 2) | ((info.a > 0.0f) ? 8 : 0));

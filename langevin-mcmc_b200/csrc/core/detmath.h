@@ -78,7 +78,7 @@ LMC_HD float dm_fmod(float a, float b) { return fmodf(a, b); }  // exact by defi
 // ---------------------------------------------------------------------------------------
 
 // sin & cos of x (double), |x| < ~1e8.
-LMC_HD void dm_sincos_d(double x, double &s, double &c) {
+LMC_HD_NOINLINE void dm_sincos_d(double x, double &s, double &c) {
     const double k = rint(x * 0.63661977236758134308);  // 2/pi
     double r = x - k * 1.57079632679489655800e+00;
     r = r - k * 6.12323399573676603587e-17;
@@ -109,7 +109,7 @@ LMC_HD void dm_sincos_d(double x, double &s, double &c) {
 }
 
 // exp(x) for double x, result in double (clamped to float-representable magnitudes).
-LMC_HD double dm_exp_d(double x) {
+LMC_HD_NOINLINE double dm_exp_d(double x) {
     if (x != x) return x;
     if (x > 90.0) return (double)dm_inf();
     if (x < -110.0) return 0.0;
@@ -135,7 +135,7 @@ LMC_HD double dm_exp_d(double x) {
 }
 
 // log(x) for positive finite normal double x.
-LMC_HD double dm_log_pos_d(double x) {
+LMC_HD_NOINLINE double dm_log_pos_d(double x) {
     uint64_t b = d2u(x);
     long long e = (long long)((b >> 52) & 0x7ffULL) - 1023LL;
     double m = u2d((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
@@ -186,7 +186,7 @@ LMC_HD double dm_atan01_d(double t) {
     return base + t * p;
 }
 
-LMC_HD double dm_atan2_d(double y, double x) {
+LMC_HD_NOINLINE double dm_atan2_d(double y, double x) {
     const double ax = x < 0.0 ? -x : x;
     const double ay = y < 0.0 ? -y : y;
     if (ax == 0.0 && ay == 0.0) return 0.0;

@@ -139,153 +139,187 @@ LMC_HD void splat(FILM &film, int width, int height, V2 screenPos, V3 contrib) {
     }
 }
 
-// --- gradient + Adam-style moments + Gaussian for one state (src/mutation_mala.h:83-166 / :178-260) ---
-template <int MAXD>
-LMC_HD void mala_build_gaussian(const Scene &sc, const MarkovState<MAXD> &st, ChainVars<MAXD> &ch,
-                                float *new_v1, float *new_v2, Gaussian<Limits<MAXD>::DIM> &out,
-                                unsigned int *gradStats) {
-    const int dim = path_dimension(st.path);
-    const SubpathContrib &csp = st.sp;
-    const bool haveFunc = (csp.camDepth + csp.lightDepth - 1) <= sc.opt.maxDervDepth &&
-                          grad_supported(sc, st.path);
-    if (dim >= sc.opt.pssMinLength && dim <= sc.opt.pssMaxLength && haveFunc) {
-        float vGrad[Limits<MAXD>::DIM];
-        for (int i = 0; i < dim; i++) vGrad[i] = 0.0f;
-        if (csp.ssScore > 1e-10f) {
-            path_gradient(sc, st.path, vGrad);
-            bool finite = true;
-            for (int i = 0; i < dim; i++) if (!dm_isfinite(vGrad[i])) finite = false;
-            if (!finite) {
-                for (int i = 0; i < dim; i++) vGrad[i] = 0.0f;
-                if (gradStats) gradStats[1]++;
-            }
-            if (gradStats) gradStats[0]++;
-        }
-        float norm = 0.0f;
-        const float drift = sc.opt.malaGN;
-        for (int i = 0; i < dim; i++) norm += vGrad[i] * vGrad[i];
-        norm = dm_sqrt(norm);
-        for (int i = 0; i < dim; i++) vGrad[i] *= drift / dm_max(drift, norm);
-        bool first = true;
-        for (int i = 0; i < dim; i++) if (new_v2[i] > 1e-10f) { first = false; break; }
-        float M[Limits<MAXD>::DIM];
-        for (int i = 0; i < dim; i++) {
-            const float g = vGrad[i];
-            new_v1[i] = first ? g : 0.9f * ch.v1[i] + 0.1f * g;
-            new_v2[i] = first ? g * g : 0.999f * ch.v2[i] + 0.001f * g * g;
-            M[i] = dm_clamp(1.0f / (1e-3f + dm_sqrt(new_v2[i])), LMC_PCD_MIN, LMC_PCD_MAX);
-        }
-        compute_gaussian_lmc(dim, new_v1, M, sc.opt.malaStepsize, sc.opt.malaStdDev, csp.ssScore, out);
-    } else {
-        isotropic_gaussian(dim, sc.opt.malaStdDev, out);
-    }
-}
+// ------------------------------------------------------------------------------------------
+// One iteration of the chain loop, split into PHASES so the device can run each phase as its
+// own kernel over a compacted list of chains (wavefront execution) while the host twin calls the
+// same functions back to back.  RNG draws happen in the reference's order:
+//   [u_large if cur.valid] -> Mutate{ u_mix -> D normals -> PerturbPathBidir normals } -> [u_accept if a > 0]
+// The gradient phases draw nothing.
+// ------------------------------------------------------------------------------------------
+enum StepKind { STEP_LARGE = 0, STEP_ISO = 1, STEP_MALA = 2 };
 
-// SmallStep::Mutate
 template <int MAXD>
-LMC_HD float small_step_mutate(const Scene &sc, float normalization, MarkovState<MAXD> &cur,
-                               MarkovState<MAXD> &prop, Rng &rng, ChainVars<MAXD> &ch) {
-    ContribList<2> contribs; contribs.clear();
-    float a = 1.0f;
-    path_copy(prop.path, cur.path);
-    NormalDist nd = normal_make(0.0f, sc.opt.perturbStdDev);
-    ch.lastMutationType = MUT_SMALL;
-    const int dim = path_dimension(cur.path);
+struct StepScratch {
+    int kind;            // StepKind of the iteration in flight
+    int needCurGrad;     // gradient of the CURRENT state wanted before the proposal (MALA, lazily)
+    int needPropGrad;    // gradient of the PROPOSAL wanted before the acceptance test (MALA)
+    int hasContrib;      // the proposal produced a contribution
+    float a;             // acceptance probability (final after phase_finish)
     float offset[Limits<MAXD>::DIM];
-    for (int i = 0; i < dim; i++) offset[i] = normal_draw(nd, rng);
-    perturb_path_bidir(sc, offset, prop.path, contribs, rng);
-    prop.gaussianInitialized = 0;
-    if (contribs.n > 0) {
-        prop.sp = contribs.c[0];
-        a = dm_clamp(prop.sp.ssScore / cur.sp.ssScore, 0.0f, 1.0f);
-        prop.nSplat = 1;
-        prop.splat[0].screenPos = prop.sp.screenPos;
-        prop.splat[0].contrib = prop.sp.contrib * (normalization / prop.sp.lsScore);
-    } else {
-        a = 0.0f;
-    }
-    return a;
+    float grad[Limits<MAXD>::DIM];
+};
+
+// How MALASmallStep obtains the Gaussian of a state (src/mutation_mala.h:94-163 with the global
+// cache never ready): 0 = IsotropicGaussian(malaStdDev); 1 = ComputeGaussian with a zero gradient
+// (ssScore <= 1e-10, the reference skips dervFunc); 2 = ComputeGaussian with the evaluated gradient.
+template <int MAXD>
+LMC_HD int mala_grad_mode(const Scene &sc, const MarkovState<MAXD> &st) {
+    const int dim = path_dimension(st.path);
+    const bool haveFunc = (st.sp.camDepth + st.sp.lightDepth - 1) <= sc.opt.maxDervDepth && grad_supported(sc, st.path);
+    if (dim >= sc.opt.pssMinLength && dim <= sc.opt.pssMaxLength && haveFunc) return (st.sp.ssScore > 1e-10f) ? 2 : 1;
+    return 0;
 }
 
-// MALASmallStep::Mutate
+// dervFunc + IsFinite guard (src/mutation_mala.h:100-110)
 template <int MAXD>
-LMC_HD float mala_small_step_mutate(const Scene &sc, float normalization, MarkovState<MAXD> &cur,
-                                    MarkovState<MAXD> &prop, Rng &rng, ChainVars<MAXD> &ch,
-                                    unsigned int *gradStats) {
-    if (rng_uniform(rng) < sc.opt.uniformMixingProbability) {
-        return small_step_mutate(sc, normalization, cur, prop, rng, ch);
+LMC_HD void mala_eval_gradient(const Scene &sc, const MarkovState<MAXD> &st, float *grad, unsigned int *gradStats) {
+    const int dim = path_dimension(st.path);
+    path_gradient(sc, st.path, grad);
+    bool finite = true;
+    for (int i = 0; i < dim; i++) if (!dm_isfinite(grad[i])) finite = false;
+    if (!finite) {
+        for (int i = 0; i < dim; i++) grad[i] = 0.0f;
+        if (gradStats) gradStats[1]++;
     }
-    ContribList<2> contribs; contribs.clear();
-    float a = 1.0f;
-    ch.lastMutationType = MUT_MALA_SMALL;
-    const int dim = path_dimension(cur.path);
+    if (gradStats) gradStats[0]++;
+}
+
+// drift clamp, Adam-style moments, diagonal Gaussian (src/mutation_mala.h:111-129, src/mala.cpp:7-51).
+// `grad` is read only when mode == 2.
+template <int MAXD>
+LMC_HD_NOINLINE void mala_finish_gaussian(const Scene &sc, const MarkovState<MAXD> &st, const ChainVars<MAXD> &ch, int mode,
+                                          const float *grad, float *new_v1, float *new_v2, Gaussian<Limits<MAXD>::DIM> &out) {
+    const int dim = path_dimension(st.path);
+    if (mode == 0) { isotropic_gaussian(dim, sc.opt.malaStdDev, out); return; }
+    float vGrad[Limits<MAXD>::DIM];
+    for (int i = 0; i < dim; i++) vGrad[i] = (mode == 2) ? grad[i] : 0.0f;
+    float norm = 0.0f;
+    const float drift = sc.opt.malaGN;
+    for (int i = 0; i < dim; i++) norm += vGrad[i] * vGrad[i];
+    norm = dm_sqrt(norm);
+    for (int i = 0; i < dim; i++) vGrad[i] *= drift / dm_max(drift, norm);
+    bool first = true;
+    for (int i = 0; i < dim; i++) if (new_v2[i] > 1e-10f) { first = false; break; }
+    float M[Limits<MAXD>::DIM];
+    for (int i = 0; i < dim; i++) {
+        const float g = vGrad[i];
+        new_v1[i] = first ? g : 0.9f * ch.v1[i] + 0.1f * g;
+        new_v2[i] = first ? g * g : 0.999f * ch.v2[i] + 0.001f * g * g;
+        M[i] = dm_clamp(1.0f / (1e-3f + dm_sqrt(new_v2[i])), LMC_PCD_MIN, LMC_PCD_MAX);
+    }
+    compute_gaussian_lmc(dim, new_v1, M, sc.opt.malaStepsize, sc.opt.malaStdDev, st.sp.ssScore, out);
+}
+
+struct RunParams {
+    float normalization;
+    int numChains;
+    long long numSamplesThisChain;   // for the LS_RATIO large-step schedule (src/mlt.cpp:96)
+    const float *initLsScore;        // initStates[i].spContrib.lsScore (outlier reset, src/mlt.cpp:152-158)
+};
+
+// Phase 0: choose the mutation (src/mlt.cpp:96-101, src/mutation_mala.h:47-81).
+template <int MAXD>
+LMC_HD void phase_begin(const Scene &sc, const RunParams &rp, long long sampleIdx, MarkovState<MAXD> &cur,
+                        ChainVars<MAXD> &ch, Rng &rng, StepScratch<MAXD> &ss) {
+    ss.needCurGrad = 0; ss.needPropGrad = 0; ss.hasContrib = 0; ss.a = 1.0f;
+    const float lsScale = ((float)sampleIdx > (float)rp.numSamplesThisChain * sc.opt.lsRatio) ? sc.opt.largeStepProbScale : 1.0f;
+    if (!cur.valid || rng_uniform(rng) < sc.opt.largeStepProbability * lsScale) { ss.kind = STEP_LARGE; return; }
+    if (!sc.opt.mala) { ss.kind = STEP_ISO; return; }
+    if (rng_uniform(rng) < sc.opt.uniformMixingProbability) { ss.kind = STEP_ISO; return; }
+    ss.kind = STEP_MALA;
     if (!ch.buffered) {
         for (int i = 0; i < Limits<MAXD>::DIM; i++) {
-            ch.v1[i] = 0; ch.v2[i] = 0; ch.curr_new_v1[i] = 0; ch.curr_new_v2[i] = 0;
-            ch.prop_new_v1[i] = 0; ch.prop_new_v2[i] = 0;
+            ch.v1[i] = 0; ch.v2[i] = 0; ch.curr_new_v1[i] = 0; ch.curr_new_v2[i] = 0; ch.prop_new_v1[i] = 0; ch.prop_new_v2[i] = 0;
         }
         ch.buffered = 1;
     }
-    if (!cur.gaussianInitialized) {
-        mala_build_gaussian(sc, cur, ch, ch.curr_new_v1, ch.curr_new_v2, cur.gaussian, gradStats);
-        cur.gaussianInitialized = 1;
-    }
-    float offset[Limits<MAXD>::DIM];
-    generate_sample(cur.gaussian, offset, rng);
-    path_copy(prop.path, cur.path);
-    perturb_path_bidir(sc, offset, prop.path, contribs, rng);
-    if (contribs.n > 0) {
-        prop.sp = contribs.c[0];
-        mala_build_gaussian(sc, prop, ch, ch.prop_new_v1, ch.prop_new_v2, prop.gaussian, gradStats);
-        prop.gaussianInitialized = 1;
-        const float py = gaussian_log_pdf(offset, 1.0f, cur.gaussian);
-        const float px = gaussian_log_pdf(offset, -1.0f, prop.gaussian);
-        a = dm_clamp(dm_exp(px - py) * prop.sp.ssScore / cur.sp.ssScore, 0.0f, 1.0f);
-        prop.nSplat = 1;
-        prop.splat[0].screenPos = prop.sp.screenPos;
-        prop.splat[0].contrib = prop.sp.contrib * normalization / prop.sp.lsScore;
-    } else {
-        a = 0.0f;
-    }
-    return a;
+    if (!cur.gaussianInitialized && mala_grad_mode(sc, cur) == 2) ss.needCurGrad = 1;
 }
 
-// LargeStep::Mutate (largeStepMultiplexed == false)
+// Phase 1 / 3: PSS gradient of the current state / of the proposal (no RNG).
 template <int MAXD>
-LMC_HD float large_step_mutate(const Scene &sc, float normalization, MarkovState<MAXD> &cur,
-                               MarkovState<MAXD> &prop, Rng &rng, ChainVars<MAXD> &ch) {
-    ch.lastMutationType = MUT_LARGE;
-    float a = 1.0f;
-    ContribList<Limits<MAXD>::MAXC> contribs; contribs.clear();
-    path_clear(prop.path);
-    const int minDepth = sc.opt.minDepth > 3 ? sc.opt.minDepth : 3;
-    generate_path_bidir(sc, minDepth, sc.opt.maxDepth, prop.path, contribs, rng);
-    prop.gaussianInitialized = 0;
-    if (contribs.n > 0) {
-        float cdf[Limits<MAXD>::MAXC + 1];
-        cdf[0] = 0.0f;
-        for (int i = 0; i < contribs.n; i++) cdf[i + 1] = cdf[i] + contribs.c[i].lsScore;
-        const float scoreSum = cdf[contribs.n];
-        const float invSc = inverse(scoreSum);
-        for (int i = 0; i <= contribs.n; i++) cdf[i] *= invSc;
-        const int it = upper_bound_f(cdf, contribs.n + 1, rng_uniform(rng));
-        const int contribId = dm_clampi(it - 1, 0, contribs.n - 1);
-        prop.sp = contribs.c[contribId];
-        prop.scoreSum = scoreSum;
-        if (cur.valid) {
-            const float probProposal = prop.sp.lsScore / prop.scoreSum;
-            const float probLast = ch.lastScore / ch.lastScoreSum;
-            a = dm_clamp((prop.sp.lsScore * probLast) / (cur.sp.lsScore * probProposal), 0.0f, 1.0f);
+LMC_HD void phase_gradient(const Scene &sc, const MarkovState<MAXD> &st, StepScratch<MAXD> &ss, unsigned int *gradStats) {
+    mala_eval_gradient(sc, st, ss.grad, gradStats);
+}
+
+// Phase 2: draw the proposal and trace it.
+// SmallStep::Mutate (src/mutation_small.h:16-55), MALASmallStep::Mutate up to the proposal's
+// gradient (src/mutation_mala.h:83-176), LargeStep::Mutate (src/mutation_large.h:31-127).
+template <int MAXD>
+LMC_HD void phase_propose(const Scene &sc, const RunParams &rp, MarkovState<MAXD> &cur, MarkovState<MAXD> &prop,
+                          ChainVars<MAXD> &ch, Rng &rng, StepScratch<MAXD> &ss) {
+    const float normalization = rp.normalization;
+    if (ss.kind == STEP_LARGE) {
+        ch.lastMutationType = MUT_LARGE;
+        float a = 1.0f;
+        ContribList<Limits<MAXD>::MAXC> contribs; contribs.clear();
+        path_clear(prop.path);
+        const int minDepth = sc.opt.minDepth > 3 ? sc.opt.minDepth : 3;
+        generate_path_bidir(sc, minDepth, sc.opt.maxDepth, prop.path, contribs, rng);
+        prop.gaussianInitialized = 0;
+        if (contribs.n > 0) {
+            float cdf[Limits<MAXD>::MAXC + 1];
+            cdf[0] = 0.0f;
+            for (int i = 0; i < contribs.n; i++) cdf[i + 1] = cdf[i] + contribs.c[i].lsScore;
+            const float scoreSum = cdf[contribs.n];
+            const float invSc = inverse(scoreSum);
+            for (int i = 0; i <= contribs.n; i++) cdf[i] *= invSc;
+            const int it = upper_bound_f(cdf, contribs.n + 1, rng_uniform(rng));
+            const int contribId = dm_clampi(it - 1, 0, contribs.n - 1);
+            prop.sp = contribs.c[contribId];
+            prop.scoreSum = scoreSum;
+            if (cur.valid) {
+                const float probProposal = prop.sp.lsScore / prop.scoreSum;
+                const float probLast = ch.lastScore / ch.lastScoreSum;
+                a = dm_clamp((prop.sp.lsScore * probLast) / (cur.sp.lsScore * probProposal), 0.0f, 1.0f);
+            }
+            prop.nSplat = contribs.n;
+            for (int i = 0; i < contribs.n; i++) {
+                prop.splat[i].screenPos = contribs.c[i].screenPos;
+                prop.splat[i].contrib = contribs.c[i].contrib * (normalization / scoreSum);
+            }
+        } else {
+            a = 0.0f;
         }
-        prop.nSplat = contribs.n;
-        for (int i = 0; i < contribs.n; i++) {
-            prop.splat[i].screenPos = contribs.c[i].screenPos;
-            prop.splat[i].contrib = contribs.c[i].contrib * (normalization / scoreSum);
-        }
-    } else {
-        a = 0.0f;
+        ss.a = a;
+        return;
     }
-    return a;
+    ContribList<2> contribs; contribs.clear();
+    const int dim = path_dimension(cur.path);
+    if (ss.kind == STEP_ISO) {
+        path_copy(prop.path, cur.path);
+        NormalDist nd = normal_make(0.0f, sc.opt.perturbStdDev);
+        ch.lastMutationType = MUT_SMALL;
+        for (int i = 0; i < dim; i++) ss.offset[i] = normal_draw(nd, rng);
+        perturb_path_bidir(sc, ss.offset, prop.path, contribs, rng);
+        prop.gaussianInitialized = 0;
+        if (contribs.n > 0) {
+            prop.sp = contribs.c[0];
+            ss.a = dm_clamp(prop.sp.ssScore / cur.sp.ssScore, 0.0f, 1.0f);
+            prop.nSplat = 1;
+            prop.splat[0].screenPos = prop.sp.screenPos;
+            prop.splat[0].contrib = prop.sp.contrib * (normalization / prop.sp.lsScore);
+        } else {
+            ss.a = 0.0f;
+        }
+        return;
+    }
+    // STEP_MALA
+    ch.lastMutationType = MUT_MALA_SMALL;
+    if (!cur.gaussianInitialized) {
+        mala_finish_gaussian(sc, cur, ch, mala_grad_mode(sc, cur), ss.grad, ch.curr_new_v1, ch.curr_new_v2, cur.gaussian);
+        cur.gaussianInitialized = 1;
+    }
+    generate_sample(cur.gaussian, ss.offset, rng);
+    path_copy(prop.path, cur.path);
+    perturb_path_bidir(sc, ss.offset, prop.path, contribs, rng);
+    if (contribs.n > 0) {
+        prop.sp = contribs.c[0];
+        ss.hasContrib = 1;
+        if (mala_grad_mode(sc, prop) == 2) ss.needPropGrad = 1;
+    } else {
+        ss.a = 0.0f;
+    }
 }
 
 struct StepInfo {          // what one iteration did (parity traces / stats)
@@ -294,33 +328,26 @@ struct StepInfo {          // what one iteration did (parity traces / stats)
     float a;
 };
 
-// Per-run constants of the chain loop
-struct RunParams {
-    float normalization;
-    int numChains;
-    long long numSamplesThisChain;   // for the LS_RATIO large-step schedule (src/mlt.cpp:96)
-    const float *initLsScore;        // initStates[i].spContrib.lsScore (outlier reset, src/mlt.cpp:152-158)
-};
-
-// One iteration of the loop at src/mlt.cpp:91-170.  `cur` and `prop` are swapped by index:
-// the caller owns two MarkovState slots and `curIdx` says which one is current.
+// Phase 4: proposal Gaussian + MH ratio (src/mutation_mala.h:178-272), splats, acceptance test,
+// state swap, moment commit, outlier reset (src/mlt.cpp:103-170).
 template <int MAXD, class FILM>
-LMC_HD StepInfo chain_step(const Scene &sc, const RunParams &rp, int chainId, long long sampleIdx,
-                           MarkovState<MAXD> *states, int &curIdx, ChainVars<MAXD> &ch, Rng &rng, FILM &film,
-                           unsigned int *gradStats) {
+LMC_HD StepInfo phase_finish(const Scene &sc, const RunParams &rp, int chainId, long long sampleIdx,
+                             MarkovState<MAXD> *states, int &curIdx, ChainVars<MAXD> &ch, Rng &rng, FILM &film,
+                             StepScratch<MAXD> &ss) {
     MarkovState<MAXD> &cur = states[curIdx];
     MarkovState<MAXD> &prop = states[curIdx ^ 1];
-    float a = 1.0f;
-    bool isLargeStep = false;
-    const float lsScale = ((float)sampleIdx > (float)rp.numSamplesThisChain * sc.opt.lsRatio)
-                              ? sc.opt.largeStepProbScale : 1.0f;
-    if (!cur.valid || rng_uniform(rng) < sc.opt.largeStepProbability * lsScale) {
-        isLargeStep = true;
-        a = large_step_mutate(sc, rp.normalization, cur, prop, rng, ch);
-    } else {
-        if (sc.opt.mala) a = mala_small_step_mutate(sc, rp.normalization, cur, prop, rng, ch, gradStats);
-        else a = small_step_mutate(sc, rp.normalization, cur, prop, rng, ch);
+    if (ss.kind == STEP_MALA && ss.hasContrib) {
+        mala_finish_gaussian(sc, prop, ch, mala_grad_mode(sc, prop), ss.grad, ch.prop_new_v1, ch.prop_new_v2, prop.gaussian);
+        prop.gaussianInitialized = 1;
+        const float py = gaussian_log_pdf(ss.offset, 1.0f, cur.gaussian);
+        const float px = gaussian_log_pdf(ss.offset, -1.0f, prop.gaussian);
+        ss.a = dm_clamp(dm_exp(px - py) * prop.sp.ssScore / cur.sp.ssScore, 0.0f, 1.0f);
+        prop.nSplat = 1;
+        prop.splat[0].screenPos = prop.sp.screenPos;
+        prop.splat[0].contrib = prop.sp.contrib * rp.normalization / prop.sp.lsScore;
     }
+    const float a = ss.a;
+    const bool isLargeStep = ss.kind == STEP_LARGE;
     const int W = sc.cam.width, H = sc.cam.height;
     if (cur.valid && a < 1.0f) {
         for (int i = 0; i < cur.nSplat; i++) splat(film, W, H, cur.splat[i].screenPos, (1.0f - a) * cur.splat[i].contrib);
@@ -366,6 +393,19 @@ LMC_HD StepInfo chain_step(const Scene &sc, const RunParams &rp, int chainId, lo
         }
     }
     return info;
+}
+
+// One whole iteration of the loop at src/mlt.cpp:91-170 (host twin; the device runs the phases
+// as separate kernels).  `cur` and `prop` are swapped by index.
+template <int MAXD, class FILM>
+LMC_HD StepInfo chain_step(const Scene &sc, const RunParams &rp, int chainId, long long sampleIdx,
+                           MarkovState<MAXD> *states, int &curIdx, ChainVars<MAXD> &ch, Rng &rng, FILM &film,
+                           unsigned int *gradStats, StepScratch<MAXD> &ss) {
+    phase_begin(sc, rp, sampleIdx, states[curIdx], ch, rng, ss);
+    if (ss.needCurGrad) phase_gradient(sc, states[curIdx], ss, gradStats);
+    phase_propose(sc, rp, states[curIdx], states[curIdx ^ 1], ch, rng, ss);
+    if (ss.needPropGrad) phase_gradient(sc, states[curIdx ^ 1], ss, gradStats);
+    return phase_finish(sc, rp, chainId, sampleIdx, states, curIdx, ch, rng, film, ss);
 }
 
 }  // namespace lmc

@@ -194,7 +194,7 @@ struct ContribList {
 };
 
 template <class CL>
-LMC_HD void connect_to_camera(const Scene &sc, int lgtDepth, const BidirPathState &ps,
+LMC_HD_NOINLINE void connect_to_camera(const Scene &sc, int lgtDepth, const BidirPathState &ps,
                               const SurfaceVertex &lgtVertex, V3 prevPosition, CL &contribs) {
     Ray centerRay; float cmin, cmax;
     camera_sample_primary(sc.cam, mk2(0.5f, 0.5f), centerRay, cmin, cmax);
@@ -244,7 +244,7 @@ LMC_HD void connect_to_camera(const Scene &sc, int lgtDepth, const BidirPathStat
 
 // BSDFSampling<adjoint, perturb>.  `next` may alias `ps`.
 template <bool adjoint, bool perturb>
-LMC_HD bool bsdf_sampling(const Scene &sc, const BidirPathState &ps, SurfaceVertex &sv,
+LMC_HD_NOINLINE bool bsdf_sampling(const Scene &sc, const BidirPathState &ps, SurfaceVertex &sv,
                           BidirPathState &next, V3 &dir, V3 &bsdfContrib) {
     const int geom = sc.tris[sv.tid].geom;
     const BsdfParams bp = bsdf_params(sc, geom, sv.st);
@@ -290,7 +290,7 @@ LMC_HD bool bsdf_sampling(const Scene &sc, const BidirPathState &ps, SurfaceVert
 }
 
 template <int MAXD, class CL>
-LMC_HD void handle_hit_light(const Scene &sc, int camDepth, int light, bool hitSurface, const Ray &ray,
+LMC_HD_NOINLINE void handle_hit_light(const Scene &sc, int camDepth, int light, bool hitSurface, const Ray &ray,
                              V2 screenPos, const BidirPathState &ps, Path<MAXD> &path, CL &contribs) {
     int lPrimID = -1;
     V3 emission; float directPdf, emissionPdf;
@@ -318,7 +318,7 @@ LMC_HD void handle_hit_light(const Scene &sc, int camDepth, int light, bool hitS
 }
 
 template <class CL>
-LMC_HD void direct_lighting(const Scene &sc, int camDepth, const BidirPathState &ps, V2 screenPos,
+LMC_HD_NOINLINE void direct_lighting(const Scene &sc, int camDepth, const BidirPathState &ps, V2 screenPos,
                             float lightPickProb, SurfaceVertex &camVertex, CL &contribs) {
     const int light = camVertex.dlLight;
     V3 dirToLight, lightContrib; float dist, cosAtLight, directPdf, emissionPdf;
@@ -351,7 +351,7 @@ LMC_HD void direct_lighting(const Scene &sc, int camDepth, const BidirPathState 
 }
 
 template <class CL>
-LMC_HD void connect_vertex(const Scene &sc, int camDepth, int lgtDepth, const BidirPathState &lps,
+LMC_HD_NOINLINE void connect_vertex(const Scene &sc, int camDepth, int lgtDepth, const BidirPathState &lps,
                            const SurfaceVertex &lgtVertex, const BidirPathState &cps,
                            const SurfaceVertex &camVertex, V2 screenPos, CL &contribs) {
     V3 dirToLight = lps.isect.position - cps.isect.position;

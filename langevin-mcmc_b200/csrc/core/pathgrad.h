@@ -231,7 +231,7 @@ template <class T> struct ADPathState {
 // ---- shapes ------------------------------------------------------------------------------
 // Intersect (static mode): TriangleIntersect<FloatType>, src/trianglemesh.cpp:81-105.  `st` is
 // not produced: BSDF parameters arrive pre-evaluated in the buffer (textures are constants).
-template <class T> LMC_HD const float *ad_intersect(const float *buffer, const ADRay<T> &ray, ADIsect<T> &isect) {
+template <class T> LMC_HD_NOINLINE const float *ad_intersect(const float *buffer, const ADRay<T> &ray, ADIsect<T> &isect) {
     const float *b = buffer + 2;   // type, isMoving
     const V3 p0 = ld3(b), e1 = ld3(b + 3), e2 = ld3(b + 6), n0 = ld3(b + 9), n1 = ld3(b + 12), n2 = ld3(b + 15);
     isect.geomNormal = tv3c<T>(normalize(cross(e1, e2)));
@@ -250,7 +250,7 @@ template <class T> LMC_HD const float *ad_intersect(const float *buffer, const A
     return buffer + LMC_SER_SHAPE;
 }
 // SampleShape (static): SampleDirect<FloatType>, src/trianglemesh.cpp:313-327; pdf = invTotalArea
-template <class T> LMC_HD void ad_sample_shape(const float *buffer, const T &r0, const T &r1, TV3<T> &pos, TV3<T> &normal, float &pdf) {
+template <class T> LMC_HD_NOINLINE void ad_sample_shape(const float *buffer, const T &r0, const T &r1, TV3<T> &pos, TV3<T> &normal, float &pdf) {
     const float *b = buffer + 2;
     const V3 p0 = ld3(b), e1 = ld3(b + 3), e2 = ld3(b + 6), n0 = ld3(b + 9), n1 = ld3(b + 12), n2 = ld3(b + 15);
     const float adEps = 1e-6f;   // ADEpsilon<ADFloat>()
@@ -263,12 +263,12 @@ template <class T> LMC_HD void ad_sample_shape(const float *buffer, const T &r0,
 }
 
 // ---- BSDF twins ----------------------------------------------------------------------------
-template <class T> LMC_HD T ad_beckmann_D(const TV3<T> &localH, const T &alphaU, const T &alphaV) {
+template <class T> LMC_HD_NOINLINE T ad_beckmann_D(const TV3<T> &localH, const T &alphaU, const T &alphaV) {
     const T cosTheta2 = ad_square(localH.z);
     const T e = (ad_square(localH.x) / ad_square(alphaU) + ad_square(localH.y) / ad_square(alphaV)) / cosTheta2;
     return ad_exp(-e) / (LMC_PI * alphaU * alphaV * ad_square(cosTheta2));
 }
-template <class T> LMC_HD T ad_beckmann_G1(float alpha, const T &cosTheta) {
+template <class T> LMC_HD_NOINLINE T ad_beckmann_G1(float alpha, const T &cosTheta) {
     const T tanTheta = ad_sqrt(ad_fabs((1.0f + 1e-6f) - ad_square(cosTheta))) / cosTheta;
     if (ad_val(tanTheta) <= 0.0f) return ad_const<T>(1.0f);
     const T a = ad_inverse(alpha * tanTheta);
@@ -276,7 +276,7 @@ template <class T> LMC_HD T ad_beckmann_G1(float alpha, const T &cosTheta) {
     const T aSqr = ad_square(a);
     return (3.535f * a + 2.181f * aSqr) / (1.0f + 2.276f * a + 2.577f * aSqr);
 }
-template <class T> LMC_HD T ad_fresnel(const T &cosThetaI_, T &cosThetaT_, float eta, float invEta) {
+template <class T> LMC_HD_NOINLINE T ad_fresnel(const T &cosThetaI_, T &cosThetaT_, float eta, float invEta) {
     const float scale = (ad_val(cosThetaI_) > 0.0f) ? invEta : eta;
     const T cosThetaTSqr = 1.0f - (1.0f - ad_square(cosThetaI_)) * (scale * scale);
     if (ad_val(cosThetaTSqr) <= 0.0f) { cosThetaT_ = ad_const<T>(0.0f); return ad_const<T>(1.0f); }
@@ -308,7 +308,7 @@ template <class T> LMC_HD void ad_face_normal(const TV3<T> &normal, T &cosWi, TV
 }
 
 // buffer points at the BSDF record (type first)
-template <class T> LMC_HD void ad_evaluate_bsdf(bool adjoint, const float *buffer, const TV3<T> &wi, const TV3<T> &normal,
+template <class T> LMC_HD_NOINLINE void ad_evaluate_bsdf(bool adjoint, const float *buffer, const TV3<T> &wi, const TV3<T> &normal,
                                                 const TV3<T> &wo, TV3<T> &contrib, T &cosWo, T &pdf, T &revPdf) {
     const int type = (int)buffer[0];
     const float *b = buffer + 1;
@@ -385,7 +385,7 @@ template <class T> LMC_HD void ad_evaluate_bsdf(bool adjoint, const float *buffe
     }
 }
 
-template <class T> LMC_HD void ad_sample_bsdf(bool adjoint, const float *buffer, const TV3<T> &wi, const TV3<T> &normal,
+template <class T> LMC_HD_NOINLINE void ad_sample_bsdf(bool adjoint, const float *buffer, const TV3<T> &wi, const TV3<T> &normal,
                                               const T &r0, const T &r1, float uDiscrete, TV3<T> &wo, TV3<T> &contrib,
                                               T &cosWo, T &pdf, T &revPdf) {
     const int type = (int)buffer[0];
@@ -520,7 +520,7 @@ struct ADEnvRec {
     V3 img00, img10, img01, img11;
     float rowWeight0, rowWeight1, normalization;
 };
-LMC_HD ADEnvRec ad_env_deserialize(const float *buffer) {
+LMC_HD_NOINLINE ADEnvRec ad_env_deserialize(const float *buffer) {
     ADEnvRec e;
     const float *b = buffer + 1;
     e.toWorld = ser_static_matrix(b); e.toLight = ser_static_matrix(b + 15);
@@ -531,7 +531,7 @@ LMC_HD ADEnvRec ad_env_deserialize(const float *buffer) {
     e.rowWeight0 = b[20]; e.rowWeight1 = b[21]; e.normalization = b[22];
     return e;
 }
-template <class T> LMC_HD void ad_env_sample_direction(const ADEnvRec &e, const T &r0, const T &r1, TV3<T> &dirToLight,
+template <class T> LMC_HD_NOINLINE void ad_env_sample_direction(const ADEnvRec &e, const T &r0, const T &r1, TV3<T> &dirToLight,
                                                        TV3<T> &value, T &pdf) {
     const T u0 = (r0 - e.cdfCol0) / (e.cdfCol1 - e.cdfCol0);
     const T u1 = (r1 - e.cdfRow0) / (e.cdfRow1 - e.cdfRow0);
@@ -550,7 +550,7 @@ template <class T> LMC_HD void ad_env_sample_direction(const ADEnvRec &e, const 
 }
 
 // SampleDirect twin; buffer points at the light record
-template <class T> LMC_HD void ad_sample_direct(const float *buffer, const ADScene &scn, const TV3<T> &pos, const T &r0,
+template <class T> LMC_HD_NOINLINE void ad_sample_direct(const float *buffer, const ADScene &scn, const TV3<T> &pos, const T &r0,
                                                 const T &r1, TV3<T> &dirToLight, TV3<T> &lightContrib, T &cosAtLight,
                                                 T &directPdf, T &emissionPdf) {
     const int type = (int)buffer[0];
@@ -587,7 +587,7 @@ template <class T> LMC_HD void ad_sample_direct(const float *buffer, const ADSce
     }
 }
 // Emission twin
-template <class T> LMC_HD void ad_emission(const float *buffer, const ADScene &scn, const TV3<T> &dirToLight,
+template <class T> LMC_HD_NOINLINE void ad_emission(const float *buffer, const ADScene &scn, const TV3<T> &dirToLight,
                                            const TV3<T> &normalOnLight, TV3<T> &emission, T &directPdf, T &emissionPdf) {
     const int type = (int)buffer[0];
     if (type == LIGHT_AREA) {
@@ -624,7 +624,7 @@ template <class T> LMC_HD void ad_sample_concentric_disc(const T &r0, const T &r
     ox = r * ad_cos(phi); oy = r * ad_sin(phi);
 }
 // Emit twin
-template <class T> LMC_HD void ad_emit(const float *buffer, const ADScene &scn, const T &p0, const T &p1, const T &d0,
+template <class T> LMC_HD_NOINLINE void ad_emit(const float *buffer, const ADScene &scn, const T &p0, const T &p1, const T &d0,
                                        const T &d1, ADRay<T> &ray, TV3<T> &emission, T &cosAtLight, T &emissionPdf,
                                        T &directPdf) {
     const int type = (int)buffer[0];
@@ -676,7 +676,7 @@ template <class T> LMC_HD void ad_convert_mis(const ADRay<T> &ray, ADPathState<T
 }
 
 // BSDFSampling<adjoint, fixedDiscrete = false> without light-coordinate sampling
-template <class T> LMC_HD const float *ad_bsdf_sampling(bool adjoint, const float *buffer, const T &r0, const T &r1,
+template <class T> LMC_HD_NOINLINE const float *ad_bsdf_sampling(bool adjoint, const float *buffer, const T &r0, const T &r1,
                                                         float bsdfDiscrete, float useAbsoluteParam, ADPathState<T> &ps,
                                                         TV3<T> &dir) {
     TV3<T> bsdfContrib; T cosWo, bsdfPdf, bsdfRevPdf, jacobian;
@@ -701,7 +701,7 @@ template <class T> LMC_HD const float *ad_bsdf_sampling(bool adjoint, const floa
 // The path function: log(Luminance(contrib)) of a (camDepth, lightDepth) path.
 // primary: D+1 values (time first); `pss` carries primary[1..D] as T (seeded duals or floats).
 template <class T>
-LMC_HD T eval_path_loglum(int maxCamDepth, int maxLightDepth, const float *sceneBuf, const float *vertParams, const T *pss) {
+LMC_HD_NOINLINE T eval_path_loglum(int maxCamDepth, int maxLightDepth, const float *sceneBuf, const float *vertParams, const T *pss) {
     const ADScene scn = ad_scene_deserialize(sceneBuf);
     const float *buffer = vertParams + 3;   // lensVertexPos
     int pi = 0;

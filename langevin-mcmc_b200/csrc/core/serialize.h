@@ -14,7 +14,7 @@ namespace lmc {
 LMC_HD void st3(float *b, V3 v) { b[0] = v.x; b[1] = v.y; b[2] = v.z; }
 
 // 46 floats
-LMC_HD void serialize_shape(const Scene &sc, int tid, float *b) {
+LMC_HD_NOINLINE void serialize_shape(const Scene &sc, int tid, float *b) {
     const TriGeom &tg = sc.tris[tid];
     const TriShade &ts = sc.shade[tid];
     const Material &m = sc.mats[tg.geom];
@@ -30,7 +30,7 @@ LMC_HD void serialize_shape(const Scene &sc, int tid, float *b) {
 }
 
 // 10 floats (padded)
-LMC_HD void serialize_bsdf(const Scene &sc, int tid, V2 st, float *b) {
+LMC_HD_NOINLINE void serialize_bsdf(const Scene &sc, int tid, V2 st, float *b) {
     const BsdfParams p = bsdf_params(sc, sc.tris[tid].geom, st);
     for (int i = 0; i < LMC_SER_BSDF; i++) b[i] = 0.0f;
     b[0] = (float)p.type;
@@ -40,7 +40,7 @@ LMC_HD void serialize_bsdf(const Scene &sc, int tid, V2 st, float *b) {
 }
 
 // 56 floats (padded)
-LMC_HD void serialize_light(const Scene &sc, int light, int lPrimID, float *b) {
+LMC_HD_NOINLINE void serialize_light(const Scene &sc, int light, int lPrimID, float *b) {
     for (int i = 0; i < LMC_SER_LIGHT; i++) b[i] = 0.0f;
     const Light &l = sc.lights[light];
     b[0] = (float)l.type;
@@ -73,7 +73,7 @@ LMC_HD int serialized_vert_size(int camDepth, int lgtDepth) {
 
 // Serialize(scene, path, subPath): returns the number of vertParams floats written
 template <int MAXD>
-LMC_HD int serialize_path(const Scene &sc, const Path<MAXD> &path, float *primary, float *vertParams) {
+LMC_HD_NOINLINE int serialize_path(const Scene &sc, const Path<MAXD> &path, float *primary, float *vertParams) {
     int pi = 0;
     primary[pi++] = path.time;
     float *b = vertParams;

@@ -78,6 +78,8 @@ struct lmc_ctx {
     // film
     float *film = nullptr; bool filmOwned = false;
     unsigned long long *statsDev = nullptr;
+    WaveLists wl{};
+    int listCap = 0;
     uint64_t launches = 0;
     double lastMs = 0.0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -91,6 +93,13 @@ int chains_begin(lmc_ctx *c) {
     if (c->states && c->stateBytes != bytes) { cudaFree(c->states); c->states = nullptr; }
     if (!c->states) { CK(cudaMalloc(&c->states, bytes)); c->stateBytes = bytes; }
     uint32_t *st = (uint32_t *)c->states;
+    if (c->listCap < n) {
+        if (c->wl.large) { cudaFree(c->wl.large); c->wl.large = nullptr; }
+        CK(cudaMalloc((void **)&c->wl.large, sizeof(int) * (size_t)n * 4 + 64));
+        c->wl.small_ = c->wl.large + n; c->wl.curGrad = c->wl.small_ + n; c->wl.propGrad = c->wl.curGrad + n;
+        c->wl.counts = c->wl.propGrad + n;
+        c->listCap = n;
+    }
     c->launches++;
     CK(d == 4 ? launch_chain_init_4(c->stream, st, n, c->desc.chain_base, c->initLs)
               : (d == 8 ? launch_chain_init_8(c->stream, st, n, c->desc.chain_base, c->initLs)
@@ -105,10 +114,11 @@ int run_chains(lmc_ctx *c, long long numSteps, unsigned char *dTrace, float *dAT
     rp.numSamplesThisChain = c->desc.samples_per_chain; rp.initLsScore = c->initLs;
     uint32_t *st = (uint32_t *)c->states;
     CK(cudaEventRecord(c->ev0, c->stream));
-    c->launches++;
-    CK(d == 4 ? launch_chain_run_4(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace)
-              : (d == 8 ? launch_chain_run_8(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace)
-                        : launch_chain_run_12(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace)));
+    unsigned long long nl = 0;
+    CK(d == 4 ? launch_chain_run_4(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl)
+              : (d == 8 ? launch_chain_run_8(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl)
+                        : launch_chain_run_12(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl)));
+    c->launches += nl;
     CK(cudaEventRecord(c->ev1, c->stream));
     return LMC_OK;
 }
@@ -232,6 +242,7 @@ void lmc_destroy(lmc_ctx *c) {
     if (c->initLs) cudaFree(c->initLs);
     if (c->film && c->filmOwned) cudaFree(c->film);
     if (c->statsDev) cudaFree(c->statsDev);
+    if (c->wl.large) cudaFree(c->wl.large);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;

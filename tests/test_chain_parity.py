@@ -116,6 +116,6 @@ def test_cuda_full_size_properties(lmc, torus_xml):
     mean = float(film.sum()) / (chains * steps) / 3.0
     assert 0.2 * norm < mean < 5.0 * norm
     # the first 1024 chains of the big job are the chains of a 1024-chain job (seed = chain id)
-    ctx.begin(1024, norm, init_ls[:1024], total_chains=chains, samples_per_chain=steps)
+    ctx.begin(1024, norm, init_ls, total_chains=chains, samples_per_chain=steps)
     t_small, _ = ctx.run(steps, trace=True)
     assert ((t_small[:, 0] & 3) == 0).all()
