@@ -79,6 +79,7 @@ struct lmc_ctx {
     float *film = nullptr; bool filmOwned = false;
     unsigned long long *statsDev = nullptr;
     WaveLists wl{};
+    int *listMem = nullptr;
     int listCap = 0;
     uint64_t launches = 0;
     double lastMs = 0.0;
@@ -92,12 +93,22 @@ int chains_begin(lmc_ctx *c) {
     const size_t bytes = (d == 4 ? chain_state_bytes_4() : (d == 8 ? chain_state_bytes_8() : chain_state_bytes_12())) * (size_t)n;
     if (c->states && c->stateBytes != bytes) { cudaFree(c->states); c->states = nullptr; }
     if (!c->states) { CK(cudaMalloc(&c->states, bytes)); c->stateBytes = bytes; }
-    uint32_t *st = (uint32_t *)c->states;
+    void *st = c->states;
     if (c->listCap < n) {
-        if (c->wl.large) { cudaFree(c->wl.large); c->wl.large = nullptr; }
-        CK(cudaMalloc((void **)&c->wl.large, sizeof(int) * (size_t)n * 4 + 64));
-        c->wl.small_ = c->wl.large + n; c->wl.curGrad = c->wl.small_ + n; c->wl.propGrad = c->wl.curGrad + n;
-        c->wl.counts = c->wl.propGrad + n;
+        if (c->listMem) { cudaFree(c->listMem); c->listMem = nullptr; }
+        // per sorted list: keys[n] + list[n] + hist/offsets/cursor[NKEYS] + count; plus the large list
+        const size_t per = (size_t)n * 2 + 3 * LMC_NKEYS + 4;
+        const size_t total = per * 3 + (size_t)n + 4;
+        CK(cudaMalloc((void **)&c->listMem, sizeof(int) * total));
+        CK(cudaMemsetAsync(c->listMem, 0, sizeof(int) * total, c->stream));
+        int *p = c->listMem;
+        SortList *sls[3] = {&c->wl.small_, &c->wl.curGrad, &c->wl.propGrad};
+        for (int k = 0; k < 3; k++) {
+            SortList &sl = *sls[k];
+            sl.keys = p; p += n; sl.list = p; p += n; sl.hist = p; p += LMC_NKEYS; sl.offsets = p; p += LMC_NKEYS;
+            sl.cursor = p; p += LMC_NKEYS; sl.count = p; p += 4;
+        }
+        c->wl.large = p; p += n; c->wl.largeCount = p;
         c->listCap = n;
     }
     c->launches++;
@@ -112,7 +123,7 @@ int run_chains(lmc_ctx *c, long long numSteps, unsigned char *dTrace, float *dAT
     const int d = c->maxdTemplate;
     RunParams rp; rp.normalization = c->desc.normalization; rp.numChains = c->desc.total_chains;
     rp.numSamplesThisChain = c->desc.samples_per_chain; rp.initLsScore = c->initLs;
-    uint32_t *st = (uint32_t *)c->states;
+    void *st = c->states;
     CK(cudaEventRecord(c->ev0, c->stream));
     unsigned long long nl = 0;
     CK(d == 4 ? launch_chain_run_4(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl)
@@ -126,7 +137,7 @@ int run_chains(lmc_ctx *c, long long numSteps, unsigned char *dTrace, float *dAT
 int chain_stats(lmc_ctx *c) {
     const int n = c->desc.num_chains;
     const int d = c->maxdTemplate;
-    const uint32_t *st = (const uint32_t *)c->states;
+    const void *st = c->states;
     CK(cudaMemsetAsync(c->statsDev, 0, 10 * sizeof(unsigned long long), c->stream));
     c->launches++;
     CK(d == 4 ? launch_chain_stats_4(c->stream, st, n, c->statsDev)
@@ -242,7 +253,7 @@ void lmc_destroy(lmc_ctx *c) {
     if (c->initLs) cudaFree(c->initLs);
     if (c->film && c->filmOwned) cudaFree(c->film);
     if (c->statsDev) cudaFree(c->statsDev);
-    if (c->wl.large) cudaFree(c->wl.large);
+    if (c->listMem) cudaFree(c->listMem);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
