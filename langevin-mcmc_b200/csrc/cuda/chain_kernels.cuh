@@ -138,13 +138,10 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_begin(const __grid_con
     int kind = -1;
     if (active) {
         uint32_t tab[64];
-        ChainRec<MAXD> r;
-        state_load<MAXD>(states, i, r);
-        ChainState<MAXD> &cs = r.cs;
+        ChainState<MAXD> &cs = states[i].cs;     // phases touch a few sectors of the record: work in place
         Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
         phase_begin(sc, rp, cs.sampleIdx, cs.st[cs.curIdx], cs.ch, rng, cs.ss);
         rng_close(rng, cs);
-        state_store<MAXD>(states, i, r);
         kind = cs.ss.kind;
         const Path<MAXD> &p = cs.st[cs.curIdx].path;
         sort_key_set(wl.small_, i, kind == STEP_LARGE ? -1 : class_key(p.camDepth, p.lgtDepth, kind == STEP_MALA ? 1 : 0));
@@ -160,10 +157,8 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_grad(const __grid_cons
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= *count) return;
     const int i = list[t];
-    ChainRec<MAXD> r;
-    state_load<MAXD>(states, i, r);
-    phase_gradient(sc, r.cs.st[r.cs.curIdx ^ which], r.cs.ss, r.cs.gradStats);
-    state_store<MAXD>(states, i, r);
+    ChainState<MAXD> &cs = states[i].cs;
+    phase_gradient(sc, cs.st[cs.curIdx ^ which], cs.ss, cs.gradStats);
 }
 
 template <int MAXD>
@@ -174,13 +169,10 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_propose(const __grid_c
     if (t >= *count) return;
     const int i = list[t];
     uint32_t tab[64];
-    ChainRec<MAXD> r;
-    state_load<MAXD>(states, i, r);
-    ChainState<MAXD> &cs = r.cs;
+    ChainState<MAXD> &cs = states[i].cs;
     Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
     phase_propose(sc, rp, cs.st[cs.curIdx], cs.st[cs.curIdx ^ 1], cs.ch, rng, cs.ss);
     rng_close(rng, cs);
-    state_store<MAXD>(states, i, r);
     const MarkovState<MAXD> &prop = cs.st[cs.curIdx ^ 1];
     sort_key_set(wl.propGrad, i, cs.ss.needPropGrad ? class_key(prop.sp.camDepth, prop.sp.lightDepth, 0) : -1);
 }
@@ -193,16 +185,13 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_finish(const __grid_co
     if (i >= n) return;
     uint32_t tab[64];
     DevFilm df; df.p = film;
-    ChainRec<MAXD> r;
-    state_load<MAXD>(states, i, r);
-    ChainState<MAXD> &cs = r.cs;
+    ChainState<MAXD> &cs = states[i].cs;
     Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
     const StepInfo info = phase_finish(sc, rp, chainBase + i, cs.sampleIdx, cs.st, cs.curIdx, cs.ch, rng, df, cs.ss);
     rng_close(rng, cs);
     cs.nPropose[info.mutationType] += 1u;
     cs.nAccept[info.mutationType] += (unsigned int)info.accepted;
     cs.sampleIdx += 1;
-    state_store<MAXD>(states, i, r);
     if (trace) trace[(size_t)i * numSteps + stepInLaunch] = (unsigned char)(info.mutationType | (info.accepted << 2) | ((info.a > 0.0f) ? 8 : 0));
     if (aTrace) aTrace[(size_t)i * numSteps + stepInLaunch] = info.a;
 }
