@@ -38,7 +38,7 @@ class _RunDesc(ctypes.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "liblmc_b200.so")
+    return os.environ.get("LMC_B200_LIB", os.path.join(_HERE, "liblmc_b200.so"))
 
 
 def load_library():

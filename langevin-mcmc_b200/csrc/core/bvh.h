@@ -20,9 +20,24 @@ struct Hit {
     float t, u, v;
 };
 
+// 16-byte loads (read-only data path on the device)
+struct F4 { float x, y, z, w; };
+LMC_HD F4 ld4(const void *p) {
+#if defined(__CUDA_ARCH__)
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#else
+    F4 r; memcpy(&r, p, 16); return r;
+#endif
+}
+// min / max that lower to single FMNMX instructions; IEEE fmin/fmax semantics on both sides
+LMC_HD float bmin(float a, float b) { return fminf(a, b); }
+LMC_HD float bmax(float a, float b) { return fmaxf(a, b); }
+
 LMC_HD bool tri_test(const TriGeom &tg, const Ray &ray, float minT, float maxT,
                      float &t, float &u, float &v) {
-    const V3 p0 = ld3(tg.p0), e1 = ld3(tg.e1), e2 = ld3(tg.e2);
+    const F4 q0 = ld4(tg.p0), q1 = ld4(tg.e1), q2 = ld4(tg.e2);
+    const V3 p0 = mk3(q0.x, q0.y, q0.z), e1 = mk3(q1.x, q1.y, q1.z), e2 = mk3(q2.x, q2.y, q2.z);
     const V3 s1 = cross(ray.dir, e2);
     const float divisor = dot(s1, e1);
     if (divisor == 0.0f) return false;
@@ -36,47 +51,64 @@ LMC_HD bool tri_test(const TriGeom &tg, const Ray &ray, float minT, float maxT,
     return (t >= minT && t <= maxT);
 }
 
-LMC_HD bool box_test(const float *bmin, const float *bmax, const V3 &org, const V3 &invDir,
-                     float minT, float maxT, float &tNear) {
-    float t0 = (bmin[0] - org.x) * invDir.x, t1 = (bmax[0] - org.x) * invDir.x;
-    float lo = dm_min(t0, t1), hi = dm_max(t0, t1);
-    t0 = (bmin[1] - org.y) * invDir.y; t1 = (bmax[1] - org.y) * invDir.y;
-    lo = dm_max(lo, dm_min(t0, t1)); hi = dm_min(hi, dm_max(t0, t1));
-    t0 = (bmin[2] - org.z) * invDir.z; t1 = (bmax[2] - org.z) * invDir.z;
-    lo = dm_max(lo, dm_min(t0, t1)); hi = dm_min(hi, dm_max(t0, t1));
-    lo = dm_max(lo, minT); hi = dm_min(hi, maxT);
+// Slab test of one child box.  t = b * invDir - org * invDir evaluated with ONE fused
+// multiply-add per plane (fmaf is correctly rounded on x86-64 and sm_100a alike, so the host twin
+// takes the same traversal decisions).  Conservative culling only: hit results always come from
+// tri_test.
+LMC_HD bool box_test(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz, const V3 &invDir,
+                     const V3 &negOrgInv, float minT, float maxT, float &tNear) {
+    float t0 = fmaf(bminx, invDir.x, negOrgInv.x), t1 = fmaf(bmaxx, invDir.x, negOrgInv.x);
+    float lo = bmin(t0, t1), hi = bmax(t0, t1);
+    t0 = fmaf(bminy, invDir.y, negOrgInv.y); t1 = fmaf(bmaxy, invDir.y, negOrgInv.y);
+    lo = bmax(lo, bmin(t0, t1)); hi = bmin(hi, bmax(t0, t1));
+    t0 = fmaf(bminz, invDir.z, negOrgInv.z); t1 = fmaf(bmaxz, invDir.z, negOrgInv.z);
+    lo = bmax(lo, bmin(t0, t1)); hi = bmin(hi, bmax(t0, t1));
+    lo = bmax(lo, minT); hi = bmin(hi, maxT);
     tNear = lo;
     return lo <= hi;
 }
 
-#define LMC_BVH_STACK 48
+#define LMC_BVH_STACK 32
+#define LMC_BVH_DONE ((int)0x80000000)
 
+// "while-while" traversal: every lane first descends through inner nodes until it holds a leaf
+// (or runs out of work), then all lanes intersect their leaves together -- the two loop bodies no
+// longer serialise against each other inside a warp.
 template <bool ANY_HIT>
 LMC_HD_NOINLINE Hit bvh_traverse(const Scene &sc, const Ray &ray, float minT, float maxT) {
     Hit best; best.tid = -1; best.t = maxT; best.u = 0.0f; best.v = 0.0f;
     if (sc.numNodes == 0) return best;
     const V3 invDir = mk3(inverse(ray.dir.x), inverse(ray.dir.y), inverse(ray.dir.z));
+    const V3 negOrgInv = mk3(-(ray.org.x * invDir.x), -(ray.org.y * invDir.y), -(ray.org.z * invDir.z));
     int stack[LMC_BVH_STACK];
     int sp = 0;
     int cur = 0;
     for (;;) {
-        if (cur >= 0) {
-            const BvhNode &n = sc.nodes[cur];
+        while (cur >= 0) {
+            const BvhNode *n = sc.nodes + cur;
+            const F4 a = ld4(&n->lmin[0]);     // lmin.xyz, lmax.x
+            const F4 b = ld4(&n->lmax[1]);     // lmax.yz, rmin.xy
+            const F4 c = ld4(&n->rmin[2]);     // rmin.z, rmax.xyz
+            const F4 d = ld4(&n->left);        // left, right, pad
             float tl, tr;
-            const bool hl = box_test(n.lmin, n.lmax, ray.org, invDir, minT, best.t, tl);
-            const bool hr = box_test(n.rmin, n.rmax, ray.org, invDir, minT, best.t, tr);
+            const bool hl = box_test(a.x, a.y, a.z, a.w, b.x, b.y, invDir, negOrgInv, minT, best.t, tl);
+            const bool hr = box_test(b.z, b.w, c.x, c.y, c.z, c.w, invDir, negOrgInv, minT, best.t, tr);
+            const int left = (int)f2u(d.x), right = (int)f2u(d.y);
             if (hl && hr) {
-                int nearC = n.left, farC = n.right;
-                if (tr < tl) { nearC = n.right; farC = n.left; }
+                const bool swap = tr < tl;
+                const int nearC = swap ? right : left, farC = swap ? left : right;
                 if (sp < LMC_BVH_STACK) stack[sp++] = farC;
                 cur = nearC;
-                continue;
             } else if (hl) {
-                cur = n.left; continue;
+                cur = left;
             } else if (hr) {
-                cur = n.right; continue;
+                cur = right;
+            } else {
+                cur = (sp > 0) ? stack[--sp] : LMC_BVH_DONE;
             }
-        } else {
+        }
+        if (cur == LMC_BVH_DONE) break;
+        {
             const int enc = ~cur;
             const int first = enc >> 3;
             const int count = (enc & 7) + 1;
@@ -91,8 +123,7 @@ LMC_HD_NOINLINE Hit bvh_traverse(const Scene &sc, const Ray &ray, float minT, fl
                 }
             }
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
+        cur = (sp > 0) ? stack[--sp] : LMC_BVH_DONE;
     }
     return best;
 }

@@ -151,8 +151,14 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_begin(const __grid_con
 }
 
 // gradient of the current state (which = 0) or of the proposal (which = 1) for a sorted list
+#ifndef LMC_GRAD_MINB
+#define LMC_GRAD_MINB 2
+#endif
+#ifndef LMC_PROP_MINB
+#define LMC_PROP_MINB 4
+#endif
 template <int MAXD>
-__global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_grad(const __grid_constant__ Scene sc, ChainRec<MAXD> *states, int n,
+__global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_GRAD_MINB) k_wave_grad(const __grid_constant__ Scene sc, ChainRec<MAXD> *states, int n,
                                                                 const int *list, const int *count, int which) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= *count) return;
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_grad(const __grid_cons
 }
 
 template <int MAXD>
-__global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_propose(const __grid_constant__ Scene sc, RunParams rp, int chainBase,
+__global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_PROP_MINB) k_wave_propose(const __grid_constant__ Scene sc, RunParams rp, int chainBase,
                                                                    ChainRec<MAXD> *states, int n, const int *list, const int *count,
                                                                    WaveLists wl) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
