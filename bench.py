@@ -35,6 +35,9 @@ CHAINS_PER_GPU = 1 << 20
 MUTATIONS_PER_STEP = 32
 # canonical state words S_LMC(L) = 14 L + 21; bytes per mutation = 8 S + 48
 ALGO_BYTES_PER_MUTATION = 8 * (14 * MAXDEPTH + 21) + 48   # 1112 B at L = 8
+# dram__bytes_read.sum + dram__bytes_write.sum of the 10 kernels of one iteration over 2^20 chains
+# (ncu, profiles/r01_launches_wavefront_2p20.csv): 10.79 GB / 2^20 mutations
+DRAM_BYTES_PER_MUTATION_NCU = 10.79e9 / (1 << 20)
 
 
 def load_package():
@@ -258,7 +261,9 @@ def main():
                 "gpu_launches": int(launches),
                 "clocks": sampler.result(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "k_chain_run<8>", "algorithmic_bytes_per_mutation": ALGO_BYTES_PER_MUTATION,
+                             "traffic": DRAM_BYTES_PER_MUTATION_NCU * float(n_local) * M,
+                             "kernel": "chain iteration = k_wave_{begin,grad,propose,finish}<8> (one lmc_run_chains call)",
+                             "algorithmic_bytes_per_mutation": ALGO_BYTES_PER_MUTATION,
                              "kernel_ms_per_launch": k_ms, "peak_source": peak_src,
                              "per_gpu_mutations_per_s": per_gpu_rate},
                 "stats": {"accepted": st["accepted"], "proposed": st["proposed"], "gradient_evals": st["gradient_evals"],
