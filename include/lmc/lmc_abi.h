@@ -117,9 +117,11 @@ int lmc_film_bind(lmc_ctx *ctx, void *device_ptr);
 /* n serialized paths of class (cam_depth, light_depth) in the reference's buffer layout
  * (SURVEY.md App. A.4): lens n x 2, primary n x (D+1) [time first], vert_params n x
  * vert_stride, scene = lmc_scene_serialized().  HOST pointers.  Outputs: log_lum[n] =
- * log(Luminance(contrib)); grad n x D (or NULL). */
+ * log(Luminance(contrib)); grad n x D (or NULL); hess n x D x D row-major (or NULL; needs grad, D <= 16) --
+ * the vGrad / vHess of PathFuncDerv (src/path.h:122-123, src/mutation_h2mc.h:74-79). */
 int lmc_eval_batch(lmc_ctx *ctx, int32_t cam_depth, int32_t light_depth, int32_t n, const float *lens,
-                   const float *primary, const float *vert_params, int32_t vert_stride, float *log_lum, float *grad);
+                   const float *primary, const float *vert_params, int32_t vert_stride, float *log_lum, float *grad,
+                   float *hess);
 /* size of one vert_params record for class (c, l): GetVertParamSize, src/path.cpp:2485-2495 */
 int32_t lmc_vert_param_size(int32_t cam_depth, int32_t light_depth);
 

@@ -67,7 +67,7 @@ def load_library():
         "lmc_get_stats": (i32, [vp, ctypes.POINTER(_Stats)]),
         "lmc_film_clear": (i32, [vp]), "lmc_film_read": (i32, [vp, vp]),
         "lmc_film_device_ptr": (i32, [vp, ctypes.POINTER(vp)]), "lmc_film_bind": (i32, [vp, vp]),
-        "lmc_eval_batch": (i32, [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
+        "lmc_eval_batch": (i32, [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
         "lmc_vert_param_size": (i32, [i32, i32]),
         "lmc_bvh_probe": (i32, [vp, i32, vp, f32, f32, i32, vp, vp, vp]),
     }
@@ -217,16 +217,19 @@ class ChainContext:
     def film_bind(self, device_ptr):
         _check(load_library().lmc_film_bind(self._c, ctypes.c_void_p(int(device_ptr))))
 
-    def eval_batch(self, cam_depth, light_depth, lens, primary, vert_params, want_grad=True):
+    def eval_batch(self, cam_depth, light_depth, lens, primary, vert_params, want_grad=True, want_hess=False):
         lens = np.ascontiguousarray(lens, np.float32)
         primary = np.ascontiguousarray(primary, np.float32)
         vert_params = np.ascontiguousarray(vert_params, np.float32)
         n = lens.shape[0]
         dim = primary.shape[1] - 1
         log_lum = np.zeros(n, np.float32)
-        grad = np.zeros((n, dim), np.float32) if want_grad else None
+        grad = np.zeros((n, dim), np.float32) if (want_grad or want_hess) else None
+        hess = np.zeros((n, dim, dim), np.float32) if want_hess else None
         _check(load_library().lmc_eval_batch(self._c, int(cam_depth), int(light_depth), n, _ptr(lens), _ptr(primary),
-                                             _ptr(vert_params), int(vert_params.shape[1]), _ptr(log_lum), _ptr(grad)))
+                                             _ptr(vert_params), int(vert_params.shape[1]), _ptr(log_lum), _ptr(grad), _ptr(hess)))
+        if want_hess:
+            return log_lum, grad, hess
         return log_lum, grad
 
     def bvh_probe(self, rays, tmin, tmax, any_hit=False):

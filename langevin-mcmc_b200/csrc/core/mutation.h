@@ -146,7 +146,180 @@ LMC_HD void splat(FILM &film, int width, int height, V2 screenPos, V3 contrib) {
 //   [u_large if cur.valid] -> Mutate{ u_mix -> D normals -> PerturbPathBidir normals } -> [u_accept if a > 0]
 // The gradient phases draw nothing.
 // ------------------------------------------------------------------------------------------
-enum StepKind { STEP_LARGE = 0, STEP_ISO = 1, STEP_MALA = 2 };
+enum StepKind { STEP_LARGE = 0, STEP_ISO = 1, STEP_MALA = 2, STEP_H2MC = 3 };
+
+// ---- H2MC (src/mutation_h2mc.h, src/h2mc.cpp): dense Gaussians live beside the chain record -----
+#define LMC_H2MC_DIM LMC_HESS_MAXDIM      // 16: derivative functions exist for c + l - 1 <= 8
+struct H2mcSide {
+    float hess[LMC_H2MC_DIM * LMC_H2MC_DIM];          // scratch: Hessian of the state being initialised
+    float covL[2][LMC_H2MC_DIM * LMC_H2MC_DIM];       // per MarkovState slot, row-major dim x dim
+    float invCov[2][LMC_H2MC_DIM * LMC_H2MC_DIM];
+    int dense[2];                                      // slot holds a dense Gaussian (else the diagonal fields are used)
+};
+
+// Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major, destroyed).
+// Replaces Eigen::SelfAdjointEigenSolver (src/h2mc.cpp:9-10; Eigen is not vendored: parity
+// unpinned, the convention below is the oracle's): eigenvalues ascending, eigenvectors = columns
+// of V, each normalised so that its first non-zero component is positive.
+LMC_HD_NOINLINE void jacobi_eigen(int n, float *A, float *V, float *w) {
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0f : 0.0f;
+    for (int sweep = 0; sweep < 16; sweep++) {
+        float off = 0.0f, diag = 0.0f;
+        for (int p = 0; p < n; p++) { diag += A[p * n + p] * A[p * n + p]; for (int q = p + 1; q < n; q++) off += A[p * n + q] * A[p * n + q]; }
+        if (off <= 1e-14f * (diag + off) || off == 0.0f) break;
+        for (int p = 0; p < n - 1; p++) {
+            for (int q = p + 1; q < n; q++) {
+                const float apq = A[p * n + q];
+                if (apq == 0.0f) continue;
+                const float theta = (A[q * n + q] - A[p * n + p]) / (2.0f * apq);
+                const float t = ((theta >= 0.0f) ? 1.0f : -1.0f) / (dm_abs(theta) + dm_sqrt(theta * theta + 1.0f));
+                const float c = 1.0f / dm_sqrt(t * t + 1.0f);
+                const float sn = t * c;
+                for (int k = 0; k < n; k++) {      // columns p, q
+                    const float akp = A[k * n + p], akq = A[k * n + q];
+                    A[k * n + p] = c * akp - sn * akq;
+                    A[k * n + q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < n; k++) {      // rows p, q
+                    const float apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = c * apk - sn * aqk;
+                    A[q * n + k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < n; k++) {
+                    const float vkp = V[k * n + p], vkq = V[k * n + q];
+                    V[k * n + p] = c * vkp - sn * vkq;
+                    V[k * n + q] = sn * vkp + c * vkq;
+                }
+            }
+        }
+    }
+    for (int i = 0; i < n; i++) w[i] = A[i * n + i];
+    for (int i = 0; i < n - 1; i++) {              // ascending selection sort, columns follow
+        int m = i;
+        for (int j = i + 1; j < n; j++) if (w[j] < w[m]) m = j;
+        if (m != i) {
+            const float tw = w[i]; w[i] = w[m]; w[m] = tw;
+            for (int k = 0; k < n; k++) { const float tv = V[k * n + i]; V[k * n + i] = V[k * n + m]; V[k * n + m] = tv; }
+        }
+    }
+    for (int j = 0; j < n; j++) {
+        float lead = 0.0f;
+        for (int k = 0; k < n; k++) if (V[k * n + j] != 0.0f) { lead = V[k * n + j]; break; }
+        if (lead < 0.0f) for (int k = 0; k < n; k++) V[k * n + j] = -V[k * n + j];
+    }
+}
+
+// ComputeGaussian(h2mcParam, sc, vGrad, vHess, gaussian)  (src/h2mc.cpp:70-142 and :3-68).
+// Diagonal outputs go to `g`, dense factors to covL / invCov; returns 1 when the result is dense.
+template <int DIM>
+LMC_HD_NOINLINE int h2mc_compute_gaussian(const Options &opt, float sc, int dim, const float *grad, float *hess,
+                                          Gaussian<DIM> &g, float *covL, float *invCov) {
+    const float sigma = opt.perturbStdDev;
+    const float invSigmaSq = 1.0f / (sigma * sigma);
+    g.dim = dim;
+    float frob = 0.0f;
+    for (int i = 0; i < dim * dim; i++) frob += hess[i] * hess[i];
+    frob = dm_sqrt(frob);
+    if (sc <= 1e-15f || frob < 0.5f / (sigma * sigma)) {
+        for (int i = 0; i < dim; i++) { g.mean[i] = 0.0f; g.covL_d[i] = sigma; g.invCov_d[i] = invSigmaSq; }
+        g.logDet = 0.0f;
+        for (int i = 0; i < dim; i++) g.logDet += dm_log(invSigmaSq);
+        return 0;
+    }
+    float V[LMC_H2MC_DIM * LMC_H2MC_DIM], w[LMC_H2MC_DIM], eigenBuff[LMC_H2MC_DIM], offsetBuff[LMC_H2MC_DIM], post[LMC_H2MC_DIM];
+    // SelfAdjointEigenSolver reads the lower triangle of the column-major map H(r, c) = vHess[c * dim + r]
+    for (int r = 0; r < dim; r++) for (int c = 0; c < r; c++) hess[c * dim + r] = hess[r * dim + c];
+    jacobi_eigen(dim, hess, V, w);
+    for (int i = 0; i < dim; i++) eigenBuff[i] = (dm_abs(w[i]) > 1e-10f) ? 1.0f / dm_abs(w[i]) : 0.0f;
+    for (int i = 0; i < dim; i++) {
+        float vtg = 0.0f;
+        for (int k = 0; k < dim; k++) vtg += V[k * dim + i] * grad[k];
+        offsetBuff[i] = eigenBuff[i] * vtg;
+    }
+    for (int i = 0; i < dim; i++) {
+        float s2 = 1.0f, o = 0.0f;
+        if (dm_abs(w[i]) > 1e-10f) {
+            o = offsetBuff[i];
+            if (w[i] > 0.0f) { s2 = opt.h2mcPosScale; o *= opt.h2mcPosOffset; }
+            else { s2 = opt.h2mcNegScale; o *= opt.h2mcNegOffset; }
+        } else {
+            s2 = opt.h2mcL * opt.h2mcL;
+            o = 0.5f * offsetBuff[i] * opt.h2mcL * opt.h2mcL;
+        }
+        eigenBuff[i] *= s2;
+        eigenBuff[i] = (eigenBuff[i] > 1e-10f) ? 1.0f / eigenBuff[i] : 0.0f;
+        offsetBuff[i] = o;
+    }
+    for (int i = 0; i < dim; i++) post[i] = eigenBuff[i] + invSigmaSq;
+    for (int r = 0; r < dim; r++) {
+        for (int c = 0; c < dim; c++) {
+            float acc = 0.0f;
+            for (int k = 0; k < dim; k++) acc += (V[r * dim + k] * post[k]) * V[c * dim + k];
+            invCov[r * dim + c] = acc;
+        }
+        float m = 0.0f;
+        for (int k = 0; k < dim; k++) m += V[r * dim + k] * ((eigenBuff[k] / post[k]) * offsetBuff[k]);
+        g.mean[r] = m;
+        for (int k = 0; k < dim; k++) covL[r * dim + k] = V[r * dim + k] * dm_sqrt(1.0f / post[k]);
+        g.covL_d[r] = 0.0f; g.invCov_d[r] = 0.0f;
+    }
+    // sic: the template parameter `dim` is -1 for D > 12, so the reference's loop adds nothing
+    g.logDet = 0.0f;
+    if (dim <= 12) for (int i = 0; i < dim; i++) g.logDet += dm_log(post[i]);
+    return 1;
+}
+
+// GaussianLogPdf / GenerateSample, dense branch (src/gaussian.cpp:29-31,49-51)
+template <int DIM>
+LMC_HD float gaussian_log_pdf_dense(const float *offset, float sign, const Gaussian<DIM> &g, const float *invCov) {
+    float logPdf = (float)g.dim * (-0.9189385332046727f);
+    logPdf += 0.5f * g.logDet;
+    float q = 0.0f;
+    for (int i = 0; i < g.dim; i++) {
+        float r = 0.0f;
+        for (int j = 0; j < g.dim; j++) r += invCov[i * g.dim + j] * (sign * offset[j] - g.mean[j]);
+        q += (sign * offset[i] - g.mean[i]) * r;
+    }
+    logPdf -= 0.5f * q;
+    return logPdf;
+}
+template <int DIM>
+LMC_HD void generate_sample_dense(const Gaussian<DIM> &g, const float *covL, float *x, Rng &rng) {
+    float z[DIM];
+    NormalDist nd = normal_make(0.0f, 1.0f);
+    for (int i = 0; i < g.dim; i++) z[i] = normal_draw(nd, rng);
+    for (int i = 0; i < g.dim; i++) {
+        float r = 0.0f;
+        for (int j = 0; j < g.dim; j++) r += covL[i * g.dim + j] * z[j];
+        x[i] = r + g.mean[i];
+    }
+}
+
+// 0: no derivative function for this (c, l) -> IsotropicGaussian(sigma); 1: function exists but
+// ssScore <= 1e-15 (zero gradient / Hessian); 2: evaluate gradient + Hessian (src/mutation_h2mc.h:62-90)
+template <int MAXD>
+LMC_HD int h2mc_grad_mode(const Scene &sc, const MarkovState<MAXD> &st) {
+    const bool haveFunc = (st.sp.camDepth + st.sp.lightDepth - 1) <= sc.opt.maxDervDepth && grad_supported(sc, st.path) &&
+                          path_dimension(st.path) <= LMC_H2MC_DIM;
+    if (!haveFunc) return 0;
+    return (st.sp.ssScore > 1e-15f) ? 2 : 1;
+}
+
+// initGaussian(state) of H2MCSmallStep::Mutate
+template <int MAXD>
+LMC_HD void h2mc_init_gaussian(const Scene &sc, MarkovState<MAXD> &st, int slot, int mode, const float *grad, H2mcSide *side) {
+    const int dim = path_dimension(st.path);
+    if (mode == 0) {
+        isotropic_gaussian(dim, sc.opt.perturbStdDev, st.gaussian);
+        side->dense[slot] = 0;
+    } else {
+        float g0[LMC_H2MC_DIM];
+        for (int i = 0; i < dim; i++) g0[i] = (mode == 2) ? grad[i] : 0.0f;
+        if (mode != 2) for (int i = 0; i < dim * dim; i++) side->hess[i] = 0.0f;
+        side->dense[slot] = h2mc_compute_gaussian(sc.opt, st.sp.ssScore, dim, g0, side->hess, st.gaussian, side->covL[slot], side->invCov[slot]);
+    }
+    st.gaussianInitialized = 1;
+}
 
 template <int MAXD>
 struct StepScratch {
@@ -224,8 +397,13 @@ LMC_HD void phase_begin(const Scene &sc, const RunParams &rp, long long sampleId
     ss.needCurGrad = 0; ss.needPropGrad = 0; ss.hasContrib = 0; ss.a = 1.0f;
     const float lsScale = ((float)sampleIdx > (float)rp.numSamplesThisChain * sc.opt.lsRatio) ? sc.opt.largeStepProbScale : 1.0f;
     if (!cur.valid || rng_uniform(rng) < sc.opt.largeStepProbability * lsScale) { ss.kind = STEP_LARGE; return; }
-    if (!sc.opt.mala) { ss.kind = STEP_ISO; return; }
+    if (!sc.opt.mala && !sc.opt.h2mc) { ss.kind = STEP_ISO; return; }
     if (rng_uniform(rng) < sc.opt.uniformMixingProbability) { ss.kind = STEP_ISO; return; }
+    if (sc.opt.h2mc) {          // src/mlt.cpp:71-74: h2mc takes precedence over mala
+        ss.kind = STEP_H2MC;
+        if (!cur.gaussianInitialized && h2mc_grad_mode(sc, cur) == 2) ss.needCurGrad = 1;
+        return;
+    }
     ss.kind = STEP_MALA;
     if (!ch.buffered) {
         for (int i = 0; i < Limits<MAXD>::DIM; i++) {
@@ -238,7 +416,23 @@ LMC_HD void phase_begin(const Scene &sc, const RunParams &rp, long long sampleId
 
 // Phase 1 / 3: PSS gradient of the current state / of the proposal (no RNG).
 template <int MAXD>
-LMC_HD void phase_gradient(const Scene &sc, const MarkovState<MAXD> &st, StepScratch<MAXD> &ss, unsigned int *gradStats) {
+LMC_HD void phase_gradient(const Scene &sc, const MarkovState<MAXD> &st, StepScratch<MAXD> &ss, unsigned int *gradStats,
+                           H2mcSide *side) {
+    if (ss.kind == STEP_H2MC) {
+        // gradient + Hessian, IsFinite guard on both (src/mutation_h2mc.h:74-86)
+        const int dim = path_dimension(st.path);
+        path_hessian(sc, st.path, ss.grad, side->hess);
+        bool finite = true;
+        for (int i = 0; i < dim; i++) if (!dm_isfinite(ss.grad[i])) finite = false;
+        for (int i = 0; i < dim * dim; i++) if (!dm_isfinite(side->hess[i])) finite = false;
+        if (!finite) {
+            for (int i = 0; i < dim; i++) ss.grad[i] = 0.0f;
+            for (int i = 0; i < dim * dim; i++) side->hess[i] = 0.0f;
+            if (gradStats) gradStats[1]++;
+        }
+        if (gradStats) gradStats[0]++;
+        return;
+    }
     mala_eval_gradient(sc, st, ss.grad, gradStats);
 }
 
@@ -247,7 +441,7 @@ LMC_HD void phase_gradient(const Scene &sc, const MarkovState<MAXD> &st, StepScr
 // gradient (src/mutation_mala.h:83-176), LargeStep::Mutate (src/mutation_large.h:31-127).
 template <int MAXD>
 LMC_HD void phase_propose(const Scene &sc, const RunParams &rp, MarkovState<MAXD> &cur, MarkovState<MAXD> &prop,
-                          ChainVars<MAXD> &ch, Rng &rng, StepScratch<MAXD> &ss) {
+                          ChainVars<MAXD> &ch, Rng &rng, StepScratch<MAXD> &ss, H2mcSide *side, int curSlot) {
     const float normalization = rp.normalization;
     if (ss.kind == STEP_LARGE) {
         ch.lastMutationType = MUT_LARGE;
@@ -304,6 +498,22 @@ LMC_HD void phase_propose(const Scene &sc, const RunParams &rp, MarkovState<MAXD
         }
         return;
     }
+    if (ss.kind == STEP_H2MC) {
+        ch.lastMutationType = MUT_H2MC_SMALL;
+        if (!cur.gaussianInitialized) h2mc_init_gaussian(sc, cur, curSlot, h2mc_grad_mode(sc, cur), ss.grad, side);
+        if (side->dense[curSlot]) generate_sample_dense(cur.gaussian, side->covL[curSlot], ss.offset, rng);
+        else generate_sample(cur.gaussian, ss.offset, rng);
+        path_copy(prop.path, cur.path);
+        perturb_path_bidir(sc, ss.offset, prop.path, contribs, rng);
+        if (contribs.n > 0) {
+            prop.sp = contribs.c[0];
+            ss.hasContrib = 1;
+            if (h2mc_grad_mode(sc, prop) == 2) ss.needPropGrad = 1;
+        } else {
+            ss.a = 0.0f;
+        }
+        return;
+    }
     // STEP_MALA
     ch.lastMutationType = MUT_MALA_SMALL;
     if (!cur.gaussianInitialized) {
@@ -333,9 +543,21 @@ struct StepInfo {          // what one iteration did (parity traces / stats)
 template <int MAXD, class FILM>
 LMC_HD StepInfo phase_finish(const Scene &sc, const RunParams &rp, int chainId, long long sampleIdx,
                              MarkovState<MAXD> *states, int &curIdx, ChainVars<MAXD> &ch, Rng &rng, FILM &film,
-                             StepScratch<MAXD> &ss) {
+                             StepScratch<MAXD> &ss, H2mcSide *side) {
     MarkovState<MAXD> &cur = states[curIdx];
     MarkovState<MAXD> &prop = states[curIdx ^ 1];
+    if (ss.kind == STEP_H2MC && ss.hasContrib) {
+        const int cs_ = curIdx, ps_ = curIdx ^ 1;
+        h2mc_init_gaussian(sc, prop, ps_, h2mc_grad_mode(sc, prop), ss.grad, side);
+        const float py = side->dense[cs_] ? gaussian_log_pdf_dense(ss.offset, 1.0f, cur.gaussian, side->invCov[cs_])
+                                          : gaussian_log_pdf(ss.offset, 1.0f, cur.gaussian);
+        const float px = side->dense[ps_] ? gaussian_log_pdf_dense(ss.offset, -1.0f, prop.gaussian, side->invCov[ps_])
+                                          : gaussian_log_pdf(ss.offset, -1.0f, prop.gaussian);
+        ss.a = dm_clamp(dm_exp(px - py) * prop.sp.ssScore / cur.sp.ssScore, 0.0f, 1.0f);
+        prop.nSplat = 1;
+        prop.splat[0].screenPos = prop.sp.screenPos;
+        prop.splat[0].contrib = prop.sp.contrib * (rp.normalization / prop.sp.lsScore);
+    }
     if (ss.kind == STEP_MALA && ss.hasContrib) {
         mala_finish_gaussian(sc, prop, ch, mala_grad_mode(sc, prop), ss.grad, ch.prop_new_v1, ch.prop_new_v2, prop.gaussian);
         prop.gaussianInitialized = 1;
@@ -400,12 +622,12 @@ LMC_HD StepInfo phase_finish(const Scene &sc, const RunParams &rp, int chainId, 
 template <int MAXD, class FILM>
 LMC_HD StepInfo chain_step(const Scene &sc, const RunParams &rp, int chainId, long long sampleIdx,
                            MarkovState<MAXD> *states, int &curIdx, ChainVars<MAXD> &ch, Rng &rng, FILM &film,
-                           unsigned int *gradStats, StepScratch<MAXD> &ss) {
+                           unsigned int *gradStats, StepScratch<MAXD> &ss, H2mcSide *side) {
     phase_begin(sc, rp, sampleIdx, states[curIdx], ch, rng, ss);
-    if (ss.needCurGrad) phase_gradient(sc, states[curIdx], ss, gradStats);
-    phase_propose(sc, rp, states[curIdx], states[curIdx ^ 1], ch, rng, ss);
-    if (ss.needPropGrad) phase_gradient(sc, states[curIdx ^ 1], ss, gradStats);
-    return phase_finish(sc, rp, chainId, sampleIdx, states, curIdx, ch, rng, film, ss);
+    if (ss.needCurGrad) phase_gradient(sc, states[curIdx], ss, gradStats, side);
+    phase_propose(sc, rp, states[curIdx], states[curIdx ^ 1], ch, rng, ss, side, curIdx);
+    if (ss.needPropGrad) phase_gradient(sc, states[curIdx ^ 1], ss, gradStats, side);
+    return phase_finish(sc, rp, chainId, sampleIdx, states, curIdx, ch, rng, film, ss, side);
 }
 
 }  // namespace lmc

@@ -28,61 +28,74 @@
 namespace lmc {
 
 // ------------------------------------------------------------------------------------------
-// dual numbers
+// dual numbers over a scalar S (float for first order; a dual itself for second order)
 // ------------------------------------------------------------------------------------------
-template <int N>
-struct Dual {
-    float v;
-    float d[N];
+template <class S, int N>
+struct DualT {
+    S v;
+    S d[N];
 };
-
-template <int N> LMC_HD Dual<N> dconst(float c) { Dual<N> r; r.v = c; for (int i = 0; i < N; i++) r.d[i] = 0.0f; return r; }
-template <int N> LMC_HD Dual<N> operator+(const Dual<N> &a, const Dual<N> &b) { Dual<N> r; r.v = a.v + b.v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] + b.d[i]; return r; }
-template <int N> LMC_HD Dual<N> operator-(const Dual<N> &a, const Dual<N> &b) { Dual<N> r; r.v = a.v - b.v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] - b.d[i]; return r; }
-template <int N> LMC_HD Dual<N> operator-(const Dual<N> &a) { Dual<N> r; r.v = -a.v; for (int i = 0; i < N; i++) r.d[i] = -a.d[i]; return r; }
-template <int N> LMC_HD Dual<N> operator*(const Dual<N> &a, const Dual<N> &b) { Dual<N> r; r.v = a.v * b.v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
-template <int N> LMC_HD Dual<N> operator/(const Dual<N> &a, const Dual<N> &b) {
-    Dual<N> r; const float ib = 1.0f / b.v; r.v = a.v * ib;
-    for (int i = 0; i < N; i++) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
-    return r;
-}
-template <int N> LMC_HD Dual<N> operator+(const Dual<N> &a, float b) { Dual<N> r = a; r.v = a.v + b; return r; }
-template <int N> LMC_HD Dual<N> operator+(float b, const Dual<N> &a) { Dual<N> r = a; r.v = b + a.v; return r; }
-template <int N> LMC_HD Dual<N> operator-(const Dual<N> &a, float b) { Dual<N> r = a; r.v = a.v - b; return r; }
-template <int N> LMC_HD Dual<N> operator-(float b, const Dual<N> &a) { Dual<N> r; r.v = b - a.v; for (int i = 0; i < N; i++) r.d[i] = -a.d[i]; return r; }
-template <int N> LMC_HD Dual<N> operator*(const Dual<N> &a, float b) { Dual<N> r; r.v = a.v * b; for (int i = 0; i < N; i++) r.d[i] = a.d[i] * b; return r; }
-template <int N> LMC_HD Dual<N> operator*(float b, const Dual<N> &a) { Dual<N> r; r.v = b * a.v; for (int i = 0; i < N; i++) r.d[i] = b * a.d[i]; return r; }
-template <int N> LMC_HD Dual<N> operator/(const Dual<N> &a, float b) { Dual<N> r; const float ib = 1.0f / b; r.v = a.v * ib; for (int i = 0; i < N; i++) r.d[i] = a.d[i] * ib; return r; }
-template <int N> LMC_HD Dual<N> operator/(float a, const Dual<N> &b) {
-    Dual<N> r; const float ib = 1.0f / b.v; r.v = a * ib; const float k = -(r.v * ib);
-    for (int i = 0; i < N; i++) r.d[i] = k * b.d[i];
-    return r;
-}
-template <int N> LMC_HD Dual<N> &operator+=(Dual<N> &a, const Dual<N> &b) { a = a + b; return a; }
-template <int N> LMC_HD Dual<N> &operator*=(Dual<N> &a, const Dual<N> &b) { a = a * b; return a; }
-template <int N> LMC_HD Dual<N> &operator*=(Dual<N> &a, float b) { a = a * b; return a; }
+template <int N> using Dual = DualT<float, N>;
 
 // value access / construction usable with T = float too
 LMC_HD float ad_val(float a) { return a; }
-template <int N> LMC_HD float ad_val(const Dual<N> &a) { return a.v; }
+template <class S, int N> LMC_HD float ad_val(const DualT<S, N> &a) { return ad_val(a.v); }
 template <class T> struct ADTraits;
 template <> struct ADTraits<float> { LMC_HD static float make(float c) { return c; } };
-template <int N> struct ADTraits<Dual<N>> { LMC_HD static Dual<N> make(float c) { return dconst<N>(c); } };
+template <class S, int N> struct ADTraits<DualT<S, N>> {
+    LMC_HD static DualT<S, N> make(float c) {
+        DualT<S, N> r; r.v = ADTraits<S>::make(c);
+        for (int i = 0; i < N; i++) r.d[i] = ADTraits<S>::make(0.0f);
+        return r;
+    }
+};
 template <class T> LMC_HD T ad_const(float c) { return ADTraits<T>::make(c); }
 
-// scale all derivative parts by k and set value to v (chain rule helper)
-template <int N> LMC_HD Dual<N> dchain(const Dual<N> &a, float v, float k) { Dual<N> r; r.v = v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] * k; return r; }
+#define LMC_DT template <class S, int N> LMC_HD DualT<S, N>
+LMC_DT operator+(const DualT<S, N> &a, const DualT<S, N> &b) { DualT<S, N> r; r.v = a.v + b.v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] + b.d[i]; return r; }
+LMC_DT operator-(const DualT<S, N> &a, const DualT<S, N> &b) { DualT<S, N> r; r.v = a.v - b.v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] - b.d[i]; return r; }
+LMC_DT operator-(const DualT<S, N> &a) { DualT<S, N> r; r.v = -a.v; for (int i = 0; i < N; i++) r.d[i] = -a.d[i]; return r; }
+LMC_DT operator*(const DualT<S, N> &a, const DualT<S, N> &b) { DualT<S, N> r; r.v = a.v * b.v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+LMC_DT operator/(const DualT<S, N> &a, const DualT<S, N> &b) {
+    DualT<S, N> r; const S ib = 1.0f / b.v; r.v = a.v * ib;
+    for (int i = 0; i < N; i++) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
+    return r;
+}
+LMC_DT operator+(const DualT<S, N> &a, float b) { DualT<S, N> r = a; r.v = a.v + b; return r; }
+LMC_DT operator+(float b, const DualT<S, N> &a) { DualT<S, N> r = a; r.v = b + a.v; return r; }
+LMC_DT operator-(const DualT<S, N> &a, float b) { DualT<S, N> r = a; r.v = a.v - b; return r; }
+LMC_DT operator-(float b, const DualT<S, N> &a) { DualT<S, N> r; r.v = b - a.v; for (int i = 0; i < N; i++) r.d[i] = -a.d[i]; return r; }
+LMC_DT operator*(const DualT<S, N> &a, float b) { DualT<S, N> r; r.v = a.v * b; for (int i = 0; i < N; i++) r.d[i] = a.d[i] * b; return r; }
+LMC_DT operator*(float b, const DualT<S, N> &a) { DualT<S, N> r; r.v = b * a.v; for (int i = 0; i < N; i++) r.d[i] = b * a.d[i]; return r; }
+LMC_DT operator/(const DualT<S, N> &a, float b) { DualT<S, N> r; const float ib = 1.0f / b; r.v = a.v * ib; for (int i = 0; i < N; i++) r.d[i] = a.d[i] * ib; return r; }
+LMC_DT operator/(float a, const DualT<S, N> &b) {
+    DualT<S, N> r; const S ib = 1.0f / b.v; r.v = a * ib; const S k = -(r.v * ib);
+    for (int i = 0; i < N; i++) r.d[i] = k * b.d[i];
+    return r;
+}
+template <class S, int N> LMC_HD DualT<S, N> &operator+=(DualT<S, N> &a, const DualT<S, N> &b) { a = a + b; return a; }
+template <class S, int N> LMC_HD DualT<S, N> &operator*=(DualT<S, N> &a, const DualT<S, N> &b) { a = a * b; return a; }
+template <class S, int N> LMC_HD DualT<S, N> &operator*=(DualT<S, N> &a, float b) { a = a * b; return a; }
+
+// chain rule helper: value v, derivative parts scaled by k (both of the scalar type S)
+LMC_DT dchain(const DualT<S, N> &a, const S &v, const S &k) { DualT<S, N> r; r.v = v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] * k; return r; }
 
 LMC_HD float ad_sqrt(float a) { return dm_sqrt(a); }
-template <int N> LMC_HD Dual<N> ad_sqrt(const Dual<N> &a) { const float s = dm_sqrt(a.v); return dchain(a, s, 0.5f / s); }
+LMC_DT ad_sqrt(const DualT<S, N> &a) { const S s = ad_sqrt(a.v); return dchain(a, s, 0.5f / s); }
 LMC_HD float ad_sin(float a) { return dm_sin(a); }
 LMC_HD float ad_cos(float a) { return dm_cos(a); }
-template <int N> LMC_HD Dual<N> ad_sin(const Dual<N> &a) { float s, c; dm_sincos(a.v, s, c); return dchain(a, s, c); }
-template <int N> LMC_HD Dual<N> ad_cos(const Dual<N> &a) { float s, c; dm_sincos(a.v, s, c); return dchain(a, c, -s); }
+// sin and cos of the same argument with ONE evaluation of the underlying kernel
+LMC_HD void ad_sincos(float a, float &s, float &c) { dm_sincos(a, s, c); }
+template <class S, int N> LMC_HD void ad_sincos(const DualT<S, N> &a, DualT<S, N> &s, DualT<S, N> &c) {
+    S sv, cv; ad_sincos(a.v, sv, cv);
+    s = dchain(a, sv, cv); c = dchain(a, cv, -sv);
+}
+LMC_DT ad_sin(const DualT<S, N> &a) { DualT<S, N> s, c; ad_sincos(a, s, c); return s; }
+LMC_DT ad_cos(const DualT<S, N> &a) { DualT<S, N> s, c; ad_sincos(a, s, c); return c; }
 LMC_HD float ad_exp(float a) { return dm_exp(a); }
-template <int N> LMC_HD Dual<N> ad_exp(const Dual<N> &a) { const float e = dm_exp(a.v); return dchain(a, e, e); }
+LMC_DT ad_exp(const DualT<S, N> &a) { const S e = ad_exp(a.v); return dchain(a, e, e); }
 LMC_HD float ad_log(float a) { return dm_log(a); }
-template <int N> LMC_HD Dual<N> ad_log(const Dual<N> &a) { return dchain(a, dm_log(a.v), 1.0f / a.v); }
+LMC_DT ad_log(const DualT<S, N> &a) { return dchain(a, ad_log(a.v), 1.0f / a.v); }
 // pow(x, y) with a constant exponent, libm semantics for a negative base with an integral
 // exponent (Phong's `pow(alpha, exponent)` has no max(alpha, 0) in the AD twin, src/phong.cpp:202).
 LMC_HD float ad_pow_c(float x, float y) {
@@ -96,23 +109,22 @@ LMC_HD float ad_pow_c(float x, float y) {
     return dm_pow(x, y);
 }
 LMC_HD float ad_pow(float x, float y) { return ad_pow_c(x, y); }
-template <int N> LMC_HD Dual<N> ad_pow(const Dual<N> &x, float y) {
-    // d/dx = y * pow(x, y - 1)   (src/chad.h:726-728)
-    return dchain(x, ad_pow_c(x.v, y), y * ad_pow_c(x.v, y - 1.0f));
-}
+// d/dx = y * pow(x, y - 1)   (src/chad.h:726-728)
+LMC_DT ad_pow(const DualT<S, N> &x, float y) { return dchain(x, ad_pow(x.v, y), y * ad_pow(x.v, y - 1.0f)); }
 LMC_HD float ad_fabs(float a) { return (a >= 0.0f) ? a : -a; }
-template <int N> LMC_HD Dual<N> ad_fabs(const Dual<N> &a) { return (a.v >= 0.0f) ? a : -a; }
+LMC_DT ad_fabs(const DualT<S, N> &a) { return (ad_val(a) >= 0.0f) ? a : -a; }
 LMC_HD float ad_fmax(float a, float b) { return (a >= b) ? a : b; }
-template <int N> LMC_HD Dual<N> ad_fmax(const Dual<N> &a, float b) { return (a.v >= b) ? a : dconst<N>(b); }
+LMC_DT ad_fmax(const DualT<S, N> &a, float b) { return (ad_val(a) >= b) ? a : ADTraits<DualT<S, N>>::make(b); }
 LMC_HD float ad_atan2(float y, float x) { return dm_atan2(y, x); }
-template <int N> LMC_HD Dual<N> ad_atan2(const Dual<N> &y, const Dual<N> &x) {
-    const float invNorm = 1.0f / (x.v * x.v + y.v * y.v);
-    Dual<N> r; r.v = dm_atan2(y.v, x.v);
-    for (int i = 0; i < N; i++) r.d[i] = (x.v * invNorm) * y.d[i] + (-y.v * invNorm) * x.d[i];
+LMC_DT ad_atan2(const DualT<S, N> &y, const DualT<S, N> &x) {
+    const S invNorm = 1.0f / (x.v * x.v + y.v * y.v);
+    DualT<S, N> r; r.v = ad_atan2(y.v, x.v);
+    const S ky = x.v * invNorm, kx = -(y.v * invNorm);
+    for (int i = 0; i < N; i++) r.d[i] = ky * y.d[i] + kx * x.d[i];
     return r;
 }
 LMC_HD float ad_acos(float a) { return dm_acos(a); }
-template <int N> LMC_HD Dual<N> ad_acos(const Dual<N> &a) { return dchain(a, dm_acos(a.v), -(1.0f / dm_sqrt(1.0f - a.v * a.v))); }
+LMC_DT ad_acos(const DualT<S, N> &a) { return dchain(a, ad_acos(a.v), -(1.0f / ad_sqrt(1.0f - a.v * a.v))); }
 template <class T> LMC_HD T ad_square(const T &a) { return a * a; }
 template <class T> LMC_HD T ad_inverse(const T &a) { return 1.0f / a; }
 template <class T> LMC_HD T ad_mis(const T &a) { return a * a; }
@@ -292,14 +304,17 @@ template <class T> LMC_HD_NOINLINE T ad_fresnel(const T &cosThetaI_, T &cosTheta
 template <class T> LMC_HD TV3<T> ad_sample_cos_hemisphere(const T &r0, const T &r1) {
     const T phi = LMC_TWOPI * r0;
     const T tmp = ad_sqrt(ad_fmax(1.0f - r1, 1e-6f));
-    return tv3<T>(ad_cos(phi) * tmp, ad_sin(phi) * tmp, ad_sqrt(ad_fmax(r1, 1e-6f)));
+    T sp, cp; ad_sincos(phi, sp, cp);
+    return tv3<T>(cp * tmp, sp * tmp, ad_sqrt(ad_fmax(r1, 1e-6f)));
 }
 template <class T> LMC_HD TV3<T> ad_sample_sphere(const T &c0, const T &c1, T &jacobian) {
     const T scaledTheta = LMC_TWOPI * c0;
     const T scaledPhi = LMC_PI * c1;
-    const T sinPhi = ad_sin(scaledPhi), cosPhi = ad_cos(scaledPhi);
+    T sinPhi, cosPhi, st, ct;
+    ad_sincos(scaledPhi, sinPhi, cosPhi);
+    ad_sincos(scaledTheta, st, ct);
     jacobian = ad_fabs(sinPhi) * LMC_TWOPI * LMC_PI;
-    return tv3<T>(sinPhi * ad_cos(scaledTheta), sinPhi * ad_sin(scaledTheta), cosPhi);
+    return tv3<T>(sinPhi * ct, sinPhi * st, cosPhi);
 }
 
 // normal flip shared by Lambertian / Phong twins (always two-sided in the AD code)
@@ -396,7 +411,7 @@ template <class T> LMC_HD_NOINLINE void ad_sample_bsdf(bool adjoint, const float
         const T scaledAlpha = alpha * (1.2f - 0.2f * ad_sqrt(ad_fabs(cosWi)));
         // SampleMicronormal<ADFloat>, src/microfacet.h:162-185
         const T phiM = LMC_TWOPI * r1;
-        const T sinPhiM = ad_sin(phiM), cosPhiM = ad_cos(phiM);
+        T sinPhiM, cosPhiM; ad_sincos(phiM, sinPhiM, cosPhiM);
         const T alphaSqr = ad_square(scaledAlpha);
         const T tanThetaMSqr = alphaSqr * (-ad_log(ad_fmax(1.0f - r0, 1e-6f)));
         const T cosThetaM = 1.0f / ad_sqrt(1.0f + tanThetaMSqr);
@@ -459,7 +474,8 @@ template <class T> LMC_HD_NOINLINE void ad_sample_bsdf(bool adjoint, const float
             const T cosAlpha = ad_pow(r1, power);
             const T sinAlpha = ad_sqrt(ad_fmax(1.0f - ad_square(cosAlpha), 1e-6f));
             const T phi = LMC_TWOPI * r0;
-            const TV3<T> localDir = tv3<T>(sinAlpha * ad_cos(phi), sinAlpha * ad_sin(phi), cosAlpha);
+            T sphi, cphi; ad_sincos(phi, sphi, cphi);
+            const TV3<T> localDir = tv3<T>(sinAlpha * cphi, sinAlpha * sphi, cosAlpha);
             TV3<T> b0, b1; tcoordinate_system(R, b0, b1);
             wo = localDir.x * b0 + localDir.y * b1 + localDir.z * R;
         }
@@ -539,7 +555,9 @@ template <class T> LMC_HD_NOINLINE void ad_env_sample_direction(const ADEnvRec &
     const T plx = e.col + tx, ply = e.row + ty;
     const T phi = (plx + 0.5f) * e.pixelSize[0];
     const T theta = (ply + 0.5f) * e.pixelSize[1];
-    const T sinPhi = ad_sin(phi), cosPhi = ad_cos(phi), sinTheta = ad_sin(theta), cosTheta = ad_cos(theta);
+    T sinPhi, cosPhi, sinTheta, cosTheta;
+    ad_sincos(phi, sinPhi, cosPhi);
+    ad_sincos(theta, sinTheta, cosTheta);
     dirToLight = txform_vector(e.toWorld, tv3<T>(sinPhi * sinTheta, cosTheta, -cosPhi * sinTheta));
     const T dx1 = tx, dx2 = 1.0f - tx, dy1 = ty, dy2 = 1.0f - ty;
     const TV3<T> value1 = tscale(e.img00, dx2) * dy2 + tscale(e.img10, dx1) * dy2;
@@ -621,7 +639,8 @@ template <class T> LMC_HD void ad_sample_concentric_disc(const T &r0, const T &r
     if (ad_val(a1) == 0.0f || ad_val(a2) == 0.0f) { r = ad_const<T>(0.0f); phi = ad_const<T>(0.0f); }
     else if (ad_val(a1) * ad_val(a1) > ad_val(a2) * ad_val(a2)) { r = a1; phi = LMC_PIOVERFOUR * (a2 / a1); }
     else { r = a2; phi = LMC_PIOVERTWO - (a1 / a2) * LMC_PIOVERFOUR; }
-    ox = r * ad_cos(phi); oy = r * ad_sin(phi);
+    T sphi, cphi; ad_sincos(phi, sphi, cphi);
+    ox = r * cphi; oy = r * sphi;
 }
 // Emit twin
 template <class T> LMC_HD_NOINLINE void ad_emit(const float *buffer, const ADScene &scn, const T &p0, const T &p1, const T &d0,
@@ -898,6 +917,45 @@ LMC_HD_NOINLINE float path_loglum_grad(int camDepth, int lightDepth, const float
         const D r = eval_path_loglum<D>(camDepth, lightDepth, sceneBuf, vertParams, pss);
         value = r.v;
         for (int k = 0; k < LMC_GRAD_CHUNK; k++) if (base + k < dim) grad[base + k] = r.d[k];
+    }
+    return value;
+}
+
+// Gradient AND Hessian w.r.t. primary[1..D] by second-order forward mode: nested duals carry
+// LMC_HESS_CHUNK outer x LMC_HESS_CHUNK inner directions per sweep; the chunk pairs (a <= b) fill
+// the symmetric matrix.  Replaces the forward-over-reverse code `evaluate_path_bidir_<c>_<l>_static_derv`
+// (src/chad.cpp:333-545); hess is row-major D x D (hess[i * D + j] = d2 f / dx_i dx_j, symmetric).
+#define LMC_HESS_CHUNK 2
+#define LMC_HESS_MAXDIM 16
+LMC_HD_NOINLINE float path_loglum_hess(int camDepth, int lightDepth, const float *sceneBuf, const float *primary,
+                                       const float *vertParams, float *grad, float *hess) {
+    const int dim = 2 * ((camDepth + lightDepth - 1) > 2 ? (camDepth + lightDepth - 1) : 2);
+    typedef DualT<float, LMC_HESS_CHUNK> D1;
+    typedef DualT<D1, LMC_HESS_CHUNK> D2;
+    float value = 0.0f;
+    for (int ba = 0; ba < dim; ba += LMC_HESS_CHUNK) {
+        for (int bb = ba; bb < dim; bb += LMC_HESS_CHUNK) {
+            D2 pss[LMC_HESS_MAXDIM];
+            for (int i = 0; i < dim; i++) {
+                pss[i].v.v = primary[1 + i];
+                for (int k = 0; k < LMC_HESS_CHUNK; k++) pss[i].v.d[k] = (i == bb + k) ? 1.0f : 0.0f;
+                for (int j = 0; j < LMC_HESS_CHUNK; j++) {
+                    pss[i].d[j].v = (i == ba + j) ? 1.0f : 0.0f;
+                    for (int k = 0; k < LMC_HESS_CHUNK; k++) pss[i].d[j].d[k] = 0.0f;
+                }
+            }
+            const D2 r = eval_path_loglum<D2>(camDepth, lightDepth, sceneBuf, vertParams, pss);
+            value = r.v.v;
+            for (int j = 0; j < LMC_HESS_CHUNK; j++) {
+                if (ba + j >= dim) continue;
+                if (bb == ba) grad[ba + j] = r.d[j].v;
+                for (int k = 0; k < LMC_HESS_CHUNK; k++) {
+                    if (bb + k >= dim) continue;
+                    hess[(ba + j) * dim + (bb + k)] = r.d[j].d[k];
+                    hess[(bb + k) * dim + (ba + j)] = r.d[j].d[k];
+                }
+            }
+        }
     }
     return value;
 }

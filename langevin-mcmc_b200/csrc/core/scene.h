@@ -117,6 +117,8 @@ struct Options {                 // src/dptoptions.h:7-34 + compile-time constan
     float discreteStdDev;        // 0.01
     float uniformMixingProbability;  // 0.1
     float lsRatio;               // LS_RATIO 0.1
+    // H2MCParam (src/h2mc.h:9-23), evaluated once on the host from sigma = perturbStdDev, L = pi/2
+    float h2mcL, h2mcPosScale, h2mcPosOffset, h2mcNegScale, h2mcNegOffset;
 };
 
 struct Scene {

@@ -138,8 +138,8 @@ LMC_HD bool grad_supported(const Scene &sc, const Path<MAXD> &path) {
 }
 
 // Serialized-path scratch large enough for every path the PSS_MAX_LENGTH gate lets through
-// (dim <= pssMaxLength <= 12  =>  c + l - 1 <= 6  =>  at most 6 surface vertices).
-#define LMC_GRAD_MAX_SURF 6
+// (LMC: dim <= pssMaxLength <= 12; H2MC: c + l - 1 <= maxDervDepth = 8  =>  at most 8 surface vertices).
+#define LMC_GRAD_MAX_SURF 8
 #define LMC_GRAD_SCRATCH (3 + 1 + LMC_SER_LIGHT + LMC_GRAD_MAX_SURF * (LMC_SER_SHAPE + 2 + LMC_SER_BSDF + 1) + LMC_SER_LIGHT + LMC_SER_BSDF + 1)
 
 // dervFunc(screenPos, primary, sceneParams, vertParams, vGrad, NULL) for the path's (c, l)
@@ -155,6 +155,22 @@ LMC_HD_NOINLINE void path_gradient(const Scene &sc, const Path<MAXD> &path, floa
     }
     serialize_path(sc, path, primary, vertParams);
     path_loglum_grad(path.camDepth, path.lgtDepth, sc.sceneSer, primary, vertParams, grad);
+}
+
+// dervFunc(..., vGrad, vHess) of the H2MC library (src/mutation_h2mc.h:74-79); hess row-major dim x dim
+template <int MAXD>
+LMC_HD_NOINLINE void path_hessian(const Scene &sc, const Path<MAXD> &path, float *grad, float *hess) {
+    float primary[2 * LMC_GRAD_MAX_SURF + 1 + 4];
+    float vertParams[LMC_GRAD_SCRATCH];
+    const int dim = path_dimension(path);
+    const int nSurf = (path.camDepth > 1 ? path.camDepth - 1 : 0) + (path.lgtDepth > 1 ? path.lgtDepth - 1 : 0);
+    if (nSurf > LMC_GRAD_MAX_SURF || dim > LMC_HESS_MAXDIM) {
+        for (int i = 0; i < dim; i++) grad[i] = 0.0f;
+        for (int i = 0; i < dim * dim && i < LMC_HESS_MAXDIM * LMC_HESS_MAXDIM; i++) hess[i] = 0.0f;
+        return;
+    }
+    serialize_path(sc, path, primary, vertParams);
+    path_loglum_hess(path.camDepth, path.lgtDepth, sc.sceneSer, primary, vertParams, grad, hess);
 }
 
 }  // namespace lmc

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_begin(const __grid_con
         rng_close(rng, cs);
         kind = cs.ss.kind;
         const Path<MAXD> &p = cs.st[cs.curIdx].path;
-        sort_key_set(wl.small_, i, kind == STEP_LARGE ? -1 : class_key(p.camDepth, p.lgtDepth, kind == STEP_MALA ? 1 : 0));
+        sort_key_set(wl.small_, i, kind == STEP_LARGE ? -1 : class_key(p.camDepth, p.lgtDepth, kind == STEP_ISO ? 0 : 1));
         sort_key_set(wl.curGrad, i, cs.ss.needCurGrad ? class_key(p.camDepth, p.lgtDepth, 0) : -1);
     }
     list_append(wl.large, wl.largeCount, active && kind == STEP_LARGE, i);
@@ -159,25 +159,25 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_begin(const __grid_con
 #endif
 template <int MAXD>
 __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_GRAD_MINB) k_wave_grad(const __grid_constant__ Scene sc, ChainRec<MAXD> *states, int n,
-                                                                const int *list, const int *count, int which) {
+                                                                const int *list, const int *count, int which, H2mcSide *sides) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= *count) return;
     const int i = list[t];
     ChainState<MAXD> &cs = states[i].cs;
-    phase_gradient(sc, cs.st[cs.curIdx ^ which], cs.ss, cs.gradStats);
+    phase_gradient(sc, cs.st[cs.curIdx ^ which], cs.ss, cs.gradStats, sides ? sides + i : nullptr);
 }
 
 template <int MAXD>
 __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_PROP_MINB) k_wave_propose(const __grid_constant__ Scene sc, RunParams rp, int chainBase,
                                                                    ChainRec<MAXD> *states, int n, const int *list, const int *count,
-                                                                   WaveLists wl) {
+                                                                   WaveLists wl, H2mcSide *sides) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= *count) return;
     const int i = list[t];
     uint32_t tab[64];
     ChainState<MAXD> &cs = states[i].cs;
     Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
-    phase_propose(sc, rp, cs.st[cs.curIdx], cs.st[cs.curIdx ^ 1], cs.ch, rng, cs.ss);
+    phase_propose(sc, rp, cs.st[cs.curIdx], cs.st[cs.curIdx ^ 1], cs.ch, rng, cs.ss, sides ? sides + i : nullptr, cs.curIdx);
     rng_close(rng, cs);
     const MarkovState<MAXD> &prop = cs.st[cs.curIdx ^ 1];
     sort_key_set(wl.propGrad, i, cs.ss.needPropGrad ? class_key(prop.sp.camDepth, prop.sp.lightDepth, 0) : -1);
@@ -186,14 +186,14 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_PROP_MINB) k_wave_propose
 template <int MAXD>
 __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_finish(const __grid_constant__ Scene sc, RunParams rp, int chainBase,
                                                                   ChainRec<MAXD> *states, int n, float *film, unsigned char *trace,
-                                                                  float *aTrace, long long numSteps, long long stepInLaunch) {
+                                                                  float *aTrace, long long numSteps, long long stepInLaunch, H2mcSide *sides) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t tab[64];
     DevFilm df; df.p = film;
     ChainState<MAXD> &cs = states[i].cs;
     Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
-    const StepInfo info = phase_finish(sc, rp, chainBase + i, cs.sampleIdx, cs.st, cs.curIdx, cs.ch, rng, df, cs.ss);
+    const StepInfo info = phase_finish(sc, rp, chainBase + i, cs.sampleIdx, cs.st, cs.curIdx, cs.ch, rng, df, cs.ss, sides ? sides + i : nullptr);
     rng_close(rng, cs);
     cs.nPropose[info.mutationType] += 1u;
     cs.nAccept[info.mutationType] += (unsigned int)info.accepted;
@@ -226,7 +226,7 @@ __global__ void k_chain_stats(const ChainRec<MAXD> *states, int n, unsigned long
     cudaError_t launch_chain_init_##MAXD(cudaStream_t st, void *states, int n, int chainBase, const float *initLs); \
     cudaError_t launch_chain_run_##MAXD(cudaStream_t st, const Scene &sc, const RunParams &rp, int chainBase, void *states, \
                                         int n, long long numSteps, float *film, unsigned char *trace, float *aTrace, \
-                                        const WaveLists &wl, unsigned long long *launches); \
+                                        const WaveLists &wl, unsigned long long *launches, H2mcSide *sides); \
     cudaError_t launch_chain_stats_##MAXD(cudaStream_t st, const void *states, int n, unsigned long long *out);
 LMC_DECLARE_CHAIN(4)
 LMC_DECLARE_CHAIN(8)
@@ -240,7 +240,7 @@ LMC_DECLARE_CHAIN(12)
     } \
     cudaError_t launch_chain_run_##MAXD(cudaStream_t st, const Scene &sc, const RunParams &rp, int chainBase, void *states_, \
                                         int n, long long numSteps, float *film, unsigned char *trace, float *aTrace, \
-                                        const WaveLists &wl, unsigned long long *launches) { \
+                                        const WaveLists &wl, unsigned long long *launches, H2mcSide *sides) { \
         ChainRec<MAXD> *states = (ChainRec<MAXD> *)states_; \
         const int B = LMC_CHAIN_BLOCK, G = (n + B - 1) / B; \
         for (long long k = 0; k < numSteps; k++) { \
@@ -249,13 +249,13 @@ LMC_DECLARE_CHAIN(12)
             k_wave_begin<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl); \
             k_sort_scan<<<2, LMC_NKEYS, 0, st>>>(wl.small_, wl.curGrad, 2); \
             k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.small_, wl.curGrad, 2); \
-            k_wave_grad<MAXD><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0); \
-            k_wave_propose<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.small_.list, wl.small_.count, wl); \
-            k_wave_propose<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.large, wl.largeCount, wl); \
+            k_wave_grad<MAXD><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides); \
+            k_wave_propose<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.small_.list, wl.small_.count, wl, sides); \
+            k_wave_propose<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.large, wl.largeCount, wl, sides); \
             k_sort_scan<<<1, LMC_NKEYS, 0, st>>>(wl.propGrad, wl.propGrad, 1); \
             k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.propGrad, wl.propGrad, 1); \
-            k_wave_grad<MAXD><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1); \
-            k_wave_finish<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k); \
+            k_wave_grad<MAXD><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides); \
+            k_wave_finish<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides); \
             *launches += 10; \
             e = cudaGetLastError(); \
             if (e != cudaSuccess) return e; \

@@ -55,6 +55,15 @@ __global__ void k_eval_batch(int camDepth, int lightDepth, int n, const float *s
     else logLum[i] = path_loglum(camDepth, lightDepth, sceneSer, p, v);
 }
 
+__global__ void __launch_bounds__(64) k_eval_batch_hess(int camDepth, int lightDepth, int n, const float *sceneSer, const float *primary,
+                                                        int primaryStride, const float *vertParams, int vertStride, float *logLum,
+                                                        float *grad, float *hess, int dim) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    logLum[i] = path_loglum_hess(camDepth, lightDepth, sceneSer, primary + (size_t)i * primaryStride,
+                                 vertParams + (size_t)i * vertStride, grad + (size_t)i * dim, hess + (size_t)i * dim * dim);
+}
+
 template <class T> int upload(const std::vector<T> &v, T **out) {
     *out = nullptr;
     const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
@@ -80,6 +89,7 @@ struct lmc_ctx {
     unsigned long long *statsDev = nullptr;
     WaveLists wl{};
     int *listMem = nullptr;
+    H2mcSide *sides = nullptr; int sidesCap = 0;
     int listCap = 0;
     uint64_t launches = 0;
     double lastMs = 0.0;
@@ -111,6 +121,14 @@ int chains_begin(lmc_ctx *c) {
         c->wl.large = p; p += n; c->wl.largeCount = p;
         c->listCap = n;
     }
+    if (c->sc.opt.h2mc) {
+        if (c->sidesCap < n) {
+            if (c->sides) { cudaFree(c->sides); c->sides = nullptr; }
+            CK(cudaMalloc((void **)&c->sides, sizeof(H2mcSide) * (size_t)n));
+            c->sidesCap = n;
+        }
+        CK(cudaMemsetAsync(c->sides, 0, sizeof(H2mcSide) * (size_t)n, c->stream));
+    }
     c->launches++;
     CK(d == 4 ? launch_chain_init_4(c->stream, st, n, c->desc.chain_base, c->initLs)
               : (d == 8 ? launch_chain_init_8(c->stream, st, n, c->desc.chain_base, c->initLs)
@@ -126,9 +144,9 @@ int run_chains(lmc_ctx *c, long long numSteps, unsigned char *dTrace, float *dAT
     void *st = c->states;
     CK(cudaEventRecord(c->ev0, c->stream));
     unsigned long long nl = 0;
-    CK(d == 4 ? launch_chain_run_4(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl)
-              : (d == 8 ? launch_chain_run_8(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl)
-                        : launch_chain_run_12(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl)));
+    CK(d == 4 ? launch_chain_run_4(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl, c->sides)
+              : (d == 8 ? launch_chain_run_8(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl, c->sides)
+                        : launch_chain_run_12(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl, c->sides)));
     c->launches += nl;
     CK(cudaEventRecord(c->ev1, c->stream));
     return LMC_OK;
@@ -218,7 +236,7 @@ int lmc_create(const lmc_scene *scene, int32_t device, lmc_ctx **out) {
     CK(cudaSetDevice(device));
     const lmc_host::SceneStore &s = scene->store;
     if (s.head.opt.maxDepth < 2 || s.head.opt.maxDepth > 12) return fail(LMC_ERR_UNSUPPORTED, "maxdepth must be in [2, 12]");
-    if (s.head.opt.h2mc) return fail(LMC_ERR_UNSUPPORTED, "h2mc mutation is not implemented in this build");
+    if (s.head.opt.h2mc && s.head.opt.maxDepth > 8) return fail(LMC_ERR_UNSUPPORTED, "h2mc needs maxdepth <= 8 (dense Gaussians are stored for dim <= 16)");
     if (s.head.opt.largeStepMultiplexed) return fail(LMC_ERR_UNSUPPORTED, "largestepmultiplexed is not supported");
     lmc_ctx *c = new lmc_ctx();
     c->device = device;
@@ -254,6 +272,7 @@ void lmc_destroy(lmc_ctx *c) {
     if (c->film && c->filmOwned) cudaFree(c->film);
     if (c->statsDev) cudaFree(c->statsDev);
     if (c->listMem) cudaFree(c->listMem);
+    if (c->sides) cudaFree(c->sides);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
@@ -362,7 +381,7 @@ int32_t lmc_vert_param_size(int32_t cam_depth, int32_t light_depth) {
 }
 
 int lmc_eval_batch(lmc_ctx *c, int32_t cam_depth, int32_t light_depth, int32_t n, const float *lens, const float *primary,
-                   const float *vert_params, int32_t vert_stride, float *log_lum, float *grad) {
+                   const float *vert_params, int32_t vert_stride, float *log_lum, float *grad, float *hess) {
     (void)lens;   // Static mode: the screen position is primary[..], `lens` is unused by the generated code too
     if (!c || !primary || !vert_params || !log_lum || n < 0) return fail(LMC_ERR_ARG, "bad argument");
     if (cam_depth < 1 || light_depth < 0 || cam_depth + light_depth < 3) return fail(LMC_ERR_ARG, "no path function for this (camDepth, lightDepth)");
@@ -372,7 +391,9 @@ int lmc_eval_batch(lmc_ctx *c, int32_t cam_depth, int32_t light_depth, int32_t n
     if (n == 0) return LMC_OK;
     CK(cudaSetDevice(c->device));
     const int dim = 2 * (len > 2 ? len : 2);
-    float *dS = nullptr, *dP = nullptr, *dV = nullptr, *dL = nullptr, *dG = nullptr;
+    if (hess && !grad) return fail(LMC_ERR_ARG, "hess requires grad");
+    float *dS = nullptr, *dP = nullptr, *dV = nullptr, *dL = nullptr, *dG = nullptr, *dH = nullptr;
+    if (hess) CK(cudaMalloc((void **)&dH, sizeof(float) * (size_t)n * dim * dim));
     CK(cudaMalloc((void **)&dS, 38 * sizeof(float)));
     CK(cudaMalloc((void **)&dP, sizeof(float) * (size_t)n * (dim + 1)));
     CK(cudaMalloc((void **)&dV, sizeof(float) * (size_t)n * vert_stride));
@@ -381,13 +402,15 @@ int lmc_eval_batch(lmc_ctx *c, int32_t cam_depth, int32_t light_depth, int32_t n
     CK(cudaMemcpyAsync(dS, c->sc.sceneSer, 38 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(dP, primary, sizeof(float) * (size_t)n * (dim + 1), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(dV, vert_params, sizeof(float) * (size_t)n * vert_stride, cudaMemcpyHostToDevice, c->stream));
-    k_eval_batch<<<(n + 63) / 64, 64, 0, c->stream>>>(cam_depth, light_depth, n, dS, dP, dim + 1, dV, vert_stride, dL, dG, dim);
+    if (hess) k_eval_batch_hess<<<(n + 63) / 64, 64, 0, c->stream>>>(cam_depth, light_depth, n, dS, dP, dim + 1, dV, vert_stride, dL, dG, dH, dim);
+    else k_eval_batch<<<(n + 63) / 64, 64, 0, c->stream>>>(cam_depth, light_depth, n, dS, dP, dim + 1, dV, vert_stride, dL, dG, dim);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(log_lum, dL, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     if (grad) CK(cudaMemcpyAsync(grad, dG, sizeof(float) * (size_t)n * dim, cudaMemcpyDeviceToHost, c->stream));
+    if (hess) CK(cudaMemcpyAsync(hess, dH, sizeof(float) * (size_t)n * dim * dim, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(dS); cudaFree(dP); cudaFree(dV); cudaFree(dL); if (dG) cudaFree(dG);
+    cudaFree(dS); cudaFree(dP); cudaFree(dV); cudaFree(dL); if (dG) cudaFree(dG); if (dH) cudaFree(dH);
     return LMC_OK;
 }
 

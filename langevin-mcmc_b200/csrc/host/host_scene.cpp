@@ -537,6 +537,13 @@ Options default_options() {
     o.perturbStdDev = 0.01f; o.roughnessThreshold = 0.05f; o.largeStepProbability = 0.05f;
     o.largeStepProbScale = 1.0f; o.malaGN = 100.0f; o.malaStepsize = 0.005f; o.malaStdDev = 0.005f;
     o.discreteStdDev = 0.01f; o.uniformMixingProbability = 0.1f; o.lsRatio = 0.1f;
+    // H2MCParam(sigma, L = Float(M_PI / 2.0)), src/h2mc.h:9-16 (float exp/sin/cos as in the reference)
+    const float L = (float)(M_PI / 2.0);
+    o.h2mcL = L;
+    o.h2mcPosScale = 0.5f * (expf(L) - expf(-L)) * 0.5f * (expf(L) - expf(-L));
+    o.h2mcPosOffset = 0.5f * (expf(L) + expf(-L) - 1.0f);
+    o.h2mcNegScale = sinf(L) * sinf(L);
+    o.h2mcNegOffset = -(cosf(L) - 1.0f);
     return o;
 }
 

@@ -52,18 +52,21 @@ void run_chains_t(const Scene &sc, int numChains, int chainBase, int totalChains
         films[w].assign((size_t)W * H * 3, 0.0f);
         HostFilm hf; hf.p = films[w].data();
         ChainState<MAXD> *cs = new ChainState<MAXD>();
+        H2mcSide *side = new H2mcSide();
         uint32_t tab[64];
         for (;;) {
             const int i = next.fetch_add(1);
             if (i >= numChains) break;
             const int gid = chainBase + i;
             chain_state_init(*cs, initLs ? initLs[gid] : 0.0f);
+            memset(side, 0, sizeof(*side));
             chain_run(sc, rp, gid, *cs, numSteps, tab, 1, hf, trace ? trace + (size_t)i * numSteps : nullptr,
-                      aTrace ? aTrace + (size_t)i * numSteps : nullptr, 1);
+                      aTrace ? aTrace + (size_t)i * numSteps : nullptr, 1, side);
             for (int k = 0; k < 4; k++) { tstats[w][k] += cs->nPropose[k]; tstats[w][4 + k] += cs->nAccept[k]; }
             tstats[w][8] += cs->gradStats[0]; tstats[w][9] += cs->gradStats[1];
         }
         delete cs;
+        delete side;
     };
     std::vector<std::thread> pool;
     for (int w = 0; w < threads; w++) pool.emplace_back(work, w);
@@ -227,6 +230,26 @@ int lmco_eval_batch(void *h, int camDepth, int lightDepth, int n, const float *p
         if (grad) logLum[i] = path_loglum_grad(camDepth, lightDepth, sceneSer, p, v, grad + (size_t)i * dim);
         else logLum[i] = path_loglum(camDepth, lightDepth, sceneSer, p, v);
     }
+    return 0;
+}
+// gradient + Hessian (second-order forward mode); hess n x dim x dim row-major
+int lmco_eval_batch_hess(void *h, int camDepth, int lightDepth, int n, const float *primary, int primaryStride,
+                         const float *vertParams, int vertStride, float *logLum, float *grad, float *hess) {
+    const lmc_host::SceneStore &st = ((OScene *)h)->store;
+    float sceneSer[38]; memcpy(sceneSer, st.head.sceneSer, sizeof(sceneSer));
+    const int dim = primary_param_size(camDepth, lightDepth) - 1;
+    if (dim > LMC_HESS_MAXDIM) return -1;
+    for (int i = 0; i < n; i++)
+        logLum[i] = path_loglum_hess(camDepth, lightDepth, sceneSer, primary + (size_t)i * primaryStride,
+                                     vertParams + (size_t)i * vertStride, grad + (size_t)i * dim, hess + (size_t)i * dim * dim);
+    return 0;
+}
+// Jacobi eigen-solver probe: A n x n symmetric row-major -> V (columns = eigenvectors), w ascending
+int lmco_jacobi(int n, const float *A, float *V, float *w) {
+    float tmp[LMC_H2MC_DIM * LMC_H2MC_DIM];
+    if (n < 1 || n > LMC_H2MC_DIM) return -1;
+    memcpy(tmp, A, sizeof(float) * n * n);
+    jacobi_eigen(n, tmp, V, w);
     return 0;
 }
 int lmco_scene_serialized(void *h, float *out38) { memcpy(out38, ((OScene *)h)->store.head.sceneSer, 38 * sizeof(float)); return 0; }
