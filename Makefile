@@ -4,10 +4,10 @@
 PKG      := langevin-mcmc_b200
 CORE_H   := $(wildcard $(PKG)/csrc/core/*.h) $(wildcard $(PKG)/csrc/host/*.h)
 CXX      := $(shell which g++)
-CXXFLAGS := -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -Wall -Wno-unused-function -pthread
+CXXFLAGS := -O2 -std=c++17 -fPIC -mfma -ffp-contract=off -fno-fast-math -Wall -Wno-unused-function -pthread
 NVCC     := nvcc
 NVFLAGS  := -ccbin /usr/bin/g++ -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --fmad=false \
-            -Xcompiler -fPIC,-ffp-contract=off,-pthread -Xptxas -v
+            -Xcompiler -fPIC,-mfma,-ffp-contract=off,-pthread -Xptxas -v
 
 all: oracle lib
 

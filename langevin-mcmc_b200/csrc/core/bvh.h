@@ -152,7 +152,7 @@ LMC_HD_NOINLINE void fill_isect(const Scene &sc, const Ray &ray, const Hit &h, I
     const V3 e1 = ld3(tg.e1), e2 = ld3(tg.e2);
     isect.geomNormal = normalize(cross(e1, e2));
     const float w = 1.0f - h.u - h.v;
-    isect.position = ray.org + h.t * ray.dir;
+    isect.position = madd(ray.dir, h.t, ray.org);
     isect.shadingNormal = normalize(w * ld3(ts.n0) + h.u * ld3(ts.n1) + h.v * ld3(ts.n2));
     if (dot(isect.geomNormal, isect.shadingNormal) < 0.0f) {
         isect.geomNormal = -isect.geomNormal;

@@ -52,13 +52,18 @@ template <class S, int N> struct ADTraits<DualT<S, N>> {
 template <class T> LMC_HD T ad_const(float c) { return ADTraits<T>::make(c); }
 
 #define LMC_DT template <class S, int N> LMC_HD DualT<S, N>
+// a * b + c: one fused multiply-add on floats (explicit, see vec.h), plain composition on duals
+LMC_HD float ad_mad(float a, float b, float c) { return fmaf(a, b, c); }
+template <class S, int N> LMC_HD DualT<S, N> operator+(const DualT<S, N> &a, const DualT<S, N> &b);
+template <class S, int N> LMC_HD DualT<S, N> operator*(const DualT<S, N> &a, const DualT<S, N> &b);
+template <class S, int N> LMC_HD DualT<S, N> ad_mad(const DualT<S, N> &a, const DualT<S, N> &b, const DualT<S, N> &c) { return a * b + c; }
 LMC_DT operator+(const DualT<S, N> &a, const DualT<S, N> &b) { DualT<S, N> r; r.v = a.v + b.v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] + b.d[i]; return r; }
 LMC_DT operator-(const DualT<S, N> &a, const DualT<S, N> &b) { DualT<S, N> r; r.v = a.v - b.v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] - b.d[i]; return r; }
 LMC_DT operator-(const DualT<S, N> &a) { DualT<S, N> r; r.v = -a.v; for (int i = 0; i < N; i++) r.d[i] = -a.d[i]; return r; }
-LMC_DT operator*(const DualT<S, N> &a, const DualT<S, N> &b) { DualT<S, N> r; r.v = a.v * b.v; for (int i = 0; i < N; i++) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+LMC_DT operator*(const DualT<S, N> &a, const DualT<S, N> &b) { DualT<S, N> r; r.v = a.v * b.v; for (int i = 0; i < N; i++) r.d[i] = ad_mad(a.d[i], b.v, a.v * b.d[i]); return r; }
 LMC_DT operator/(const DualT<S, N> &a, const DualT<S, N> &b) {
     DualT<S, N> r; const S ib = 1.0f / b.v; r.v = a.v * ib;
-    for (int i = 0; i < N; i++) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
+    for (int i = 0; i < N; i++) r.d[i] = ad_mad(-r.v, b.d[i], a.d[i]) * ib;
     return r;
 }
 LMC_DT operator+(const DualT<S, N> &a, float b) { DualT<S, N> r = a; r.v = a.v + b; return r; }
@@ -120,7 +125,7 @@ LMC_DT ad_atan2(const DualT<S, N> &y, const DualT<S, N> &x) {
     const S invNorm = 1.0f / (x.v * x.v + y.v * y.v);
     DualT<S, N> r; r.v = ad_atan2(y.v, x.v);
     const S ky = x.v * invNorm, kx = -(y.v * invNorm);
-    for (int i = 0; i < N; i++) r.d[i] = ky * y.d[i] + kx * x.d[i];
+    for (int i = 0; i < N; i++) r.d[i] = ad_mad(ky, y.d[i], kx * x.d[i]);
     return r;
 }
 LMC_HD float ad_acos(float a) { return dm_acos(a); }
@@ -141,17 +146,18 @@ template <class T> LMC_HD TV3<T> operator-(const TV3<T> &a) { return tv3<T>(-a.x
 template <class T> LMC_HD TV3<T> operator*(const TV3<T> &a, const T &s) { return tv3<T>(a.x * s, a.y * s, a.z * s); }
 template <class T> LMC_HD TV3<T> operator*(const T &s, const TV3<T> &a) { return tv3<T>(s * a.x, s * a.y, s * a.z); }
 template <class T> LMC_HD TV3<T> tcmul(const TV3<T> &a, const TV3<T> &b) { return tv3<T>(a.x * b.x, a.y * b.y, a.z * b.z); }
-template <class T> LMC_HD T tdot(const TV3<T> &a, const TV3<T> &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <class T> LMC_HD T tdot(const TV3<T> &a, const TV3<T> &b) { return ad_mad(a.z, b.z, ad_mad(a.y, b.y, a.x * b.x)); }
 template <class T> LMC_HD TV3<T> tcross(const TV3<T> &a, const TV3<T> &b) {
-    return tv3<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+    return tv3<T>(ad_mad(a.y, b.z, -(a.z * b.y)), ad_mad(a.z, b.x, -(a.x * b.z)), ad_mad(a.x, b.y, -(a.y * b.x)));
 }
-template <class T> LMC_HD T tlength_squared(const TV3<T> &v) { return ad_square(v.x) + ad_square(v.y) + ad_square(v.z); }
+template <class T> LMC_HD T tlength_squared(const TV3<T> &v) { return ad_mad(v.z, v.z, ad_mad(v.y, v.y, v.x * v.x)); }
 template <class T> LMC_HD TV3<T> tnormalize(const TV3<T> &v) {
-    const T il = ad_inverse(ad_sqrt(v.x * v.x + v.y * v.y + v.z * v.z));
+    const T il = ad_inverse(ad_sqrt(tlength_squared(v)));
     return v * il;
 }
 template <class T> LMC_HD T tdistance_squared(const TV3<T> &a, const TV3<T> &b) {
-    return ad_square(a.x - b.x) + ad_square(a.y - b.y) + ad_square(a.z - b.z);
+    const T dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    return ad_mad(dz, dz, ad_mad(dy, dy, dx * dx));
 }
 template <class T> LMC_HD T tluminance(const TV3<T> &v) { return v.x * 0.212671f + v.y * 0.715160f + v.z * 0.072169f; }
 // constant-vector (V3) mixed helpers

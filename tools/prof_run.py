@@ -9,7 +9,7 @@ m = importlib.util.module_from_spec(spec); sys.modules["lmc_b200"] = m; spec.loa
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 launches = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-sc = m.ParseScene(os.path.join(ROOT, "scenes", "torus", "lmc.xml"))
+sc = m.ParseScene(os.path.join(ROOT, "scenes", os.environ.get("LMC_SCENE", "torus/lmc.xml")))
 sc.options["maxdepth"] = int(os.environ.get("LMC_MAXDEPTH", "8"))
 chains = 1 << lg
 norm, init_small = m.MLTInit(sc, 300000, min(chains, 8192), 32)
