@@ -74,10 +74,16 @@ LMC_HD bool box_test(float bminx, float bminy, float bminz, float bmaxx, float b
 // "while-while" traversal: every lane first descends through inner nodes until it holds a leaf
 // (or runs out of work), then all lanes intersect their leaves together -- the two loop bodies no
 // longer serialise against each other inside a warp.
+#ifdef LMC_BVH_STATS
+static long long g_bvhNodes = 0, g_bvhTris = 0, g_bvhRays = 0;
+#endif
 template <bool ANY_HIT>
 LMC_HD_NOINLINE Hit bvh_traverse(const Scene &sc, const Ray &ray, float minT, float maxT) {
     Hit best; best.tid = -1; best.t = maxT; best.u = 0.0f; best.v = 0.0f;
     if (sc.numNodes == 0) return best;
+#ifdef LMC_BVH_STATS
+    g_bvhRays++;
+#endif
     const V3 invDir = mk3(inverse(ray.dir.x), inverse(ray.dir.y), inverse(ray.dir.z));
     const V3 negOrgInv = mk3(-(ray.org.x * invDir.x), -(ray.org.y * invDir.y), -(ray.org.z * invDir.z));
     int stack[LMC_BVH_STACK];
@@ -85,6 +91,9 @@ LMC_HD_NOINLINE Hit bvh_traverse(const Scene &sc, const Ray &ray, float minT, fl
     int cur = 0;
     for (;;) {
         while (cur >= 0) {
+#ifdef LMC_BVH_STATS
+            g_bvhNodes++;
+#endif
             const BvhNode *n = sc.nodes + cur;
             const F4 a = ld4(&n->lmin[0]);     // lmin.xyz, lmax.x
             const F4 b = ld4(&n->lmax[1]);     // lmax.yz, rmin.xy
@@ -113,6 +122,9 @@ LMC_HD_NOINLINE Hit bvh_traverse(const Scene &sc, const Ray &ray, float minT, fl
             const int first = enc >> 3;
             const int count = (enc & 7) + 1;
             for (int i = 0; i < count; ++i) {
+#ifdef LMC_BVH_STATS
+                g_bvhTris++;
+#endif
                 const int tid = first + i;
                 float t, u, v;
                 if (tri_test(sc.tris[tid], ray, minT, best.t, t, u, v)) {

@@ -415,10 +415,13 @@ LMC_HD void phase_begin(const Scene &sc, const RunParams &rp, long long sampleId
 }
 
 // Phase 1 / 3: PSS gradient of the current state / of the proposal (no RNG).
-template <int MAXD>
+// ORDER: -1 = decided at run time (host twin); 1 = gradient only (LMC); 2 = gradient + Hessian (H2MC)
+template <int MAXD, int ORDER = -1>
 LMC_HD void phase_gradient(const Scene &sc, const MarkovState<MAXD> &st, StepScratch<MAXD> &ss, unsigned int *gradStats,
                            H2mcSide *side) {
-    if (ss.kind == STEP_H2MC) {
+    if (ORDER == 1 && ss.kind == STEP_H2MC) return;
+    if (ORDER == 2 && ss.kind != STEP_H2MC) return;
+    if (ORDER != 1 && ss.kind == STEP_H2MC) {
         // gradient + Hessian, IsFinite guard on both (src/mutation_h2mc.h:74-86)
         const int dim = path_dimension(st.path);
         path_hessian(sc, st.path, ss.grad, side->hess);
@@ -433,17 +436,22 @@ LMC_HD void phase_gradient(const Scene &sc, const MarkovState<MAXD> &st, StepScr
         if (gradStats) gradStats[0]++;
         return;
     }
+    if (ORDER == 2) return;
     mala_eval_gradient(sc, st, ss.grad, gradStats);
 }
 
 // Phase 2: draw the proposal and trace it.
 // SmallStep::Mutate (src/mutation_small.h:16-55), MALASmallStep::Mutate up to the proposal's
 // gradient (src/mutation_mala.h:83-176), LargeStep::Mutate (src/mutation_large.h:31-127).
-template <int MAXD>
+// ONLY: -1 = any kind (host twin); 0 = large steps only; 1 = small steps only (the device compiles
+// one kernel per case so each carries half of the code)
+template <int MAXD, int ONLY = -1>
 LMC_HD void phase_propose(const Scene &sc, const RunParams &rp, MarkovState<MAXD> &cur, MarkovState<MAXD> &prop,
                           ChainVars<MAXD> &ch, Rng &rng, StepScratch<MAXD> &ss, H2mcSide *side, int curSlot) {
     const float normalization = rp.normalization;
-    if (ss.kind == STEP_LARGE) {
+    if (ONLY == 1 && ss.kind == STEP_LARGE) return;
+    if (ONLY == 0 && ss.kind != STEP_LARGE) return;
+    if (ONLY != 1 && ss.kind == STEP_LARGE) {
         ch.lastMutationType = MUT_LARGE;
         float a = 1.0f;
         ContribList<Limits<MAXD>::MAXC> contribs; contribs.clear();
@@ -478,6 +486,7 @@ LMC_HD void phase_propose(const Scene &sc, const RunParams &rp, MarkovState<MAXD
         ss.a = a;
         return;
     }
+    if (ONLY == 0) return;
     ContribList<2> contribs; contribs.clear();
     const int dim = path_dimension(cur.path);
     if (ss.kind == STEP_ISO) {

@@ -157,17 +157,17 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_begin(const __grid_con
 #ifndef LMC_PROP_MINB
 #define LMC_PROP_MINB 4
 #endif
-template <int MAXD>
+template <int MAXD, int ORDER>
 __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_GRAD_MINB) k_wave_grad(const __grid_constant__ Scene sc, ChainRec<MAXD> *states, int n,
                                                                 const int *list, const int *count, int which, H2mcSide *sides) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= *count) return;
     const int i = list[t];
     ChainState<MAXD> &cs = states[i].cs;
-    phase_gradient(sc, cs.st[cs.curIdx ^ which], cs.ss, cs.gradStats, sides ? sides + i : nullptr);
+    phase_gradient<MAXD, ORDER>(sc, cs.st[cs.curIdx ^ which], cs.ss, cs.gradStats, sides ? sides + i : nullptr);
 }
 
-template <int MAXD>
+template <int MAXD, int ONLY>
 __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_PROP_MINB) k_wave_propose(const __grid_constant__ Scene sc, RunParams rp, int chainBase,
                                                                    ChainRec<MAXD> *states, int n, const int *list, const int *count,
                                                                    WaveLists wl, H2mcSide *sides) {
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_PROP_MINB) k_wave_propose
     uint32_t tab[64];
     ChainState<MAXD> &cs = states[i].cs;
     Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
-    phase_propose(sc, rp, cs.st[cs.curIdx], cs.st[cs.curIdx ^ 1], cs.ch, rng, cs.ss, sides ? sides + i : nullptr, cs.curIdx);
+    phase_propose<MAXD, ONLY>(sc, rp, cs.st[cs.curIdx], cs.st[cs.curIdx ^ 1], cs.ch, rng, cs.ss, sides ? sides + i : nullptr, cs.curIdx);
     rng_close(rng, cs);
     const MarkovState<MAXD> &prop = cs.st[cs.curIdx ^ 1];
     sort_key_set(wl.propGrad, i, cs.ss.needPropGrad ? class_key(prop.sp.camDepth, prop.sp.lightDepth, 0) : -1);
@@ -249,12 +249,14 @@ LMC_DECLARE_CHAIN(12)
             k_wave_begin<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl); \
             k_sort_scan<<<2, LMC_NKEYS, 0, st>>>(wl.small_, wl.curGrad, 2); \
             k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.small_, wl.curGrad, 2); \
-            k_wave_grad<MAXD><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides); \
-            k_wave_propose<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.small_.list, wl.small_.count, wl, sides); \
-            k_wave_propose<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.large, wl.largeCount, wl, sides); \
+            if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides); \
+            else k_wave_grad<MAXD, 1><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides); \
+            k_wave_propose<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.small_.list, wl.small_.count, wl, sides); \
+            k_wave_propose<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.large, wl.largeCount, wl, sides); \
             k_sort_scan<<<1, LMC_NKEYS, 0, st>>>(wl.propGrad, wl.propGrad, 1); \
             k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.propGrad, wl.propGrad, 1); \
-            k_wave_grad<MAXD><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides); \
+            if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides); \
+            else k_wave_grad<MAXD, 1><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides); \
             k_wave_finish<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides); \
             *launches += 10; \
             e = cudaGetLastError(); \
