@@ -13,7 +13,7 @@ all: oracle lib
 
 oracle: oracle/liblmc_oracle.so
 oracle/liblmc_oracle.so: oracle/oracle_api.cpp $(PKG)/csrc/host/host_scene.cpp $(CORE_H)
-	$(CXX) $(CXXFLAGS) -shared -o $@ oracle/oracle_api.cpp $(PKG)/csrc/host/host_scene.cpp -lz
+	$(CXX) $(CXXFLAGS) -shared -o $@ oracle/oracle_api.cpp $(PKG)/csrc/host/host_scene.cpp -lz -ldl
 
 CUDA_SRC := $(PKG)/csrc/cuda
 CUDA_OBJ := $(PKG)/build/lmc_abi.o $(PKG)/build/chain_inst_4.o $(PKG)/build/chain_inst_8.o $(PKG)/build/chain_inst_12.o

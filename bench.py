@@ -101,6 +101,9 @@ def cpu_chain_rate(threads, budget_s, maxdepth=MAXDEPTH):
     o = Oracle()
     h = o.load(SCENE_XML)
     o.set_option(h, "maxdepth", maxdepth)
+    # when the reference's generated gradient code was built (oracle/_ref), the CPU arm evaluates
+    # gradients with it (reverse mode, as the reference does) instead of the twin's evaluator
+    ref_grad = o.use_reference_gradient(True) > 0
     chains, steps = 256 * threads, 32
     norm, init_ls = o.mlt_init(h, 300000, chains, 32)
     t0 = time.time()
@@ -112,7 +115,8 @@ def cpu_chain_rate(threads, budget_s, maxdepth=MAXDEPTH):
     t0 = time.time()
     o.run_chains(h, chains, steps2, norm, init_ls, threads=threads, want_trace=False, samples_per_chain=steps2)
     dt = time.time() - t0
-    return chains * steps2 / dt, "%d chains x %d mutations, torus maxdepth %d, %d threads" % (chains, steps2, maxdepth, threads)
+    return chains * steps2 / dt, "%d chains x %d mutations, torus maxdepth %d, %d threads, gradient = %s" % (
+        chains, steps2, maxdepth, threads, "reference generated code (oracle/_ref)" if ref_grad else "oracle evaluator")
 
 
 def run_reference_arm(args):

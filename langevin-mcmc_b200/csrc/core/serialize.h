@@ -142,11 +142,32 @@ LMC_HD bool grad_supported(const Scene &sc, const Path<MAXD> &path) {
 #define LMC_GRAD_MAX_SURF 8
 #define LMC_GRAD_SCRATCH (3 + 1 + LMC_SER_LIGHT + LMC_GRAD_MAX_SURF * (LMC_SER_SHAPE + 2 + LMC_SER_BSDF + 1) + LMC_SER_LIGHT + LMC_SER_BSDF + 1)
 
+#if defined(LMC_ORACLE_HOOK) && !defined(__CUDA_ARCH__)
+// Test-only hook (oracle build): lets "Oracle-R" route the gradient through the REFERENCE's own
+// generated reverse-mode code (oracle/_ref) instead of the evaluator below.  Never compiled into
+// the product.
+typedef void (*RefGradHook)(int camDepth, int lightDepth, const float *lens, const float *primary, const float *sceneSer,
+                            float *vertParams, int nVert, float *grad, int dim);
+inline RefGradHook &ref_grad_hook() { static thread_local RefGradHook h = nullptr; return h; }
+#endif
+
 // dervFunc(screenPos, primary, sceneParams, vertParams, vGrad, NULL) for the path's (c, l)
 template <int MAXD>
 LMC_HD_NOINLINE void path_gradient(const Scene &sc, const Path<MAXD> &path, float *grad) {
     float primary[2 * LMC_GRAD_MAX_SURF + 1 + 4];
     float vertParams[LMC_GRAD_SCRATCH];
+#if defined(LMC_ORACLE_HOOK) && !defined(__CUDA_ARCH__)
+    if (ref_grad_hook()) {
+        const int dim_ = path_dimension(path);
+        float big[1100];
+        for (int i = 0; i < 1100; i++) big[i] = 0.0f;
+        float prim_[32];
+        const int nv = serialize_path(sc, path, prim_, big);
+        const float lens[2] = {path.screenPos.x, path.screenPos.y};
+        ref_grad_hook()(path.camDepth, path.lgtDepth, lens, prim_, sc.sceneSer, big, nv, grad, dim_);
+        return;
+    }
+#endif
     const int dim = path_dimension(path);
     const int nSurf = (path.camDepth > 1 ? path.camDepth - 1 : 0) + (path.lgtDepth > 1 ? path.lgtDepth - 1 : 0);
     if (nSurf > LMC_GRAD_MAX_SURF || dim > 2 * LMC_GRAD_MAX_SURF) {   // outside the gate: caller should not ask

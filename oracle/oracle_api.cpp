@@ -17,6 +17,8 @@
 // tests/golden/ holds vectors produced by that code.  Embree, Eigen, OIIO and libm are not
 // importable here: closest-hit tie-breaking, texture filtering and transcendental rounding are
 // "parity unpinned"  and defined by this oracle.
+#define LMC_ORACLE_HOOK 1
+#include <dlfcn.h>
 #include <atomic>
 #include <cstring>
 #include <string>
@@ -29,6 +31,26 @@
 using namespace lmc;
 
 namespace {
+// ---- Oracle-R: the reference's own generated reverse-mode gradient (oracle/_ref) -----------------
+typedef void (*RefDerv)(const float *, const float *, const float *, const float *, float *, float *);
+RefDerv g_refDerv[10][9];
+bool g_refLoaded = false;
+void ref_gradient(int c, int l, const float *lens, const float *primary, const float *sceneSer, float *vert, int nVert,
+                  float *grad, int dim) {
+    for (int i = 0; i < dim; i++) grad[i] = 0.0f;
+    if (c < 1 || c > 9 || l < 0 || l > 8 || !g_refDerv[c][l]) return;
+    // The reference reuses one vertParams buffer, so the shape block of an env-map miss holds stale
+    // data of an earlier path (src/path.cpp:2547-2550); an all-zero block makes its reverse sweep
+    // return NaN.  Mimic the common case: a valid (the first vertex's) triangle.
+    if (l == 0) {
+        float *blk = vert + 3 + (c - 2) * 59;
+        bool zero = true;
+        for (int i = 0; i < 46; i++) if (blk[i] != 0.0f) zero = false;
+        if (zero) for (int i = 0; i < 46; i++) blk[i] = vert[3 + i];
+    }
+    (void)nVert;
+    g_refDerv[c][l](lens, primary, sceneSer, vert, grad, nullptr);
+}
 struct OScene { lmc_host::SceneStore store; };
 thread_local std::string g_err;
 
@@ -37,6 +59,7 @@ struct HostFilm {
     void add(int pix, int c, float v) { p[3 * pix + c] += v; }
 };
 
+bool g_useRef = false;
 template <int MAXD>
 void run_chains_t(const Scene &sc, int numChains, int chainBase, int totalChains, long long numSteps,
                   long long numSamplesThisChain, float normalization, const float *initLs, float *film,
@@ -49,6 +72,7 @@ void run_chains_t(const Scene &sc, int numChains, int chainBase, int totalChains
     std::vector<std::vector<unsigned long long>> tstats(threads, std::vector<unsigned long long>(10, 0ULL));
     std::atomic<int> next(0);
     auto work = [&](int w) {
+        ref_grad_hook() = (g_useRef && g_refLoaded) ? ref_gradient : nullptr;
         films[w].assign((size_t)W * H * 3, 0.0f);
         HostFilm hf; hf.p = films[w].data();
         ChainState<MAXD> *cs = new ChainState<MAXD>();
@@ -154,6 +178,30 @@ int lmco_run_chains(void *h, int numChains, int chainBase, int totalChains, long
     else if (sc.opt.maxDepth <= 12) run_chains_t<12>(sc, numChains, chainBase, totalChains, numSteps, numSamplesThisChain, normalization, initLs, film, trace, aTrace, threads, stats);
     else throw std::runtime_error("maxdepth > 12 is not supported");
     LMCO_CATCH
+}
+
+// Oracle-R switch: load oracle/_ref/libpathref_mala.so and route every MALA gradient of subsequent
+// lmco_run_chains calls through the reference's generated reverse-mode code (enable = 0 switches back
+// to the twin evaluator).  Returns the number of (c, l) functions resolved, or -1.
+int lmco_use_reference_gradient(const char *libPath, int enable) {
+    if (!enable) { g_useRef = false; return 0; }
+    if (!g_refLoaded) {
+        void *dl = dlopen(libPath, RTLD_NOW | RTLD_LOCAL);
+        if (!dl) { g_err = dlerror(); return -1; }
+        int n = 0;
+        for (int c = 1; c <= 9; c++) for (int l = 0; l <= 8; l++) {
+            char name[96];
+            snprintf(name, sizeof(name), "evaluate_path_bidir_mala_%d_%d_static_derv", c, l);
+            g_refDerv[c][l] = (RefDerv)dlsym(dl, name);
+            if (g_refDerv[c][l]) n++;
+        }
+        g_refLoaded = n > 0;
+        if (!g_refLoaded) { g_err = "no path functions found"; return -1; }
+    }
+    g_useRef = true;
+    int n = 0;
+    for (int c = 1; c <= 9; c++) for (int l = 0; l <= 8; l++) if (g_refDerv[c][l]) n++;
+    return n;
 }
 
 // plain bidirectional path tracing estimate of the image (sanity reference for the MLT film)

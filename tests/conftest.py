@@ -88,6 +88,13 @@ class Oracle:
         assert rc == 0, self.L.lmco_last_error()
         return film, trace, a, stats
 
+    def use_reference_gradient(self, enable):
+        """Oracle-R: route MALA gradients through oracle/_ref/libpathref_mala.so (reference's own code)."""
+        path = os.path.join(ROOT, "oracle", "_ref", "libpathref_mala.so")
+        if enable and not os.path.exists(path):
+            return -1
+        return self.L.lmco_use_reference_gradient(path.encode(), 1 if enable else 0)
+
     def sample_paths(self, h, seed, num_large_steps, perturb=True, max_len=8, max_records=20000):
         rec = self.REC_HEAD + 25 + self.VSTRIDE
         out = np.zeros((max_records, rec), np.float32)

@@ -34,6 +34,33 @@ def test_oracle_chain_loop_properties(oracle, torus_xml):
     assert np.isfinite(f1).all() and f1.sum() > 0
 
 
+def test_oracle_R_vs_T_divergence_statistics(oracle, torus_xml, ref_mala):
+    """Two-tier oracle: Oracle-R = the same chain loop with the REFERENCE's own
+    generated reverse-mode gradient (oracle/_ref); Oracle-T = the twin the GPU matches bit for bit.
+    Their decision strings cannot be identical (the reference's reverse sweep deviates from its own
+    forward-mode gradient on glass paths, App. B#13): the agreement is reported and bounded."""
+    h = oracle.load(torus_xml)
+    oracle.set_option(h, "maxdepth", 4)
+    chains, steps = 1024, 100            # BASELINE configs[0]
+    norm, ls = oracle.mlt_init(h, 300000, chains, 32)
+    fT, tT, aT, sT = oracle.run_chains(h, chains, steps, norm, ls, samples_per_chain=steps)
+    assert oracle.use_reference_gradient(True) == 42
+    try:
+        fR, tR, aR, sR = oracle.run_chains(h, chains, steps, norm, ls, samples_per_chain=steps)
+    finally:
+        oracle.use_reference_gradient(False)
+    same = (tT == tR).all(axis=1).mean()
+    first = np.where(tT != tR, np.arange(steps)[None, :], steps).min(axis=1)
+    accT, accR = sT[7] / sT[3], sR[7] / sR[3]
+    print("Oracle-R vs Oracle-T: identical 100-step decision strings %.1f%% of chains; median first divergence %d; "
+          "MALA acceptance T %.4f R %.4f; film sum T %.1f R %.1f" % (100 * same, int(np.median(first)), accT, accR, fT.sum(), fR.sum()))
+    assert same > 0.5
+    assert abs(accT - accR) < 0.02
+    assert abs(fT.sum() - fR.sum()) < 0.03 * fR.sum()
+    # step-type sequences agree wherever the chains have not diverged: first steps are always equal
+    assert np.array_equal(tT[:, 0], tR[:, 0])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("maxdepth,chains,steps", [(4, 1024, 100), (8, 512, 48), (12, 256, 24)])
 def test_cuda_trace_bit_identical_to_oracle(lmc, oracle, torus_xml, maxdepth, chains, steps):
