@@ -51,7 +51,8 @@ LMC_HD void chain_state_init(ChainState<MAXD> &cs, float initLsScore) {
 template <int MAXD, class FILM>
 LMC_HD void chain_run(const Scene &sc, const RunParams &rp, int globalChainId, ChainState<MAXD> &cs,
                       long long numSteps, uint32_t *tab, int stride, FILM &film,
-                      unsigned char *trace, float *aTrace, long long traceStride, H2mcSide *side = nullptr) {
+                      unsigned char *trace, float *aTrace, long long traceStride, H2mcSide *side = nullptr,
+                      StagedWork<MAXD> *staged = nullptr) {
     Rng rng; rng.tab = tab; rng.stride = stride;
     const uint64_t seed = (uint64_t)(long long)(globalChainId + sc.opt.seedOffset);
     if (!cs.seeded) {
@@ -62,7 +63,7 @@ LMC_HD void chain_run(const Scene &sc, const RunParams &rp, int globalChainId, C
     }
     for (long long k = 0; k < numSteps; k++) {
         const StepInfo info = chain_step(sc, rp, globalChainId, cs.sampleIdx, cs.st, cs.curIdx, cs.ch, rng, film,
-                                         cs.gradStats, cs.ss, side);
+                                         cs.gradStats, cs.ss, side, staged);
         cs.nPropose[info.mutationType] += 1u;
         cs.nAccept[info.mutationType] += (unsigned int)info.accepted;
         if (trace) trace[k * traceStride] = (unsigned char)(info.mutationType | (info.accepted << 2) | ((info.a > 0.0f) ? 8 : 0));

@@ -14,6 +14,7 @@
 // false, so every eligible MALA step evaluates a gradient.
 #pragma once
 #include "path.h"
+#include "stages.h"
 #include "serialize.h"
 
 namespace lmc {
@@ -443,68 +444,60 @@ LMC_HD void phase_gradient(const Scene &sc, const MarkovState<MAXD> &st, StepScr
 // Phase 2: draw the proposal and trace it.
 // SmallStep::Mutate (src/mutation_small.h:16-55), MALASmallStep::Mutate up to the proposal's
 // gradient (src/mutation_mala.h:83-176), LargeStep::Mutate (src/mutation_large.h:31-127).
-// ONLY: -1 = any kind (host twin); 0 = large steps only; 1 = small steps only (the device compiles
-// one kernel per case so each carries half of the code)
-template <int MAXD, int ONLY = -1>
-LMC_HD void phase_propose(const Scene &sc, const RunParams &rp, MarkovState<MAXD> &cur, MarkovState<MAXD> &prop,
-                          ChainVars<MAXD> &ch, Rng &rng, StepScratch<MAXD> &ss, H2mcSide *side, int curSlot) {
-    const float normalization = rp.normalization;
-    if (ONLY == 1 && ss.kind == STEP_LARGE) return;
-    if (ONLY == 0 && ss.kind != STEP_LARGE) return;
-    if (ONLY != 1 && ss.kind == STEP_LARGE) {
-        ch.lastMutationType = MUT_LARGE;
-        float a = 1.0f;
-        ContribList<Limits<MAXD>::MAXC> contribs; contribs.clear();
-        path_clear(prop.path);
-        const int minDepth = sc.opt.minDepth > 3 ? sc.opt.minDepth : 3;
-        generate_path_bidir(sc, minDepth, sc.opt.maxDepth, prop.path, contribs, rng);
-        prop.gaussianInitialized = 0;
-        if (contribs.n > 0) {
-            float cdf[Limits<MAXD>::MAXC + 1];
-            cdf[0] = 0.0f;
-            for (int i = 0; i < contribs.n; i++) cdf[i + 1] = cdf[i] + contribs.c[i].lsScore;
-            const float scoreSum = cdf[contribs.n];
-            const float invSc = inverse(scoreSum);
-            for (int i = 0; i <= contribs.n; i++) cdf[i] *= invSc;
-            const int it = upper_bound_f(cdf, contribs.n + 1, rng_uniform(rng));
-            const int contribId = dm_clampi(it - 1, 0, contribs.n - 1);
-            prop.sp = contribs.c[contribId];
-            prop.scoreSum = scoreSum;
-            if (cur.valid) {
-                const float probProposal = prop.sp.lsScore / prop.scoreSum;
-                const float probLast = ch.lastScore / ch.lastScoreSum;
-                a = dm_clamp((prop.sp.lsScore * probLast) / (cur.sp.lsScore * probProposal), 0.0f, 1.0f);
-            }
-            prop.nSplat = contribs.n;
-            for (int i = 0; i < contribs.n; i++) {
-                prop.splat[i].screenPos = contribs.c[i].screenPos;
-                prop.splat[i].contrib = contribs.c[i].contrib * (normalization / scoreSum);
-            }
-        } else {
-            a = 0.0f;
+// Each mutation is cut around its path-tracing call into a PRE part (everything before
+// GeneratePathBidir / PerturbPathBidir) and a POST part (everything after), so the wavefront can
+// run the tracing in between as per-vertex stages (stages.h) while the host twin calls the
+// monolithic path functions.
+
+// LargeStep::Mutate before GeneratePathBidir
+template <int MAXD>
+LMC_HD void propose_pre_large(MarkovState<MAXD> &prop, ChainVars<MAXD> &ch) {
+    ch.lastMutationType = MUT_LARGE;
+    path_clear(prop.path);
+}
+// LargeStep::Mutate after GeneratePathBidir (src/mutation_large.h:60-127): contribution choice, acceptance, splats
+template <int MAXD, class CL>
+LMC_HD void propose_post_large(const RunParams &rp, const MarkovState<MAXD> &cur, MarkovState<MAXD> &prop,
+                               const ChainVars<MAXD> &ch, Rng &rng, StepScratch<MAXD> &ss, const CL &contribs) {
+    float a = 1.0f;
+    prop.gaussianInitialized = 0;
+    if (contribs.n > 0) {
+        float cdf[Limits<MAXD>::MAXC + 1];
+        cdf[0] = 0.0f;
+        for (int i = 0; i < contribs.n; i++) cdf[i + 1] = cdf[i] + contribs.c[i].lsScore;
+        const float scoreSum = cdf[contribs.n];
+        const float invSc = inverse(scoreSum);
+        for (int i = 0; i <= contribs.n; i++) cdf[i] *= invSc;
+        const int it = upper_bound_f(cdf, contribs.n + 1, rng_uniform(rng));
+        const int contribId = dm_clampi(it - 1, 0, contribs.n - 1);
+        prop.sp = contribs.c[contribId];
+        prop.scoreSum = scoreSum;
+        if (cur.valid) {
+            const float probProposal = prop.sp.lsScore / prop.scoreSum;
+            const float probLast = ch.lastScore / ch.lastScoreSum;
+            a = dm_clamp((prop.sp.lsScore * probLast) / (cur.sp.lsScore * probProposal), 0.0f, 1.0f);
         }
-        ss.a = a;
-        return;
+        prop.nSplat = contribs.n;
+        for (int i = 0; i < contribs.n; i++) {
+            prop.splat[i].screenPos = contribs.c[i].screenPos;
+            prop.splat[i].contrib = contribs.c[i].contrib * (rp.normalization / scoreSum);
+        }
+    } else {
+        a = 0.0f;
     }
-    if (ONLY == 0) return;
-    ContribList<2> contribs; contribs.clear();
+    ss.a = a;
+}
+
+// small steps before PerturbPathBidir: the proposal offset in ss.offset, prop.path = cur.path
+template <int MAXD>
+LMC_HD void propose_pre_small(const Scene &sc, MarkovState<MAXD> &cur, MarkovState<MAXD> &prop, ChainVars<MAXD> &ch,
+                              Rng &rng, StepScratch<MAXD> &ss, H2mcSide *side, int curSlot) {
     const int dim = path_dimension(cur.path);
     if (ss.kind == STEP_ISO) {
         path_copy(prop.path, cur.path);
         NormalDist nd = normal_make(0.0f, sc.opt.perturbStdDev);
         ch.lastMutationType = MUT_SMALL;
         for (int i = 0; i < dim; i++) ss.offset[i] = normal_draw(nd, rng);
-        perturb_path_bidir(sc, ss.offset, prop.path, contribs, rng);
-        prop.gaussianInitialized = 0;
-        if (contribs.n > 0) {
-            prop.sp = contribs.c[0];
-            ss.a = dm_clamp(prop.sp.ssScore / cur.sp.ssScore, 0.0f, 1.0f);
-            prop.nSplat = 1;
-            prop.splat[0].screenPos = prop.sp.screenPos;
-            prop.splat[0].contrib = prop.sp.contrib * (normalization / prop.sp.lsScore);
-        } else {
-            ss.a = 0.0f;
-        }
         return;
     }
     if (ss.kind == STEP_H2MC) {
@@ -513,14 +506,6 @@ LMC_HD void phase_propose(const Scene &sc, const RunParams &rp, MarkovState<MAXD
         if (side->dense[curSlot]) generate_sample_dense(cur.gaussian, side->covL[curSlot], ss.offset, rng);
         else generate_sample(cur.gaussian, ss.offset, rng);
         path_copy(prop.path, cur.path);
-        perturb_path_bidir(sc, ss.offset, prop.path, contribs, rng);
-        if (contribs.n > 0) {
-            prop.sp = contribs.c[0];
-            ss.hasContrib = 1;
-            if (h2mc_grad_mode(sc, prop) == 2) ss.needPropGrad = 1;
-        } else {
-            ss.a = 0.0f;
-        }
         return;
     }
     // STEP_MALA
@@ -531,15 +516,99 @@ LMC_HD void phase_propose(const Scene &sc, const RunParams &rp, MarkovState<MAXD
     }
     generate_sample(cur.gaussian, ss.offset, rng);
     path_copy(prop.path, cur.path);
-    perturb_path_bidir(sc, ss.offset, prop.path, contribs, rng);
+}
+// small steps after PerturbPathBidir (contribs holds 0 or 1 entries)
+template <int MAXD, class CL>
+LMC_HD void propose_post_small(const Scene &sc, const RunParams &rp, const MarkovState<MAXD> &cur, MarkovState<MAXD> &prop,
+                               StepScratch<MAXD> &ss, const CL &contribs) {
+    if (ss.kind == STEP_ISO) {
+        prop.gaussianInitialized = 0;
+        if (contribs.n > 0) {
+            prop.sp = contribs.c[0];
+            ss.a = dm_clamp(prop.sp.ssScore / cur.sp.ssScore, 0.0f, 1.0f);
+            prop.nSplat = 1;
+            prop.splat[0].screenPos = prop.sp.screenPos;
+            prop.splat[0].contrib = prop.sp.contrib * (rp.normalization / prop.sp.lsScore);
+        } else {
+            ss.a = 0.0f;
+        }
+        return;
+    }
     if (contribs.n > 0) {
         prop.sp = contribs.c[0];
         ss.hasContrib = 1;
-        if (mala_grad_mode(sc, prop) == 2) ss.needPropGrad = 1;
+        if (ss.kind == STEP_H2MC) { if (h2mc_grad_mode(sc, prop) == 2) ss.needPropGrad = 1; }
+        else if (mala_grad_mode(sc, prop) == 2) ss.needPropGrad = 1;
     } else {
         ss.a = 0.0f;
     }
 }
+
+// ONLY: -1 = any kind (host twin); 0 = large steps only; 1 = small steps only
+template <int MAXD, int ONLY = -1>
+LMC_HD void phase_propose(const Scene &sc, const RunParams &rp, MarkovState<MAXD> &cur, MarkovState<MAXD> &prop,
+                          ChainVars<MAXD> &ch, Rng &rng, StepScratch<MAXD> &ss, H2mcSide *side, int curSlot) {
+    if (ONLY == 1 && ss.kind == STEP_LARGE) return;
+    if (ONLY == 0 && ss.kind != STEP_LARGE) return;
+    if (ONLY != 1 && ss.kind == STEP_LARGE) {
+        propose_pre_large(prop, ch);
+        ContribList<Limits<MAXD>::MAXC> contribs; contribs.clear();
+        const int minDepth = sc.opt.minDepth > 3 ? sc.opt.minDepth : 3;
+        generate_path_bidir(sc, minDepth, sc.opt.maxDepth, prop.path, contribs, rng);
+        propose_post_large(rp, cur, prop, ch, rng, ss, contribs);
+        return;
+    }
+    if (ONLY == 0) return;
+    ContribList<2> contribs; contribs.clear();
+    propose_pre_small(sc, cur, prop, ch, rng, ss, side, curSlot);
+    perturb_path_bidir(sc, ss.offset, prop.path, contribs, rng);
+    propose_post_small(sc, rp, cur, prop, ss, contribs);
+}
+
+// The same phase through the staged path functions (stages.h), ray queries answered on the spot:
+// the host-side model of the device wavefront (tests/test_staged.py compares it with phase_propose).
+struct ImmediateShadowSink {
+    const Scene *sc;
+    LMC_HD void emit(const Ray &ray, float dist, int, int *flag) { *flag = cand_resolve(*flag, scene_occluded(*sc, ray, dist)); }
+};
+template <int MAXD>
+LMC_HD void phase_propose_staged(const Scene &sc, const RunParams &rp, MarkovState<MAXD> &cur, MarkovState<MAXD> &prop,
+                                 ChainVars<MAXD> &ch, Rng &rng, StepScratch<MAXD> &ss, H2mcSide *side, int curSlot,
+                                 TraceState &ts, GenWork<MAXD, Limits<MAXD>::MAXC> &gw) {
+    ImmediateShadowSink sink; sink.sc = &sc;
+    DeferredList<ImmediateShadowSink> dl;
+    if (ss.kind == STEP_LARGE) {
+        propose_pre_large(prop, ch);
+        gw.n = 0;
+        dl.bind(gw.c, gw.flag, &gw.n, Limits<MAXD>::MAXC, &sink);
+        const int minDepth = sc.opt.minDepth > 3 ? sc.opt.minDepth : 3;
+        bool more = gen_stage_begin(sc, prop.path, ts, gw, rng);
+        while (more) {
+            const Hit h = bvh_traverse<false>(sc, ts.ray, ts.minT, ts.maxT);
+            if (ts.stage == TS_G_LGT) more = gen_stage_light(sc, minDepth, sc.opt.maxDepth, prop.path, ts, gw, dl, rng, h);
+            else more = gen_stage_camera(sc, minDepth, sc.opt.maxDepth, prop.path, ts, gw, dl, rng, h);
+        }
+        gw.n = deferred_compact(gw.c, gw.flag, gw.n);
+        propose_post_large(rp, cur, prop, ch, rng, ss, gw);
+        return;
+    }
+    propose_pre_small(sc, cur, prop, ch, rng, ss, side, curSlot);
+    ts.nCand = 0;
+    dl.bind(ts.cand, ts.candFlag, &ts.nCand, 2, &sink);
+    bool more = perturb_stage_begin(sc, ss.offset, prop.path, ts, rng);
+    while (more) {
+        const Hit h = bvh_traverse<false>(sc, ts.ray, ts.minT, ts.maxT);
+        if (ts.stage == TS_P_LGT) more = perturb_stage_light(sc, ss.offset, prop.path, ts, dl, rng, h);
+        else more = perturb_stage_camera(sc, ss.offset, prop.path, ts, dl, rng, h);
+    }
+    ContribList<2> contribs;
+    contribs.n = deferred_compact(ts.cand, ts.candFlag, ts.nCand);
+    for (int i = 0; i < contribs.n; i++) contribs.c[i] = ts.cand[i];
+    propose_post_small(sc, rp, cur, prop, ss, contribs);
+}
+
+template <int MAXD>
+struct StagedWork { TraceState ts; GenWork<MAXD, Limits<MAXD>::MAXC> gw; };
 
 struct StepInfo {          // what one iteration did (parity traces / stats)
     int mutationType;
@@ -631,10 +700,11 @@ LMC_HD StepInfo phase_finish(const Scene &sc, const RunParams &rp, int chainId, 
 template <int MAXD, class FILM>
 LMC_HD StepInfo chain_step(const Scene &sc, const RunParams &rp, int chainId, long long sampleIdx,
                            MarkovState<MAXD> *states, int &curIdx, ChainVars<MAXD> &ch, Rng &rng, FILM &film,
-                           unsigned int *gradStats, StepScratch<MAXD> &ss, H2mcSide *side) {
+                           unsigned int *gradStats, StepScratch<MAXD> &ss, H2mcSide *side, StagedWork<MAXD> *staged = nullptr) {
     phase_begin(sc, rp, sampleIdx, states[curIdx], ch, rng, ss);
     if (ss.needCurGrad) phase_gradient(sc, states[curIdx], ss, gradStats, side);
-    phase_propose(sc, rp, states[curIdx], states[curIdx ^ 1], ch, rng, ss, side, curIdx);
+    if (staged) phase_propose_staged(sc, rp, states[curIdx], states[curIdx ^ 1], ch, rng, ss, side, curIdx, staged->ts, staged->gw);
+    else phase_propose(sc, rp, states[curIdx], states[curIdx ^ 1], ch, rng, ss, side, curIdx);
     if (ss.needPropGrad) phase_gradient(sc, states[curIdx ^ 1], ss, gradStats, side);
     return phase_finish(sc, rp, chainId, sampleIdx, states, curIdx, ch, rng, film, ss, side);
 }

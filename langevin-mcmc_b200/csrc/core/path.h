@@ -191,6 +191,9 @@ struct ContribList {
     SubpathContrib c[CAP];
     LMC_HD void clear() { n = 0; }
     LMC_HD void push(const SubpathContrib &x) { if (n < CAP) c[n++] = x; }
+    // visibility of a connection segment: traced on the spot (see DeferredList in stages.h for
+    // the wavefront variant, which queues the shadow ray and resolves the contribution later)
+    LMC_HD bool occluded(const Scene &sc, const Ray &ray, float dist) { return scene_occluded(sc, ray, dist); }
 };
 
 template <class CL>
@@ -207,8 +210,9 @@ LMC_HD_NOINLINE void connect_to_camera(const Scene &sc, int lgtDepth, const Bidi
     const float distSq = length_squared(dirToCamera);
     const float dist = dm_sqrt(distSq);
     dirToCamera *= inverse(dist);
+    // The visibility test has no side effects, so it is evaluated LAST (only for connections
+    // that would contribute): same result as the reference's order (src/path.cpp:662-664).
     Ray sray; sray.org = ps.isect.position; sray.dir = dirToCamera;
-    if (scene_occluded(sc, sray, dist)) return;
     const int geom = sc.tris[lgtVertex.tid].geom;
     const BsdfParams bp = bsdf_params(sc, geom, lgtVertex.st);
     V3 bsdfContrib; float cosToCamera, bsdfPdf, bsdfRevPdf;
@@ -220,7 +224,7 @@ LMC_HD_NOINLINE void connect_to_camera(const Scene &sc, int lgtDepth, const Bidi
     const bool useAbsoluteParam = bsdf_roughness(bp) > sc.opt.roughnessThreshold;
     if (useAbsoluteParam && lgtDepth >= 1) {
         const float dsq = distance_squared(ps.isect.position, prevPosition);
-        if (dsq <= 0.0f) { contribs.clear(); return; }
+        if (dsq <= 0.0f) { if (!contribs.occluded(sc, sray, dist)) contribs.clear(); return; }
     }
     const float cosAtCamera = -dot(camDir, dirToCamera);
     const float imagePointToCameraDist = sc.cam.dist / cosAtCamera;
@@ -234,7 +238,7 @@ LMC_HD_NOINLINE void connect_to_camera(const Scene &sc, int lgtDepth, const Bidi
     V3 contrib = misWeight * bsdfContrib / (screenPixelCount * surfaceToImageFactor);
     contrib = cmul(contrib, ps.throughput);
     const float score = luminance(contrib);
-    if (score > 0.0f) {
+    if (score > 0.0f && !contribs.occluded(sc, sray, dist)) {
         SubpathContrib c;
         c.camDepth = 1; c.lightDepth = 2 + lgtDepth; c.screenPos = screenPos; c.contrib = contrib;
         c.lsScore = score; c.ssScore = score * ps.ssJacobian;
@@ -324,8 +328,7 @@ LMC_HD_NOINLINE void direct_lighting(const Scene &sc, int camDepth, const BidirP
     V3 dirToLight, lightContrib; float dist, cosAtLight, directPdf, emissionPdf;
     if (!light_sample_direct(sc, light, ps.isect.position, camVertex.dlRndParam, camVertex.dlPrim,
                              dirToLight, dist, lightContrib, cosAtLight, directPdf, emissionPdf)) return;
-    Ray sray; sray.org = ps.isect.position; sray.dir = dirToLight;
-    if (scene_occluded(sc, sray, dist)) return;
+    Ray sray; sray.org = ps.isect.position; sray.dir = dirToLight;   // visibility tested last (src/path.cpp:1003-1005)
     const int geom = sc.tris[camVertex.tid].geom;
     const BsdfParams bp = bsdf_params(sc, geom, camVertex.st);
     V3 bsdfContrib; float cosToLight, bsdfPdf, bsdfRevPdf;
@@ -342,7 +345,7 @@ LMC_HD_NOINLINE void direct_lighting(const Scene &sc, int camDepth, const BidirP
     const float misWeight = inverse(wLight + 1.0f + wCamera);
     contrib *= misWeight;
     const float score = luminance(contrib);
-    if (score > 0.0f) {
+    if (score > 0.0f && !contribs.occluded(sc, sray, dist)) {
         SubpathContrib c;
         c.camDepth = 2 + camDepth; c.lightDepth = 1; c.screenPos = screenPos; c.contrib = contrib;
         c.lsScore = score; c.ssScore = score * ps.ssJacobian;
@@ -358,8 +361,7 @@ LMC_HD_NOINLINE void connect_vertex(const Scene &sc, int camDepth, int lgtDepth,
     const float distSq = length_squared(dirToLight);
     const float dist = dm_sqrt(distSq);
     dirToLight *= inverse(dist);
-    Ray sray; sray.org = cps.isect.position; sray.dir = dirToLight;
-    if (scene_occluded(sc, sray, dist)) return;
+    Ray sray; sray.org = cps.isect.position; sray.dir = dirToLight;   // visibility tested last (src/path.cpp:1116-1118)
     const BsdfParams cbp = bsdf_params(sc, sc.tris[camVertex.tid].geom, camVertex.st);
     V3 camBsdfFactor; float cosCamera, camBsdfPdf, camBsdfRevPdf;
     bsdf_eval(false, cbp, cps.wi, cps.isect.shadingNormal, dirToLight, camBsdfFactor, cosCamera, camBsdfPdf, camBsdfRevPdf);
@@ -386,7 +388,7 @@ LMC_HD_NOINLINE void connect_vertex(const Scene &sc, int camDepth, int lgtDepth,
     contrib *= misWeight;
     const float ssJacobian = lps.ssJacobian * cps.ssJacobian;
     const float score = luminance(contrib);
-    if (score > 0.0f) {
+    if (score > 0.0f && !contribs.occluded(sc, sray, dist)) {
         SubpathContrib c;
         c.camDepth = 2 + camDepth; c.lightDepth = 2 + lgtDepth; c.screenPos = screenPos; c.contrib = contrib;
         c.lsScore = score; c.ssScore = score * ssJacobian;

@@ -1,0 +1,328 @@
+// stages.h -- resumable ("staged") forms of PerturbPathBidir and GeneratePathBidir for the
+// per-vertex wavefront: every function here runs the reference's statements between two
+// closest-hit ray queries, so the device can do ALL ray queries of an iteration in dedicated
+// traversal kernels (cuda/trace_kernels.cuh) and everything else in small shading kernels.
+//
+//   PerturbPathBidir   src/path.cpp:1953-2160   ->  perturb_stage_begin / _light / _camera
+//   GeneratePathBidir  src/path.cpp:1237-1449   ->  gen_stage_begin / _light / _camera
+//
+// The statements, their order and the order of the RNG draws are those of path.h's monolithic
+// functions (which stay: the host twin calls them, and tests/test_staged.py checks that both
+// forms produce bit-identical chains).  Two things differ in mechanism, not in result:
+//   * a closest-hit query is "return true with ts.ray/minT/maxT set"; the caller answers with a
+//     Hit (tid, t, u, v) and calls the next stage function;
+//   * visibility of connection segments is DEFERRED: ConnectToCamera / DirectLighting /
+//     ConnectVertex evaluate the whole contribution first and ask for visibility last
+//     (path.h), DeferredList answers "visible", records the contribution as PENDING and hands
+//     the shadow ray to a sink; when the ray has been traced the flag becomes VISIBLE or
+//     OCCLUDED, and deferred_compact() rebuilds the reference's contribution vector in order.
+#pragma once
+#include "path.h"
+
+namespace lmc {
+
+enum TraceStage { TS_DONE = 0, TS_P_LGT = 1, TS_P_CAM = 2, TS_G_LGT = 3, TS_G_CAM = 4 };
+enum CandFlag { CAND_VISIBLE = 0, CAND_PENDING = 1, CAND_OCCLUDED = 2, CAND_CLEAR = 4 };
+
+// SINK: void emit(const Ray &ray, float dist, int slot, int *flag)
+template <class SINK>
+struct DeferredList {
+    SubpathContrib *c;
+    int *flag;
+    int *np;            // number of entries (lives with the chain)
+    int cap;
+    SINK *sink;
+    bool pend;
+    Ray pray;
+    float pdist;
+    LMC_HD void bind(SubpathContrib *c_, int *flag_, int *np_, int cap_, SINK *sink_) {
+        c = c_; flag = flag_; np = np_; cap = cap_; sink = sink_; pend = false;
+    }
+    LMC_HD bool occluded(const Scene &, const Ray &ray, float dist) { pend = true; pray = ray; pdist = dist; return false; }
+    LMC_HD void push(const SubpathContrib &x) {
+        const int n = *np;
+        if (n < cap) {
+            c[n] = x;
+            flag[n] = pend ? CAND_PENDING : CAND_VISIBLE;
+            *np = n + 1;
+            if (pend) sink->emit(pray, pdist, n, flag + n);
+        }
+        pend = false;
+    }
+    // clear() right after a visibility query = "clear if that segment is visible"
+    LMC_HD void clear() {
+        if (pend) {
+            const int n = *np;
+            if (n < cap) {
+                flag[n] = CAND_PENDING | CAND_CLEAR;
+                *np = n + 1;
+                sink->emit(pray, pdist, n, flag + n);
+            }
+            pend = false;
+        } else {
+            *np = 0;
+        }
+    }
+};
+
+// what the shadow-ray kernel does with its answer
+LMC_HD int cand_resolve(int flag, bool occluded) { return (flag & CAND_CLEAR) | (occluded ? CAND_OCCLUDED : CAND_VISIBLE); }
+
+// Rebuild the reference's contribution vector (in push order) from resolved candidates, in place.
+LMC_HD int deferred_compact(SubpathContrib *c, const int *flag, int n) {
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const int f = flag[i];
+        if (f & CAND_OCCLUDED) continue;
+        if (f & CAND_CLEAR) { m = 0; continue; }
+        if (m != i) c[m] = c[i];
+        m++;
+    }
+    return m;
+}
+
+// Per-chain state that lives across the stages of one proposal.
+struct TraceState {
+    int stage;            // TraceStage: which function consumes the next Hit
+    int depth;            // lgtDepth / camDepth of the vertex the pending ray will find
+    int offsetId;
+    int nLightStates;
+    float ndSaved;        // NormalDist(0, discreteStdDev) carry of PerturbPathBidir
+    int ndAvail;
+    Ray ray;
+    float minT, maxT;
+    BidirPathState cps, lps;
+    int nCand;            // small steps: at most one contribution (+ a conditional clear)
+    int candFlag[2];
+    SubpathContrib cand[2];
+};
+
+// Large-step workspace: light subpath states and the contribution candidates.
+template <int MAXD, int MAXC>
+struct GenWork {
+    BidirPathState ls[MAXD];
+    int n;
+    int flag[MAXC];
+    SubpathContrib c[MAXC];
+};
+
+LMC_HD void trace_state_init(TraceState &ts) {
+    memset(&ts, 0, sizeof(ts));
+}
+
+// ---- PerturbPathBidir --------------------------------------------------------------------
+template <int MAXD>
+LMC_HD bool perturb_camera_begin(const Scene &sc, const float *offset, Path<MAXD> &path, TraceState &ts) {
+    perturb(path.screenPos.x, offset, ts.offsetId);
+    perturb(path.screenPos.y, offset, ts.offsetId);
+    emit_from_camera(sc, path.screenPos, ts.ray, ts.minT, ts.maxT, ts.cps);
+    if (path.nCam <= 0) { ts.stage = TS_DONE; return false; }
+    ts.stage = TS_P_CAM; ts.depth = 0;
+    return true;
+}
+
+template <int MAXD>
+LMC_HD bool perturb_stage_begin(const Scene &sc, const float *offset, Path<MAXD> &path, TraceState &ts, Rng &rng) {
+    NormalDist nd = normal_make(0.0f, sc.opt.discreteStdDev);
+    ts.offsetId = 0;
+    path.time = modulo1(path.time + normal_draw(nd, rng));
+    ts.ndSaved = nd.saved; ts.ndAvail = nd.savedAvailable ? 1 : 0;
+    if (path.lgtDepth > 1) {
+        const float lightPickProb = pick_light_prob(sc, path.lgtLight);
+        perturb(path.lgtRndPos.x, offset, ts.offsetId);
+        perturb(path.lgtRndPos.y, offset, ts.offsetId);
+        perturb(path.lgtRndDir.x, offset, ts.offsetId);
+        perturb(path.lgtRndDir.y, offset, ts.offsetId);
+        emit_from_light(sc, lightPickProb, path, ts.ray, ts.lps);
+        ts.minT = LMC_ISECT_EPS; ts.maxT = dm_inf();
+        if (path.nLgt > 0) { ts.stage = TS_P_LGT; ts.depth = 0; return true; }
+    }
+    return perturb_camera_begin(sc, offset, path, ts);
+}
+
+template <int MAXD, class CL>
+LMC_HD bool perturb_stage_light(const Scene &sc, const float *offset, Path<MAXD> &path, TraceState &ts, CL &contribs,
+                                Rng &rng, const Hit &hit) {
+    const int lgtDepth = ts.depth;
+    SurfaceVertex &sv = path.lgt[lgtDepth];
+    BidirPathState &lps = ts.lps;
+    if (hit.tid < 0) { ts.stage = TS_DONE; return false; }
+    sv.tid = hit.tid;
+    fill_isect(sc, ts.ray, hit, lps.isect, sv.st);
+    lps.wi = -ts.ray.dir;
+    NormalDist nd = normal_make(0.0f, sc.opt.discreteStdDev);
+    nd.saved = ts.ndSaved; nd.savedAvailable = ts.ndAvail != 0;
+    sv.bsdfDiscrete = modulo1(sv.bsdfDiscrete + normal_draw(nd, rng));
+    ts.ndSaved = nd.saved; ts.ndAvail = nd.savedAvailable ? 1 : 0;
+    convert_mis(sc, lgtDepth, path.lgtLight, ts.ray, lps);
+    if (lgtDepth == path.nLgt - 1 && path.camDepth == 1) {
+        connect_to_camera(sc, lgtDepth, lps, sv, ts.ray.org, contribs);
+        ts.stage = TS_DONE; return false;
+    }
+    if (lgtDepth == path.nLgt - 1) return perturb_camera_begin(sc, offset, path, ts);
+    perturb(sv.bsdfRndParam.x, offset, ts.offsetId);
+    perturb(sv.bsdfRndParam.y, offset, ts.offsetId);
+    V3 bsdfContrib;
+    if (!bsdf_sampling<true, true>(sc, lps, sv, lps, ts.ray.dir, bsdfContrib)) { ts.stage = TS_DONE; return false; }
+    lps.throughput *= sv.rrWeight;
+    ts.ray.org = lps.isect.position;
+    ts.depth = lgtDepth + 1;
+    return true;
+}
+
+template <int MAXD, class CL>
+LMC_HD bool perturb_stage_camera(const Scene &sc, const float *offset, Path<MAXD> &path, TraceState &ts, CL &contribs,
+                                 Rng &rng, const Hit &hit) {
+    const int camDepth = ts.depth;
+    SurfaceVertex &sv = path.cam[camDepth];
+    BidirPathState &cps = ts.cps;
+    const bool hitSurface = hit.tid >= 0;
+    if (hitSurface) { sv.tid = hit.tid; fill_isect(sc, ts.ray, hit, cps.isect, sv.st); }
+    cps.wi = -ts.ray.dir;
+    if (hitSurface) convert_mis(sc, camDepth, -1, ts.ray, cps);
+    if (camDepth == path.nCam - 1 && path.lgtDepth == 0) {
+        const int light = get_hit_light(sc, hitSurface, sv.tid);
+        if (light >= 0) handle_hit_light(sc, camDepth, light, hitSurface, ts.ray, path.screenPos, cps, path, contribs);
+        ts.stage = TS_DONE; return false;
+    }
+    if (!hitSurface) { ts.stage = TS_DONE; return false; }
+    NormalDist nd = normal_make(0.0f, sc.opt.discreteStdDev);
+    nd.saved = ts.ndSaved; nd.savedAvailable = ts.ndAvail != 0;
+    sv.bsdfDiscrete = modulo1(sv.bsdfDiscrete + normal_draw(nd, rng));
+    ts.ndSaved = nd.saved; ts.ndAvail = nd.savedAvailable ? 1 : 0;
+    if (camDepth == 1) {
+        path.lensVertexPos = cps.isect.position;
+        const float distSq = distance_squared(cps.isect.position, ts.ray.org);
+        if (distSq <= 0.0f) { contribs.clear(); ts.stage = TS_DONE; return false; }
+    }
+    if (camDepth == path.nCam - 1) {
+        if (path.lgtDepth == 1) {
+            const float directLightPickProb = pick_light_prob(sc, sv.dlLight);
+            perturb(sv.dlRndParam.x, offset, ts.offsetId);
+            perturb(sv.dlRndParam.y, offset, ts.offsetId);
+            direct_lighting(sc, camDepth, cps, path.screenPos, directLightPickProb, sv, contribs);
+        } else {
+            connect_vertex(sc, camDepth, path.nLgt - 1, ts.lps, path.lgt[path.nLgt - 1], cps, sv, path.screenPos, contribs);
+        }
+        ts.stage = TS_DONE; return false;
+    }
+    perturb(sv.bsdfRndParam.x, offset, ts.offsetId);
+    perturb(sv.bsdfRndParam.y, offset, ts.offsetId);
+    V3 bsdfContrib;
+    if (!bsdf_sampling<false, true>(sc, cps, sv, cps, ts.ray.dir, bsdfContrib)) { ts.stage = TS_DONE; return false; }
+    cps.throughput *= sv.rrWeight;
+    ts.ray.org = cps.isect.position;
+    ts.minT = LMC_ISECT_EPS; ts.maxT = dm_inf();
+    ts.depth = camDepth + 1;
+    return true;
+}
+
+// ---- GeneratePathBidir(scene, (-1,-1), minDepth, maxDepth, ...) ---------------------------------
+template <int MAXD>
+LMC_HD bool gen_camera_begin(const Scene &sc, Path<MAXD> &path, TraceState &ts, Rng &rng) {
+    path.screenPos.x = rng_uniform(rng); path.screenPos.y = rng_uniform(rng);
+    emit_from_camera(sc, path.screenPos, ts.ray, ts.minT, ts.maxT, ts.cps);
+    ts.stage = TS_G_CAM; ts.depth = 0;
+    return true;
+}
+
+template <int MAXD, int MAXC>
+LMC_HD bool gen_stage_begin(const Scene &sc, Path<MAXD> &path, TraceState &ts, GenWork<MAXD, MAXC> &gw, Rng &rng) {
+    path.time = rng_uniform(rng);
+    ts.nLightStates = 1;
+    float lightPickProb = 1.0f;
+    path.lgtRndPos.x = rng_uniform(rng); path.lgtRndPos.y = rng_uniform(rng);
+    path.lgtRndDir.x = rng_uniform(rng); path.lgtRndDir.y = rng_uniform(rng);
+    path.lgtLight = pick_light(sc, rng_uniform(rng), lightPickProb);
+    path.lgtPrim = light_sample_discrete(sc, path.lgtLight, rng_uniform(rng));
+    emit_from_light(sc, lightPickProb, path, ts.ray, gw.ls[0]);
+    ts.minT = LMC_ISECT_EPS; ts.maxT = dm_inf();
+    ts.stage = TS_G_LGT; ts.depth = 0;
+    return true;
+}
+
+template <int MAXD, int MAXC, class CL>
+LMC_HD bool gen_stage_light(const Scene &sc, int minDepth, int maxDepth, Path<MAXD> &path, TraceState &ts,
+                            GenWork<MAXD, MAXC> &gw, CL &contribs, Rng &rng, const Hit &hit) {
+    const int lgtDepth = ts.depth;
+    path.lgt[path.nLgt] = surface_vertex_zero();
+    SurfaceVertex &sv = path.lgt[path.nLgt];
+    path.nLgt++;
+    BidirPathState &cur = gw.ls[lgtDepth];
+    if (hit.tid < 0) { ts.nLightStates--; path.nLgt--; return gen_camera_begin(sc, path, ts, rng); }
+    sv.tid = hit.tid;
+    fill_isect(sc, ts.ray, hit, cur.isect, sv.st);
+    sv.bsdfDiscrete = rng_uniform(rng);
+    cur.wi = -ts.ray.dir;
+    convert_mis(sc, lgtDepth, path.lgtLight, ts.ray, cur);
+    if (lgtDepth + 2 >= minDepth) connect_to_camera(sc, lgtDepth, cur, sv, ts.ray.org, contribs);
+    if (maxDepth != -1 && lgtDepth + 2 >= maxDepth) return gen_camera_begin(sc, path, ts, rng);
+    ts.nLightStates++;
+    sv.bsdfRndParam.x = rng_uniform(rng); sv.bsdfRndParam.y = rng_uniform(rng);
+    V3 bsdfContrib;
+    gw.ls[lgtDepth + 1].ssJacobian = 0.0f;
+    if (!bsdf_sampling<true, false>(sc, cur, sv, gw.ls[lgtDepth + 1], ts.ray.dir, bsdfContrib)) {
+        ts.nLightStates--; return gen_camera_begin(sc, path, ts, rng);
+    }
+    if (!russian_roulette(lgtDepth, bsdfContrib, sv.rrWeight, gw.ls[lgtDepth + 1].throughput, rng)) {
+        ts.nLightStates--; return gen_camera_begin(sc, path, ts, rng);
+    }
+    ts.ray.org = cur.isect.position;
+    ts.depth = lgtDepth + 1;
+    return true;
+}
+
+template <int MAXD, int MAXC, class CL>
+LMC_HD bool gen_stage_camera(const Scene &sc, int minDepth, int maxDepth, Path<MAXD> &path, TraceState &ts,
+                             GenWork<MAXD, MAXC> &gw, CL &contribs, Rng &rng, const Hit &hit) {
+    const int camDepth = ts.depth;
+    BidirPathState &cps = ts.cps;
+    path.cam[path.nCam] = surface_vertex_zero();
+    SurfaceVertex &sv = path.cam[path.nCam];
+    path.nCam++;
+    const bool hitSurface = hit.tid >= 0;
+    if (hitSurface) { sv.tid = hit.tid; fill_isect(sc, ts.ray, hit, cps.isect, sv.st); }
+    cps.wi = -ts.ray.dir;
+    if (hitSurface) convert_mis(sc, camDepth, -1, ts.ray, cps);
+    if (camDepth + 1 >= minDepth) {
+        const int light = get_hit_light(sc, hitSurface, sv.tid);
+        if (light >= 0) {
+            handle_hit_light(sc, camDepth, light, hitSurface, ts.ray, path.screenPos, cps, path, contribs);
+            ts.stage = TS_DONE; return false;
+        }
+    }
+    if (!hitSurface || (maxDepth != -1 && camDepth + 1 >= maxDepth)) { ts.stage = TS_DONE; return false; }
+    if (camDepth == 1) {
+        path.lensVertexPos = cps.isect.position;
+        const float distSq = distance_squared(cps.isect.position, ts.ray.org);
+        if (distSq <= 0.0f) { contribs.clear(); ts.stage = TS_DONE; return false; }
+    }
+    sv.bsdfDiscrete = rng_uniform(rng);
+    if (camDepth + 2 >= minDepth) {
+        float directLightPickProb = 1.0f;
+        sv.dlLight = pick_light(sc, rng_uniform(rng), directLightPickProb);
+        sv.dlRndParam.x = rng_uniform(rng); sv.dlRndParam.y = rng_uniform(rng);
+        sv.dlPrim = light_sample_discrete(sc, sv.dlLight, rng_uniform(rng));
+        direct_lighting(sc, camDepth, cps, path.screenPos, directLightPickProb, sv, contribs);
+    }
+    int maxLgtDepth = ts.nLightStates - 1;
+    if (maxDepth != -1) {
+        const int m = maxDepth - camDepth - 3;
+        if (m < maxLgtDepth) maxLgtDepth = m;
+    }
+    for (int lgtDepth = 0; lgtDepth <= maxLgtDepth; lgtDepth++) {
+        if (camDepth + lgtDepth + 3 >= minDepth) {
+            connect_vertex(sc, camDepth, lgtDepth, gw.ls[lgtDepth], path.lgt[lgtDepth], cps, sv, path.screenPos, contribs);
+        }
+    }
+    sv.bsdfRndParam.x = rng_uniform(rng); sv.bsdfRndParam.y = rng_uniform(rng);
+    V3 bsdfContrib;
+    if (!bsdf_sampling<false, false>(sc, cps, sv, cps, ts.ray.dir, bsdfContrib)) { ts.stage = TS_DONE; return false; }
+    if (!russian_roulette(camDepth, bsdfContrib, sv.rrWeight, cps.throughput, rng)) { ts.stage = TS_DONE; return false; }
+    ts.ray.org = cps.isect.position;
+    ts.minT = LMC_ISECT_EPS; ts.maxT = dm_inf();
+    ts.depth = camDepth + 1;
+    return true;
+}
+
+}  // namespace lmc

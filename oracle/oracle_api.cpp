@@ -60,6 +60,7 @@ struct HostFilm {
 };
 
 bool g_useRef = false;
+bool g_staged = false;     // run the proposal phase through the staged path functions (core/stages.h)
 template <int MAXD>
 void run_chains_t(const Scene &sc, int numChains, int chainBase, int totalChains, long long numSteps,
                   long long numSamplesThisChain, float normalization, const float *initLs, float *film,
@@ -77,6 +78,8 @@ void run_chains_t(const Scene &sc, int numChains, int chainBase, int totalChains
         HostFilm hf; hf.p = films[w].data();
         ChainState<MAXD> *cs = new ChainState<MAXD>();
         H2mcSide *side = new H2mcSide();
+        StagedWork<MAXD> *staged = g_staged ? new StagedWork<MAXD>() : nullptr;
+        if (staged) memset(staged, 0, sizeof(*staged));
         uint32_t tab[64];
         for (;;) {
             const int i = next.fetch_add(1);
@@ -85,12 +88,13 @@ void run_chains_t(const Scene &sc, int numChains, int chainBase, int totalChains
             chain_state_init(*cs, initLs ? initLs[gid] : 0.0f);
             memset(side, 0, sizeof(*side));
             chain_run(sc, rp, gid, *cs, numSteps, tab, 1, hf, trace ? trace + (size_t)i * numSteps : nullptr,
-                      aTrace ? aTrace + (size_t)i * numSteps : nullptr, 1, side);
+                      aTrace ? aTrace + (size_t)i * numSteps : nullptr, 1, side, staged);
             for (int k = 0; k < 4; k++) { tstats[w][k] += cs->nPropose[k]; tstats[w][4 + k] += cs->nAccept[k]; }
             tstats[w][8] += cs->gradStats[0]; tstats[w][9] += cs->gradStats[1];
         }
         delete cs;
         delete side;
+        delete staged;
     };
     std::vector<std::thread> pool;
     for (int w = 0; w < threads; w++) pool.emplace_back(work, w);
@@ -203,6 +207,9 @@ int lmco_use_reference_gradient(const char *libPath, int enable) {
     for (int c = 1; c <= 9; c++) for (int l = 0; l <= 8; l++) if (g_refDerv[c][l]) n++;
     return n;
 }
+
+// 1: lmco_run_chains runs every proposal through the staged (wavefront) path functions
+int lmco_use_staged(int enable) { g_staged = enable != 0; return 0; }
 
 // plain bidirectional path tracing estimate of the image (sanity reference for the MLT film)
 int lmco_bdpt(void *h, int spp, int minDepth, float *film, int threads) {

@@ -95,6 +95,10 @@ class Oracle:
             return -1
         return self.L.lmco_use_reference_gradient(path.encode(), 1 if enable else 0)
 
+    def use_staged(self, enable):
+        """Run the proposal phase through the staged (per-vertex wavefront) path functions."""
+        return self.L.lmco_use_staged(1 if enable else 0)
+
     def sample_paths(self, h, seed, num_large_steps, perturb=True, max_len=8, max_records=20000):
         rec = self.REC_HEAD + 25 + self.VSTRIDE
         out = np.zeros((max_records, rec), np.float32)
