@@ -13,6 +13,7 @@ struct ChainState {
     MarkovState<MAXD> st[2];
     ChainVars<MAXD> ch;
     StepScratch<MAXD> ss;
+    PropCand pc;                 // small step: the proposal's candidate contribution (wavefront, stages.h)
     int curIdx;
     unsigned long long rngState;
     unsigned int rngEpoch;
@@ -39,6 +40,7 @@ LMC_HD void chain_state_init(ChainState<MAXD> &cs, float initLsScore) {
     chain_vars_init(cs.ch);
     cs.ss.kind = STEP_LARGE; cs.ss.needCurGrad = 0; cs.ss.needPropGrad = 0; cs.ss.hasContrib = 0; cs.ss.a = 0.0f;
     for (int i = 0; i < Limits<MAXD>::DIM; i++) { cs.ss.offset[i] = 0.0f; cs.ss.grad[i] = 0.0f; }
+    cs.pc.n = 0;
     cs.curIdx = 0; cs.rngState = 0ULL; cs.rngEpoch = 0u; cs.seeded = 0u; cs.sampleIdx = 0;
     for (int i = 0; i < 4; i++) { cs.nAccept[i] = 0; cs.nPropose[i] = 0; }
     cs.gradStats[0] = 0; cs.gradStats[1] = 0;

@@ -488,13 +488,15 @@ LMC_HD void propose_post_large(const RunParams &rp, const MarkovState<MAXD> &cur
     ss.a = a;
 }
 
-// small steps before PerturbPathBidir: the proposal offset in ss.offset, prop.path = cur.path
-template <int MAXD>
+// small steps before PerturbPathBidir: the proposal offset in ss.offset, prop.path = cur.path.
+// COPY_PATH = false leaves the path alone: the device wavefront carries the PathHead in its payload and
+// reads each vertex from cur.path / writes it to prop.path as PerturbPathBidir reaches it.
+template <int MAXD, bool COPY_PATH = true>
 LMC_HD void propose_pre_small(const Scene &sc, MarkovState<MAXD> &cur, MarkovState<MAXD> &prop, ChainVars<MAXD> &ch,
                               Rng &rng, StepScratch<MAXD> &ss, H2mcSide *side, int curSlot) {
     const int dim = path_dimension(cur.path);
     if (ss.kind == STEP_ISO) {
-        path_copy(prop.path, cur.path);
+        if (COPY_PATH) path_copy(prop.path, cur.path);
         NormalDist nd = normal_make(0.0f, sc.opt.perturbStdDev);
         ch.lastMutationType = MUT_SMALL;
         for (int i = 0; i < dim; i++) ss.offset[i] = normal_draw(nd, rng);
@@ -505,7 +507,7 @@ LMC_HD void propose_pre_small(const Scene &sc, MarkovState<MAXD> &cur, MarkovSta
         if (!cur.gaussianInitialized) h2mc_init_gaussian(sc, cur, curSlot, h2mc_grad_mode(sc, cur), ss.grad, side);
         if (side->dense[curSlot]) generate_sample_dense(cur.gaussian, side->covL[curSlot], ss.offset, rng);
         else generate_sample(cur.gaussian, ss.offset, rng);
-        path_copy(prop.path, cur.path);
+        if (COPY_PATH) path_copy(prop.path, cur.path);
         return;
     }
     // STEP_MALA
@@ -515,7 +517,7 @@ LMC_HD void propose_pre_small(const Scene &sc, MarkovState<MAXD> &cur, MarkovSta
         cur.gaussianInitialized = 1;
     }
     generate_sample(cur.gaussian, ss.offset, rng);
-    path_copy(prop.path, cur.path);
+    if (COPY_PATH) path_copy(prop.path, cur.path);
 }
 // small steps after PerturbPathBidir (contribs holds 0 or 1 entries)
 template <int MAXD, class CL>
@@ -572,43 +574,44 @@ struct ImmediateShadowSink {
     LMC_HD void emit(const Ray &ray, float dist, int, int *flag) { *flag = cand_resolve(*flag, scene_occluded(*sc, ray, dist)); }
 };
 template <int MAXD>
+struct StagedWork { TraceState ts; PropCand pc; GenWork<MAXD, Limits<MAXD>::MAXC> gw; };
+
+template <int MAXD>
 LMC_HD void phase_propose_staged(const Scene &sc, const RunParams &rp, MarkovState<MAXD> &cur, MarkovState<MAXD> &prop,
                                  ChainVars<MAXD> &ch, Rng &rng, StepScratch<MAXD> &ss, H2mcSide *side, int curSlot,
-                                 TraceState &ts, GenWork<MAXD, Limits<MAXD>::MAXC> &gw) {
+                                 StagedWork<MAXD> &w) {
     ImmediateShadowSink sink; sink.sc = &sc;
     DeferredList<ImmediateShadowSink> dl;
+    TraceState &ts = w.ts;
+    Path<MAXD> &path = prop.path;
     if (ss.kind == STEP_LARGE) {
         propose_pre_large(prop, ch);
-        gw.n = 0;
-        dl.bind(gw.c, gw.flag, &gw.n, Limits<MAXD>::MAXC, &sink);
+        w.gw.n = 0;
+        dl.bind(w.gw.c, w.gw.flag, &w.gw.n, Limits<MAXD>::MAXC, &sink);
         const int minDepth = sc.opt.minDepth > 3 ? sc.opt.minDepth : 3;
-        bool more = gen_stage_begin(sc, prop.path, ts, gw, rng);
+        bool more = gen_stage_begin(sc, path, ts, w.gw.ls, rng);
         while (more) {
             const Hit h = bvh_traverse<false>(sc, ts.ray, ts.minT, ts.maxT);
-            if (ts.stage == TS_G_LGT) more = gen_stage_light(sc, minDepth, sc.opt.maxDepth, prop.path, ts, gw, dl, rng, h);
-            else more = gen_stage_camera(sc, minDepth, sc.opt.maxDepth, prop.path, ts, gw, dl, rng, h);
+            if (ts.stage == TS_G_LGT) more = gen_stage_light(sc, minDepth, sc.opt.maxDepth, path, path.lgt[path.nLgt], ts, w.gw.ls, dl, rng, h);
+            else more = gen_stage_camera(sc, minDepth, sc.opt.maxDepth, path, path.cam[path.nCam], path.lgt, ts, w.gw.ls, dl, rng, h);
         }
-        gw.n = deferred_compact(gw.c, gw.flag, gw.n);
-        propose_post_large(rp, cur, prop, ch, rng, ss, gw);
+        w.gw.n = deferred_compact(w.gw.c, w.gw.flag, w.gw.n);
+        propose_post_large(rp, cur, prop, ch, rng, ss, w.gw);
         return;
     }
     propose_pre_small(sc, cur, prop, ch, rng, ss, side, curSlot);
-    ts.nCand = 0;
-    dl.bind(ts.cand, ts.candFlag, &ts.nCand, 2, &sink);
-    bool more = perturb_stage_begin(sc, ss.offset, prop.path, ts, rng);
+    w.pc.n = 0;
+    dl.bind(w.pc.c, w.pc.flag, &w.pc.n, 2, &sink);
+    const float *offset = ss.offset;
+    bool more = perturb_stage_begin(sc, offset, path, ts, rng);
     while (more) {
         const Hit h = bvh_traverse<false>(sc, ts.ray, ts.minT, ts.maxT);
-        if (ts.stage == TS_P_LGT) more = perturb_stage_light(sc, ss.offset, prop.path, ts, dl, rng, h);
-        else more = perturb_stage_camera(sc, ss.offset, prop.path, ts, dl, rng, h);
+        if (ts.stage == TS_P_LGT) more = perturb_stage_light(sc, offset, path, path.lgt[ts.depth], ts, dl, rng, h);
+        else more = perturb_stage_camera(sc, offset, path, path.cam[ts.depth], path.lgt, ts, dl, rng, h);
     }
-    ContribList<2> contribs;
-    contribs.n = deferred_compact(ts.cand, ts.candFlag, ts.nCand);
-    for (int i = 0; i < contribs.n; i++) contribs.c[i] = ts.cand[i];
-    propose_post_small(sc, rp, cur, prop, ss, contribs);
+    w.pc.n = deferred_compact(w.pc.c, w.pc.flag, w.pc.n);
+    propose_post_small(sc, rp, cur, prop, ss, w.pc);
 }
-
-template <int MAXD>
-struct StagedWork { TraceState ts; GenWork<MAXD, Limits<MAXD>::MAXC> gw; };
 
 struct StepInfo {          // what one iteration did (parity traces / stats)
     int mutationType;
@@ -703,7 +706,7 @@ LMC_HD StepInfo chain_step(const Scene &sc, const RunParams &rp, int chainId, lo
                            unsigned int *gradStats, StepScratch<MAXD> &ss, H2mcSide *side, StagedWork<MAXD> *staged = nullptr) {
     phase_begin(sc, rp, sampleIdx, states[curIdx], ch, rng, ss);
     if (ss.needCurGrad) phase_gradient(sc, states[curIdx], ss, gradStats, side);
-    if (staged) phase_propose_staged(sc, rp, states[curIdx], states[curIdx ^ 1], ch, rng, ss, side, curIdx, staged->ts, staged->gw);
+    if (staged) phase_propose_staged(sc, rp, states[curIdx], states[curIdx ^ 1], ch, rng, ss, side, curIdx, *staged);
     else phase_propose(sc, rp, states[curIdx], states[curIdx ^ 1], ch, rng, ss, side, curIdx);
     if (ss.needPropGrad) phase_gradient(sc, states[curIdx ^ 1], ss, gradStats, side);
     return phase_finish(sc, rp, chainId, sampleIdx, states, curIdx, ch, rng, film, ss, side);

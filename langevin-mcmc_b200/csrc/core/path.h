@@ -33,7 +33,7 @@ struct SubpathContrib {          // src/path.h:12-21
     float lsScore, ssScore;
 };
 
-struct SurfaceVertex {           // src/path.h:31-39
+struct alignas(16) SurfaceVertex {   // src/path.h:31-39; 48 B, moved as 3 x 16 B
     int tid;                     // shapeInst (triangle id in BVH order; -1 = none)
     V2 st;
     V2 bsdfRndParam;
@@ -44,8 +44,8 @@ struct SurfaceVertex {           // src/path.h:31-39
     float rrWeight;
 };
 
-template <int MAXD>
-struct Path {                    // src/path.h:47-62
+// Everything of a Path except the per-vertex arrays: 80 B, travels with the wavefront payload.
+struct alignas(16) PathHead {
     float time;
     V2 screenPos;                // camVertex
     V2 lgtRndPos, lgtRndDir;     // lgtVertex
@@ -54,12 +54,15 @@ struct Path {                    // src/path.h:47-62
     V3 lensVertexPos;
     int isSubpath, camDepth, lgtDepth;
     int nCam, nLgt;              // vector sizes
+    int headPad;
+};
+template <int MAXD>
+struct Path : PathHead {         // src/path.h:47-62
     SurfaceVertex cam[MAXD];
     SurfaceVertex lgt[MAXD];
 };
 
-template <int MAXD>
-LMC_HD void path_clear(Path<MAXD> &p) {
+LMC_HD void path_clear(PathHead &p) {
     p.nCam = 0; p.nLgt = 0; p.envLight = -1; p.envPrim = -1; p.isSubpath = 0;
 }
 template <int MAXD>
@@ -82,8 +85,7 @@ LMC_HD int primary_param_size(int camDepth, int lightDepth) {
     const int l = camDepth + lightDepth - 1;
     return (l > 2 ? l : 2) * 2 + 1;
 }
-template <int MAXD>
-LMC_HD int path_dimension(const Path<MAXD> &p) { return primary_param_size(p.camDepth, p.lgtDepth) - 1; }
+LMC_HD int path_dimension(const PathHead &p) { return primary_param_size(p.camDepth, p.lgtDepth) - 1; }
 
 template <int MAXD>
 LMC_HD void to_subpath(int camDepth, int lgtDepth, Path<MAXD> &path) {
@@ -160,8 +162,7 @@ LMC_HD void emit_from_camera(const Scene &sc, V2 screenPos, Ray &ray, float &min
     ps.ssJacobian = 1.0f;
 }
 
-template <int MAXD>
-LMC_HD void emit_from_light(const Scene &sc, float lightPickProb, Path<MAXD> &path, Ray &ray, BidirPathState &ps) {
+LMC_HD void emit_from_light(const Scene &sc, float lightPickProb, PathHead &path, Ray &ray, BidirPathState &ps) {
     float cosLight, emissionPdf, directPdf;
     light_emit(sc, path.lgtLight, path.lgtRndPos, path.lgtRndDir, path.lgtPrim, ray, ps.throughput,
                cosLight, emissionPdf, directPdf);
@@ -293,9 +294,9 @@ LMC_HD_NOINLINE bool bsdf_sampling(const Scene &sc, const BidirPathState &ps, Su
     return true;
 }
 
-template <int MAXD, class CL>
+template <class CL>
 LMC_HD_NOINLINE void handle_hit_light(const Scene &sc, int camDepth, int light, bool hitSurface, const Ray &ray,
-                             V2 screenPos, const BidirPathState &ps, Path<MAXD> &path, CL &contribs) {
+                             V2 screenPos, const BidirPathState &ps, PathHead &path, CL &contribs) {
     int lPrimID = -1;
     V3 emission; float directPdf, emissionPdf;
     light_emission(sc, light, ray.dir, ps.isect.shadingNormal, lPrimID, emission, directPdf, emissionPdf);
@@ -507,7 +508,8 @@ LMC_HD_NOINLINE void generate_path_bidir(const Scene &sc, int minDepth, int maxD
     }
 }
 
-LMC_HD void perturb(float &value, const float *offset, int &offsetId) {
+template <class OFF>
+LMC_HD void perturb(float &value, const OFF &offset, int &offsetId) {
     value = modulo1(value + offset[offsetId++]);
 }
 

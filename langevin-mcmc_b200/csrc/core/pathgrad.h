@@ -907,7 +907,9 @@ LMC_HD_NOINLINE float path_loglum(int camDepth, int lightDepth, const float *sce
 }
 
 // Gradient w.r.t. primary[1..D] (time excluded: Static mode), NCHUNK directions per sweep.
+#ifndef LMC_GRAD_CHUNK
 #define LMC_GRAD_CHUNK 4
+#endif
 #define LMC_GRAD_MAXDIM 24
 LMC_HD_NOINLINE float path_loglum_grad(int camDepth, int lightDepth, const float *sceneBuf, const float *primary,
                                        const float *vertParams, float *grad) {

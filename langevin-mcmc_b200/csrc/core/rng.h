@@ -26,7 +26,32 @@ struct Rng {
     uint32_t *tab;    // 64 entries, element i at tab[i * stride]
     int stride;
     uint32_t epoch;   // number of advance_table() calls so far (persisted with the chain)
+    // Lazy mode: while the table has never advanced (epoch == 0; an advance happens once per 2^32
+    // draws) entry i is a pure function of the seed, xsh_rs(s_{i+2}) ^ xdiff, and is computed on
+    // demand with the LCG jump-ahead constants below instead of materialising 64 entries.
+    int lazy;
+    uint64_t s0;      // bump(seed + increment): the state selfinit() starts from
+    uint32_t xdiff;
 };
+
+// (A^k, C_k), k = 0..66: s_k = A^k * s_0 + C_k
+#define LMC_PCG_JUMP_N 67
+static const unsigned long long LMC_PCG_JUMP_H[2 * LMC_PCG_JUMP_N] = {
+#include "pcg_jump.inc"
+};
+#if defined(__CUDACC__)
+static __device__ const unsigned long long LMC_PCG_JUMP_D[2 * LMC_PCG_JUMP_N] = {
+#include "pcg_jump.inc"
+};
+#endif
+LMC_HD uint64_t pcg_jump(uint64_t s0, uint32_t k) {
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 ac = __ldg(reinterpret_cast<const ulonglong2 *>(LMC_PCG_JUMP_D) + k);
+    return ac.x * s0 + ac.y;
+#else
+    return LMC_PCG_JUMP_H[2 * k] * s0 + LMC_PCG_JUMP_H[2 * k + 1];
+#endif
+}
 
 LMC_HD uint32_t pcg_xsh_rs(uint64_t s) {
     const uint32_t rshift = (uint32_t)(s >> 61) & 7u;
@@ -71,7 +96,14 @@ LMC_HD bool pcg_external_step(uint32_t &randval, uint32_t i) {
     return result == 0u;
 }
 
+LMC_HD void rng_materialize(Rng &r) {      // leave lazy mode: write the 64 seed-defined entries
+    if (!r.lazy) return;
+    for (uint32_t i = 0; i < 64u; ++i) r.tab[i * r.stride] = pcg_xsh_rs(pcg_jump(r.s0, i + 2u)) ^ r.xdiff;
+    r.lazy = 0;
+}
+
 LMC_HD void rng_advance_table(Rng &r) {
+    rng_materialize(r);
     bool carry = false;
     for (uint32_t i = 0; i < 64u; ++i) {
         uint32_t v = r.tab[i * r.stride];
@@ -96,6 +128,27 @@ LMC_HD void rng_seed(Rng &r, uint64_t seed) {
         r.tab[i * r.stride] = pcg_base_next(r.state) ^ xdiff;
     }
     r.epoch = 0u;
+    r.lazy = 0;
+}
+
+// Lazy forms of RNG(seed) and of the restore below: nothing is written to the table unless it
+// has to advance (r.tab must still point at 64 words of scratch for that case).
+LMC_HD void rng_lazy_base(Rng &r, uint64_t seed) {
+    r.s0 = (seed + LMC_PCG_INC) * LMC_PCG_MULT + LMC_PCG_INC;
+    r.xdiff = pcg_xsh_rs(r.s0) - pcg_xsh_rs(pcg_jump(r.s0, 1u));
+    r.lazy = 1;
+}
+LMC_HD void rng_seed_lazy(Rng &r, uint64_t seed) {
+    rng_lazy_base(r, seed);
+    r.state = pcg_jump(r.s0, 66u);
+    r.epoch = 0u;
+}
+LMC_HD void rng_advance_table(Rng &r);
+LMC_HD void rng_restore_lazy(Rng &r, uint64_t seed, uint64_t state, uint32_t epoch) {
+    rng_lazy_base(r, seed);
+    r.epoch = 0u;
+    for (uint32_t e = 0; e < epoch; ++e) rng_advance_table(r);
+    r.state = state;
 }
 
 // Rebuild the table for a chain that was seeded with `seed` and has advanced its table
@@ -112,7 +165,8 @@ LMC_HD uint32_t rng_next(Rng &r) {
     if ((s & 0xFFFFFFFFULL) == 0ULL) {
         rng_advance_table(r);
     }
-    const uint32_t rhs = r.tab[(uint32_t)(s & 63ULL) * r.stride];
+    const uint32_t idx = (uint32_t)(s & 63ULL);
+    const uint32_t rhs = r.lazy ? (pcg_xsh_rs(pcg_jump(r.s0, idx + 2u)) ^ r.xdiff) : r.tab[idx * r.stride];
     const uint32_t lhs = pcg_base_next(r.state);
     return lhs ^ rhs;
 }

@@ -81,20 +81,31 @@ LMC_HD int deferred_compact(SubpathContrib *c, const int *flag, int n) {
     return m;
 }
 
-// Per-chain state that lives across the stages of one proposal.
-struct TraceState {
+// State of a proposal between two stages.  The device moves it from ray queue to ray queue as
+// the wavefront payload (together with the PathHead), 16 bytes at a time: keep it a multiple of 16 B
+// and keep the ray at words 6..13 (cuda/chain_kernels.cuh k_trace reads it from there).
+struct alignas(16) TraceState {
     int stage;            // TraceStage: which function consumes the next Hit
     int depth;            // lgtDepth / camDepth of the vertex the pending ray will find
     int offsetId;
     int nLightStates;
     float ndSaved;        // NormalDist(0, discreteStdDev) carry of PerturbPathBidir
     int ndAvail;
-    Ray ray;
     float minT, maxT;
+    Ray ray;
+    uint32_t rngLo, rngHi;   // the chain's RNG state rides along (device); unused by the host model
+    uint32_t rngEpoch;
+    int curIdx;              // which MarkovState slot is the current state (device)
+    int tsPad[2];
     BidirPathState cps, lps;
-    int nCand;            // small steps: at most one contribution (+ a conditional clear)
-    int candFlag[2];
-    SubpathContrib cand[2];
+    int tsPad2[2];
+};
+
+// Candidate contribution(s) of a small step: at most one (+ a conditional clear)
+struct PropCand {
+    int n;
+    int flag[2];
+    SubpathContrib c[2];
 };
 
 // Large-step workspace: light subpath states and the contribution candidates.
@@ -106,45 +117,44 @@ struct GenWork {
     SubpathContrib c[MAXC];
 };
 
-LMC_HD void trace_state_init(TraceState &ts) {
-    memset(&ts, 0, sizeof(ts));
-}
+LMC_HD void trace_state_init(TraceState &ts) { memset(&ts, 0, sizeof(ts)); }
 
 // ---- PerturbPathBidir --------------------------------------------------------------------
-template <int MAXD>
-LMC_HD bool perturb_camera_begin(const Scene &sc, const float *offset, Path<MAXD> &path, TraceState &ts) {
-    perturb(path.screenPos.x, offset, ts.offsetId);
-    perturb(path.screenPos.y, offset, ts.offsetId);
-    emit_from_camera(sc, path.screenPos, ts.ray, ts.minT, ts.maxT, ts.cps);
-    if (path.nCam <= 0) { ts.stage = TS_DONE; return false; }
+// `ph` is the proposal's PathHead, `sv` the vertex the pending ray was shot for (path.lgt[ts.depth] /
+// path.cam[ts.depth]), `lgtVerts` = path.lgt.  OFF: anything indexable like the offset vector.
+template <class OFF>
+LMC_HD bool perturb_camera_begin(const Scene &sc, const OFF &offset, PathHead &ph, TraceState &ts) {
+    perturb(ph.screenPos.x, offset, ts.offsetId);
+    perturb(ph.screenPos.y, offset, ts.offsetId);
+    emit_from_camera(sc, ph.screenPos, ts.ray, ts.minT, ts.maxT, ts.cps);
+    if (ph.nCam <= 0) { ts.stage = TS_DONE; return false; }
     ts.stage = TS_P_CAM; ts.depth = 0;
     return true;
 }
 
-template <int MAXD>
-LMC_HD bool perturb_stage_begin(const Scene &sc, const float *offset, Path<MAXD> &path, TraceState &ts, Rng &rng) {
+template <class OFF>
+LMC_HD bool perturb_stage_begin(const Scene &sc, const OFF &offset, PathHead &ph, TraceState &ts, Rng &rng) {
     NormalDist nd = normal_make(0.0f, sc.opt.discreteStdDev);
     ts.offsetId = 0;
-    path.time = modulo1(path.time + normal_draw(nd, rng));
+    ph.time = modulo1(ph.time + normal_draw(nd, rng));
     ts.ndSaved = nd.saved; ts.ndAvail = nd.savedAvailable ? 1 : 0;
-    if (path.lgtDepth > 1) {
-        const float lightPickProb = pick_light_prob(sc, path.lgtLight);
-        perturb(path.lgtRndPos.x, offset, ts.offsetId);
-        perturb(path.lgtRndPos.y, offset, ts.offsetId);
-        perturb(path.lgtRndDir.x, offset, ts.offsetId);
-        perturb(path.lgtRndDir.y, offset, ts.offsetId);
-        emit_from_light(sc, lightPickProb, path, ts.ray, ts.lps);
+    if (ph.lgtDepth > 1) {
+        const float lightPickProb = pick_light_prob(sc, ph.lgtLight);
+        perturb(ph.lgtRndPos.x, offset, ts.offsetId);
+        perturb(ph.lgtRndPos.y, offset, ts.offsetId);
+        perturb(ph.lgtRndDir.x, offset, ts.offsetId);
+        perturb(ph.lgtRndDir.y, offset, ts.offsetId);
+        emit_from_light(sc, lightPickProb, ph, ts.ray, ts.lps);
         ts.minT = LMC_ISECT_EPS; ts.maxT = dm_inf();
-        if (path.nLgt > 0) { ts.stage = TS_P_LGT; ts.depth = 0; return true; }
+        if (ph.nLgt > 0) { ts.stage = TS_P_LGT; ts.depth = 0; return true; }
     }
-    return perturb_camera_begin(sc, offset, path, ts);
+    return perturb_camera_begin(sc, offset, ph, ts);
 }
 
-template <int MAXD, class CL>
-LMC_HD bool perturb_stage_light(const Scene &sc, const float *offset, Path<MAXD> &path, TraceState &ts, CL &contribs,
-                                Rng &rng, const Hit &hit) {
+template <class OFF, class CL>
+LMC_HD bool perturb_stage_light(const Scene &sc, const OFF &offset, PathHead &ph, SurfaceVertex &sv, TraceState &ts,
+                                CL &contribs, Rng &rng, const Hit &hit) {
     const int lgtDepth = ts.depth;
-    SurfaceVertex &sv = path.lgt[lgtDepth];
     BidirPathState &lps = ts.lps;
     if (hit.tid < 0) { ts.stage = TS_DONE; return false; }
     sv.tid = hit.tid;
@@ -154,12 +164,12 @@ LMC_HD bool perturb_stage_light(const Scene &sc, const float *offset, Path<MAXD>
     nd.saved = ts.ndSaved; nd.savedAvailable = ts.ndAvail != 0;
     sv.bsdfDiscrete = modulo1(sv.bsdfDiscrete + normal_draw(nd, rng));
     ts.ndSaved = nd.saved; ts.ndAvail = nd.savedAvailable ? 1 : 0;
-    convert_mis(sc, lgtDepth, path.lgtLight, ts.ray, lps);
-    if (lgtDepth == path.nLgt - 1 && path.camDepth == 1) {
+    convert_mis(sc, lgtDepth, ph.lgtLight, ts.ray, lps);
+    if (lgtDepth == ph.nLgt - 1 && ph.camDepth == 1) {
         connect_to_camera(sc, lgtDepth, lps, sv, ts.ray.org, contribs);
         ts.stage = TS_DONE; return false;
     }
-    if (lgtDepth == path.nLgt - 1) return perturb_camera_begin(sc, offset, path, ts);
+    if (lgtDepth == ph.nLgt - 1) return perturb_camera_begin(sc, offset, ph, ts);
     perturb(sv.bsdfRndParam.x, offset, ts.offsetId);
     perturb(sv.bsdfRndParam.y, offset, ts.offsetId);
     V3 bsdfContrib;
@@ -170,19 +180,18 @@ LMC_HD bool perturb_stage_light(const Scene &sc, const float *offset, Path<MAXD>
     return true;
 }
 
-template <int MAXD, class CL>
-LMC_HD bool perturb_stage_camera(const Scene &sc, const float *offset, Path<MAXD> &path, TraceState &ts, CL &contribs,
-                                 Rng &rng, const Hit &hit) {
+template <class OFF, class CL>
+LMC_HD bool perturb_stage_camera(const Scene &sc, const OFF &offset, PathHead &ph, SurfaceVertex &sv,
+                                 const SurfaceVertex *lgtVerts, TraceState &ts, CL &contribs, Rng &rng, const Hit &hit) {
     const int camDepth = ts.depth;
-    SurfaceVertex &sv = path.cam[camDepth];
     BidirPathState &cps = ts.cps;
     const bool hitSurface = hit.tid >= 0;
     if (hitSurface) { sv.tid = hit.tid; fill_isect(sc, ts.ray, hit, cps.isect, sv.st); }
     cps.wi = -ts.ray.dir;
     if (hitSurface) convert_mis(sc, camDepth, -1, ts.ray, cps);
-    if (camDepth == path.nCam - 1 && path.lgtDepth == 0) {
+    if (camDepth == ph.nCam - 1 && ph.lgtDepth == 0) {
         const int light = get_hit_light(sc, hitSurface, sv.tid);
-        if (light >= 0) handle_hit_light(sc, camDepth, light, hitSurface, ts.ray, path.screenPos, cps, path, contribs);
+        if (light >= 0) handle_hit_light(sc, camDepth, light, hitSurface, ts.ray, ph.screenPos, cps, ph, contribs);
         ts.stage = TS_DONE; return false;
     }
     if (!hitSurface) { ts.stage = TS_DONE; return false; }
@@ -191,18 +200,19 @@ LMC_HD bool perturb_stage_camera(const Scene &sc, const float *offset, Path<MAXD
     sv.bsdfDiscrete = modulo1(sv.bsdfDiscrete + normal_draw(nd, rng));
     ts.ndSaved = nd.saved; ts.ndAvail = nd.savedAvailable ? 1 : 0;
     if (camDepth == 1) {
-        path.lensVertexPos = cps.isect.position;
+        ph.lensVertexPos = cps.isect.position;
         const float distSq = distance_squared(cps.isect.position, ts.ray.org);
         if (distSq <= 0.0f) { contribs.clear(); ts.stage = TS_DONE; return false; }
     }
-    if (camDepth == path.nCam - 1) {
-        if (path.lgtDepth == 1) {
+    if (camDepth == ph.nCam - 1) {
+        if (ph.lgtDepth == 1) {
             const float directLightPickProb = pick_light_prob(sc, sv.dlLight);
             perturb(sv.dlRndParam.x, offset, ts.offsetId);
             perturb(sv.dlRndParam.y, offset, ts.offsetId);
-            direct_lighting(sc, camDepth, cps, path.screenPos, directLightPickProb, sv, contribs);
+            direct_lighting(sc, camDepth, cps, ph.screenPos, directLightPickProb, sv, contribs);
         } else {
-            connect_vertex(sc, camDepth, path.nLgt - 1, ts.lps, path.lgt[path.nLgt - 1], cps, sv, path.screenPos, contribs);
+            const SurfaceVertex lv = lgtVerts[ph.nLgt - 1];
+            connect_vertex(sc, camDepth, ph.nLgt - 1, ts.lps, lv, cps, sv, ph.screenPos, contribs);
         }
         ts.stage = TS_DONE; return false;
     }
@@ -218,68 +228,67 @@ LMC_HD bool perturb_stage_camera(const Scene &sc, const float *offset, Path<MAXD
 }
 
 // ---- GeneratePathBidir(scene, (-1,-1), minDepth, maxDepth, ...) ---------------------------------
-template <int MAXD>
-LMC_HD bool gen_camera_begin(const Scene &sc, Path<MAXD> &path, TraceState &ts, Rng &rng) {
-    path.screenPos.x = rng_uniform(rng); path.screenPos.y = rng_uniform(rng);
-    emit_from_camera(sc, path.screenPos, ts.ray, ts.minT, ts.maxT, ts.cps);
+// `ls` = the light subpath states (GenWork::ls); `sv` = the slot path.lgt[ph.nLgt] / path.cam[ph.nCam]
+// AT ENTRY (the stage zero-fills it first, as the reference's emplace_back does).
+LMC_HD bool gen_camera_begin(const Scene &sc, PathHead &ph, TraceState &ts, Rng &rng) {
+    ph.screenPos.x = rng_uniform(rng); ph.screenPos.y = rng_uniform(rng);
+    emit_from_camera(sc, ph.screenPos, ts.ray, ts.minT, ts.maxT, ts.cps);
     ts.stage = TS_G_CAM; ts.depth = 0;
     return true;
 }
 
-template <int MAXD, int MAXC>
-LMC_HD bool gen_stage_begin(const Scene &sc, Path<MAXD> &path, TraceState &ts, GenWork<MAXD, MAXC> &gw, Rng &rng) {
-    path.time = rng_uniform(rng);
+LMC_HD bool gen_stage_begin(const Scene &sc, PathHead &ph, TraceState &ts, BidirPathState *ls, Rng &rng) {
+    ph.time = rng_uniform(rng);
     ts.nLightStates = 1;
     float lightPickProb = 1.0f;
-    path.lgtRndPos.x = rng_uniform(rng); path.lgtRndPos.y = rng_uniform(rng);
-    path.lgtRndDir.x = rng_uniform(rng); path.lgtRndDir.y = rng_uniform(rng);
-    path.lgtLight = pick_light(sc, rng_uniform(rng), lightPickProb);
-    path.lgtPrim = light_sample_discrete(sc, path.lgtLight, rng_uniform(rng));
-    emit_from_light(sc, lightPickProb, path, ts.ray, gw.ls[0]);
+    ph.lgtRndPos.x = rng_uniform(rng); ph.lgtRndPos.y = rng_uniform(rng);
+    ph.lgtRndDir.x = rng_uniform(rng); ph.lgtRndDir.y = rng_uniform(rng);
+    ph.lgtLight = pick_light(sc, rng_uniform(rng), lightPickProb);
+    ph.lgtPrim = light_sample_discrete(sc, ph.lgtLight, rng_uniform(rng));
+    emit_from_light(sc, lightPickProb, ph, ts.ray, ls[0]);
     ts.minT = LMC_ISECT_EPS; ts.maxT = dm_inf();
     ts.stage = TS_G_LGT; ts.depth = 0;
     return true;
 }
 
-template <int MAXD, int MAXC, class CL>
-LMC_HD bool gen_stage_light(const Scene &sc, int minDepth, int maxDepth, Path<MAXD> &path, TraceState &ts,
-                            GenWork<MAXD, MAXC> &gw, CL &contribs, Rng &rng, const Hit &hit) {
+template <class CL>
+LMC_HD bool gen_stage_light(const Scene &sc, int minDepth, int maxDepth, PathHead &ph, SurfaceVertex &sv, TraceState &ts,
+                            BidirPathState *ls, CL &contribs, Rng &rng, const Hit &hit) {
     const int lgtDepth = ts.depth;
-    path.lgt[path.nLgt] = surface_vertex_zero();
-    SurfaceVertex &sv = path.lgt[path.nLgt];
-    path.nLgt++;
-    BidirPathState &cur = gw.ls[lgtDepth];
-    if (hit.tid < 0) { ts.nLightStates--; path.nLgt--; return gen_camera_begin(sc, path, ts, rng); }
+    sv = surface_vertex_zero();
+    ph.nLgt++;
+    BidirPathState &cur = ls[lgtDepth];
+    if (hit.tid < 0) { ts.nLightStates--; ph.nLgt--; return gen_camera_begin(sc, ph, ts, rng); }
     sv.tid = hit.tid;
     fill_isect(sc, ts.ray, hit, cur.isect, sv.st);
     sv.bsdfDiscrete = rng_uniform(rng);
     cur.wi = -ts.ray.dir;
-    convert_mis(sc, lgtDepth, path.lgtLight, ts.ray, cur);
+    convert_mis(sc, lgtDepth, ph.lgtLight, ts.ray, cur);
     if (lgtDepth + 2 >= minDepth) connect_to_camera(sc, lgtDepth, cur, sv, ts.ray.org, contribs);
-    if (maxDepth != -1 && lgtDepth + 2 >= maxDepth) return gen_camera_begin(sc, path, ts, rng);
+    if (maxDepth != -1 && lgtDepth + 2 >= maxDepth) return gen_camera_begin(sc, ph, ts, rng);
     ts.nLightStates++;
     sv.bsdfRndParam.x = rng_uniform(rng); sv.bsdfRndParam.y = rng_uniform(rng);
     V3 bsdfContrib;
-    gw.ls[lgtDepth + 1].ssJacobian = 0.0f;
-    if (!bsdf_sampling<true, false>(sc, cur, sv, gw.ls[lgtDepth + 1], ts.ray.dir, bsdfContrib)) {
-        ts.nLightStates--; return gen_camera_begin(sc, path, ts, rng);
+    ls[lgtDepth + 1].ssJacobian = 0.0f;
+    if (!bsdf_sampling<true, false>(sc, cur, sv, ls[lgtDepth + 1], ts.ray.dir, bsdfContrib)) {
+        ts.nLightStates--; return gen_camera_begin(sc, ph, ts, rng);
     }
-    if (!russian_roulette(lgtDepth, bsdfContrib, sv.rrWeight, gw.ls[lgtDepth + 1].throughput, rng)) {
-        ts.nLightStates--; return gen_camera_begin(sc, path, ts, rng);
+    if (!russian_roulette(lgtDepth, bsdfContrib, sv.rrWeight, ls[lgtDepth + 1].throughput, rng)) {
+        ts.nLightStates--; return gen_camera_begin(sc, ph, ts, rng);
     }
     ts.ray.org = cur.isect.position;
     ts.depth = lgtDepth + 1;
     return true;
 }
 
-template <int MAXD, int MAXC, class CL>
-LMC_HD bool gen_stage_camera(const Scene &sc, int minDepth, int maxDepth, Path<MAXD> &path, TraceState &ts,
-                             GenWork<MAXD, MAXC> &gw, CL &contribs, Rng &rng, const Hit &hit) {
+template <class CL>
+LMC_HD bool gen_stage_camera(const Scene &sc, int minDepth, int maxDepth, PathHead &ph, SurfaceVertex &sv,
+                             const SurfaceVertex *lgtVerts, TraceState &ts, const BidirPathState *ls, CL &contribs,
+                             Rng &rng, const Hit &hit) {
     const int camDepth = ts.depth;
     BidirPathState &cps = ts.cps;
-    path.cam[path.nCam] = surface_vertex_zero();
-    SurfaceVertex &sv = path.cam[path.nCam];
-    path.nCam++;
+    sv = surface_vertex_zero();
+    ph.nCam++;
     const bool hitSurface = hit.tid >= 0;
     if (hitSurface) { sv.tid = hit.tid; fill_isect(sc, ts.ray, hit, cps.isect, sv.st); }
     cps.wi = -ts.ray.dir;
@@ -287,13 +296,13 @@ LMC_HD bool gen_stage_camera(const Scene &sc, int minDepth, int maxDepth, Path<M
     if (camDepth + 1 >= minDepth) {
         const int light = get_hit_light(sc, hitSurface, sv.tid);
         if (light >= 0) {
-            handle_hit_light(sc, camDepth, light, hitSurface, ts.ray, path.screenPos, cps, path, contribs);
+            handle_hit_light(sc, camDepth, light, hitSurface, ts.ray, ph.screenPos, cps, ph, contribs);
             ts.stage = TS_DONE; return false;
         }
     }
     if (!hitSurface || (maxDepth != -1 && camDepth + 1 >= maxDepth)) { ts.stage = TS_DONE; return false; }
     if (camDepth == 1) {
-        path.lensVertexPos = cps.isect.position;
+        ph.lensVertexPos = cps.isect.position;
         const float distSq = distance_squared(cps.isect.position, ts.ray.org);
         if (distSq <= 0.0f) { contribs.clear(); ts.stage = TS_DONE; return false; }
     }
@@ -303,7 +312,7 @@ LMC_HD bool gen_stage_camera(const Scene &sc, int minDepth, int maxDepth, Path<M
         sv.dlLight = pick_light(sc, rng_uniform(rng), directLightPickProb);
         sv.dlRndParam.x = rng_uniform(rng); sv.dlRndParam.y = rng_uniform(rng);
         sv.dlPrim = light_sample_discrete(sc, sv.dlLight, rng_uniform(rng));
-        direct_lighting(sc, camDepth, cps, path.screenPos, directLightPickProb, sv, contribs);
+        direct_lighting(sc, camDepth, cps, ph.screenPos, directLightPickProb, sv, contribs);
     }
     int maxLgtDepth = ts.nLightStates - 1;
     if (maxDepth != -1) {
@@ -312,7 +321,8 @@ LMC_HD bool gen_stage_camera(const Scene &sc, int minDepth, int maxDepth, Path<M
     }
     for (int lgtDepth = 0; lgtDepth <= maxLgtDepth; lgtDepth++) {
         if (camDepth + lgtDepth + 3 >= minDepth) {
-            connect_vertex(sc, camDepth, lgtDepth, gw.ls[lgtDepth], path.lgt[lgtDepth], cps, sv, path.screenPos, contribs);
+            const SurfaceVertex lv = lgtVerts[lgtDepth];
+            connect_vertex(sc, camDepth, lgtDepth, ls[lgtDepth], lv, cps, sv, ph.screenPos, contribs);
         }
     }
     sv.bsdfRndParam.x = rng_uniform(rng); sv.bsdfRndParam.y = rng_uniform(rng);

@@ -122,10 +122,11 @@ static __global__ void k_sort_scatter(int n, SortList a, SortList b, int nb) {
 
 template <int MAXD>
 __device__ __forceinline__ void rng_open(Rng &rng, uint32_t *tab, const Scene &sc, int globalChainId, ChainState<MAXD> &cs) {
+    // lazy table: `tab` (local scratch) is written only if the table must advance (2^-32 per draw)
     rng.tab = tab; rng.stride = 1;
     const uint64_t seed = (uint64_t)(long long)(globalChainId + sc.opt.seedOffset);
-    if (!cs.seeded) { rng_seed(rng, seed); cs.seeded = 1u; }
-    else rng_restore(rng, seed, cs.rngState, cs.rngEpoch);
+    if (!cs.seeded) { rng_seed_lazy(rng, seed); cs.seeded = 1u; }
+    else rng_restore_lazy(rng, seed, cs.rngState, cs.rngEpoch);
 }
 template <int MAXD>
 __device__ __forceinline__ void rng_close(const Rng &rng, ChainState<MAXD> &cs) { cs.rngState = rng.state; cs.rngEpoch = rng.epoch; }
@@ -202,6 +203,276 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_finish(const __grid_co
     if (aTrace) aTrace[(size_t)i * numSteps + stepInLaunch] = info.a;
 }
 
+// ---- per-vertex wavefront of the proposal phase ------------------------------------------------
+// The proposal (PerturbPathBidir / GeneratePathBidir) advances one path vertex per WAVE:
+//   k_trace      closest hit for every pending ray of the wave
+//   k_shade<S>   the reference's statements between two ray queries (core/stages.h) for the chains
+//                whose pending ray belongs to stage S; pushes the next ray into the other queue
+//                set and the shadow rays of candidate contributions into the shadow queue
+// and after the last wave
+//   k_shadow     any-hit for all queued connection segments -> candidate flags
+//   k_prop_post  contribution choice / acceptance bookkeeping (mutation.h propose_post_*)
+//
+// A queue entry carries the whole between-stage state of its proposal (TraceState + PathHead =
+// LMC_PAYLOAD_U4 x 16 B) as chunk-major SoA, payload[chunk * cap + slot], so a warp moves it with
+// fully coalesced 512-byte accesses and a shade kernel touches the 5 KB chain record only for the
+// one path vertex it works on.  A chain has at most one pending ray, so the two queues of a step
+// kind (light / camera subpath) share one buffer of `cap` = numChains slots and grow towards each
+// other from its two ends.
+struct alignas(16) Payload { TraceState ts; PathHead ph; };
+#define LMC_PAYLOAD_U4 ((int)(sizeof(Payload) / 16))
+struct RayQueue {
+    int *chain;       // chain slot of entry s
+    uint4 *payload;   // [LMC_PAYLOAD_U4][cap]
+    float4 *hit;      // x = tid (int bits), y = t, z = u, w = v     (written by k_trace)
+    int *count;
+    int base, dirn;   // entry t lives in slot base + dirn * t
+    int cap;
+};
+struct ShadowQueue {
+    float4 *org;      // xyz, w = dist
+    float4 *dir;
+    int **flag;       // candidate flag to resolve
+    int *count;
+    int cap;
+};
+struct WaveQueues {
+    RayQueue q[2][4]; // [set][stage - 1]
+    ShadowQueue sh;
+};
+
+struct DevShadowSink {
+    ShadowQueue sh;
+    const Scene *sc;
+    __device__ __forceinline__ void emit(const Ray &ray, float dist, int, int *flag) {
+        const int pos = atomicAdd(sh.count, 1);
+        if (pos < sh.cap) {
+            sh.org[pos] = make_float4(ray.org.x, ray.org.y, ray.org.z, dist);
+            sh.dir[pos] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, 0.0f);
+            sh.flag[pos] = flag;
+        } else {
+            *flag = cand_resolve(*flag, scene_occluded(*sc, ray, dist));    // queue full: resolve on the spot
+        }
+    }
+};
+
+__device__ __forceinline__ void payload_load(const RayQueue &q, int slot, Payload &p) {
+    uint4 *d = reinterpret_cast<uint4 *>(&p);
+#pragma unroll
+    for (int k = 0; k < LMC_PAYLOAD_U4; k++) d[k] = q.payload[(size_t)k * q.cap + slot];
+}
+__device__ __forceinline__ void ray_push(const RayQueue &q, bool pred, int chain, const Payload &p) {
+    const unsigned mask = __ballot_sync(__activemask(), pred);
+    if (!pred) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(q.count, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    const int slot = q.base + q.dirn * (base + __popc(mask & ((1u << lane) - 1u)));
+    q.chain[slot] = chain;
+    const uint4 *s = reinterpret_cast<const uint4 *>(&p);
+#pragma unroll
+    for (int k = 0; k < LMC_PAYLOAD_U4; k++) q.payload[(size_t)k * q.cap + slot] = s[k];
+}
+template <class T>
+__device__ __forceinline__ void copy_u4(T &dst, const T &src) {
+    static_assert(sizeof(T) % 16 == 0 && alignof(T) >= 16, "16-byte records only");
+    uint4 *d = reinterpret_cast<uint4 *>(&dst);
+    const uint4 *s = reinterpret_cast<const uint4 *>(&src);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(T) / 16); k++) d[k] = s[k];
+}
+// the two offsets a perturbation stage consumes, fetched up front
+struct OffPair {
+    float v0, v1; int base;
+    __device__ __forceinline__ float operator[](int i) const { return (i == base) ? v0 : v1; }
+};
+__device__ __forceinline__ void rng_from_payload(Rng &rng, uint32_t *tab, const Scene &sc, int globalChainId, const TraceState &ts) {
+    rng.tab = tab; rng.stride = 1;
+    const uint64_t seed = (uint64_t)(long long)(globalChainId + sc.opt.seedOffset);
+    rng_restore_lazy(rng, seed, ((uint64_t)ts.rngHi << 32) | (uint64_t)ts.rngLo, ts.rngEpoch);
+}
+__device__ __forceinline__ void rng_to_payload(const Rng &rng, TraceState &ts) {
+    ts.rngLo = (uint32_t)rng.state; ts.rngHi = (uint32_t)(rng.state >> 32); ts.rngEpoch = rng.epoch;
+}
+
+#ifndef LMC_SHADE_MINB
+#define LMC_SHADE_MINB 4
+#endif
+template <int MAXD> struct GenWorkT { typedef GenWork<MAXD, Limits<MAXD>::MAXC> type; };
+
+// first stage of every proposal: PRE part of the mutation + the statements up to the first ray
+template <int MAXD, int LARGE>
+__global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_SHADE_MINB) k_prop_start(const __grid_constant__ Scene sc, int chainBase, ChainRec<MAXD> *states,
+                                                                 typename GenWorkT<MAXD>::type *genWork, const int *list, const int *countp,
+                                                                 WaveQueues wq, H2mcSide *sides) {
+    const int count = *countp;
+    const int stride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x; base < count; base += stride) {
+        const int t = base + threadIdx.x;
+        bool more = false; int i = -1;
+        Payload p;
+        if (t < count) {
+            i = list[t];
+            uint32_t tab[64];
+            ChainState<MAXD> &cs = states[i].cs;
+            Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
+            const int curIdx = cs.curIdx;
+            MarkovState<MAXD> &cur = cs.st[curIdx], &prop = cs.st[curIdx ^ 1];
+            memset(&p.ts, 0, sizeof(p.ts));
+            p.ts.curIdx = curIdx;
+            if (LARGE) {
+                cs.ch.lastMutationType = MUT_LARGE;             // propose_pre_large on the payload's head
+                copy_u4<PathHead>(p.ph, prop.path);
+                path_clear(p.ph);
+                genWork[i].n = 0;
+                more = gen_stage_begin(sc, p.ph, p.ts, genWork[i].ls, rng);
+            } else {
+                propose_pre_small<MAXD, false>(sc, cur, prop, cs.ch, rng, cs.ss, sides ? sides + i : nullptr, curIdx);
+                cs.pc.n = 0;
+                copy_u4<PathHead>(p.ph, cur.path);
+                const float *offset = cs.ss.offset;
+                more = perturb_stage_begin(sc, offset, p.ph, p.ts, rng);
+            }
+            rng_to_payload(rng, p.ts);
+            if (!more) { copy_u4<PathHead>(prop.path, p.ph); rng_close(rng, cs); }
+        }
+        if (LARGE) {
+            ray_push(wq.q[0][TS_G_LGT - 1], more, i, p);
+        } else {
+            ray_push(wq.q[0][TS_P_LGT - 1], more && p.ts.stage == TS_P_LGT, i, p);
+            ray_push(wq.q[0][TS_P_CAM - 1], more && p.ts.stage == TS_P_CAM, i, p);
+        }
+    }
+}
+
+template <int MAXD, int STAGE>
+__global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_SHADE_MINB) k_shade(const __grid_constant__ Scene sc, int chainBase, ChainRec<MAXD> *states,
+                                                            typename GenWorkT<MAXD>::type *genWork, WaveQueues wq, int curSet) {
+    const RayQueue &qi = wq.q[curSet][STAGE - 1];
+    const int count = *qi.count;
+    const int stride = gridDim.x * blockDim.x;
+    const int nextSet = curSet ^ 1;
+    for (int base = blockIdx.x * blockDim.x; base < count; base += stride) {
+        const int t = base + threadIdx.x;
+        bool more = false; int i = -1;
+        Payload p;
+        if (t < count) {
+            const int slot = qi.base + qi.dirn * t;
+            i = qi.chain[slot];
+            payload_load(qi, slot, p);
+            const float4 h4 = qi.hit[slot];
+            Hit hit; hit.tid = __float_as_int(h4.x); hit.t = h4.y; hit.u = h4.z; hit.v = h4.w;
+            ChainState<MAXD> &cs = states[i].cs;
+            MarkovState<MAXD> &cur = cs.st[p.ts.curIdx], &prop = cs.st[p.ts.curIdx ^ 1];
+            uint32_t tab[64];
+            Rng rng; rng_from_payload(rng, tab, sc, chainBase + i, p.ts);
+            DevShadowSink sink; sink.sh = wq.sh; sink.sc = &sc;
+            DeferredList<DevShadowSink> dl;
+            SurfaceVertex sv;
+            if (STAGE == TS_P_LGT || STAGE == TS_P_CAM) {
+                OffPair off; off.base = p.ts.offsetId;
+                off.v0 = cs.ss.offset[off.base]; off.v1 = cs.ss.offset[off.base + 1];
+                dl.bind(cs.pc.c, cs.pc.flag, &cs.pc.n, 2, &sink);
+                const int d = p.ts.depth;
+                if (STAGE == TS_P_LGT) {
+                    copy_u4<SurfaceVertex>(sv, cur.path.lgt[d]);
+                    more = perturb_stage_light(sc, off, p.ph, sv, p.ts, dl, rng, hit);
+                    copy_u4<SurfaceVertex>(prop.path.lgt[d], sv);
+                } else {
+                    copy_u4<SurfaceVertex>(sv, cur.path.cam[d]);
+                    more = perturb_stage_camera(sc, off, p.ph, sv, prop.path.lgt, p.ts, dl, rng, hit);
+                    copy_u4<SurfaceVertex>(prop.path.cam[d], sv);
+                }
+            } else {
+                typename GenWorkT<MAXD>::type &gw = genWork[i];
+                dl.bind(gw.c, gw.flag, &gw.n, Limits<MAXD>::MAXC, &sink);
+                const int minDepth = sc.opt.minDepth > 3 ? sc.opt.minDepth : 3;
+                if (STAGE == TS_G_LGT) {
+                    const int d = p.ph.nLgt;
+                    more = gen_stage_light(sc, minDepth, sc.opt.maxDepth, p.ph, sv, p.ts, gw.ls, dl, rng, hit);
+                    copy_u4<SurfaceVertex>(prop.path.lgt[d], sv);
+                } else {
+                    const int d = p.ph.nCam;
+                    more = gen_stage_camera(sc, minDepth, sc.opt.maxDepth, p.ph, sv, prop.path.lgt, p.ts, gw.ls, dl, rng, hit);
+                    copy_u4<SurfaceVertex>(prop.path.cam[d], sv);
+                }
+            }
+            rng_to_payload(rng, p.ts);
+            if (!more) { copy_u4<PathHead>(prop.path, p.ph); rng_close(rng, cs); }   // leaving the wavefront
+        }
+        if (STAGE == TS_P_LGT) {
+            ray_push(wq.q[nextSet][TS_P_LGT - 1], more && p.ts.stage == TS_P_LGT, i, p);
+            ray_push(wq.q[nextSet][TS_P_CAM - 1], more && p.ts.stage == TS_P_CAM, i, p);
+        } else if (STAGE == TS_P_CAM) {
+            ray_push(wq.q[nextSet][TS_P_CAM - 1], more, i, p);
+        } else if (STAGE == TS_G_LGT) {
+            ray_push(wq.q[nextSet][TS_G_LGT - 1], more && p.ts.stage == TS_G_LGT, i, p);
+            ray_push(wq.q[nextSet][TS_G_CAM - 1], more && p.ts.stage == TS_G_CAM, i, p);
+        } else {
+            ray_push(wq.q[nextSet][TS_G_CAM - 1], more, i, p);
+        }
+    }
+}
+
+// closest hit for the four ray queues of a wave; the ray sits in payload words 6..13
+static __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ Scene sc, WaveQueues wq, int curSet) {
+    const int c0 = *wq.q[curSet][0].count, c1 = c0 + *wq.q[curSet][1].count, c2 = c1 + *wq.q[curSet][2].count,
+              c3 = c2 + *wq.q[curSet][3].count;
+    const int stride = gridDim.x * blockDim.x;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < c3; idx += stride) {
+        const int k = (idx >= c0) + (idx >= c1) + (idx >= c2);
+        const int pos = idx - (k == 0 ? 0 : (k == 1 ? c0 : (k == 2 ? c1 : c2)));
+        const RayQueue &q = wq.q[curSet][k];
+        const int slot = q.base + q.dirn * pos;
+        const uint4 a = q.payload[(size_t)1 * q.cap + slot], b = q.payload[(size_t)2 * q.cap + slot], c = q.payload[(size_t)3 * q.cap + slot];
+        Ray ray;
+        ray.org = mk3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
+        ray.dir = mk3(__uint_as_float(b.w), __uint_as_float(c.x), __uint_as_float(c.y));
+        const Hit h = bvh_traverse<false>(sc, ray, __uint_as_float(a.z), __uint_as_float(a.w));
+        q.hit[slot] = make_float4(__int_as_float(h.tid), h.t, h.u, h.v);
+    }
+}
+// any hit for the queued connection segments
+static __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ Scene sc, ShadowQueue sh) {
+    int n = *sh.count; if (n > sh.cap) n = sh.cap;
+    const int stride = gridDim.x * blockDim.x;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+        const float4 o = sh.org[idx], d = sh.dir[idx];
+        Ray ray; ray.org = mk3(o.x, o.y, o.z); ray.dir = mk3(d.x, d.y, d.z);
+        const bool occ = scene_occluded(sc, ray, o.w);
+        int *f = sh.flag[idx];
+        *f = cand_resolve(*f, occ);
+    }
+}
+
+// POST part of the mutation once every candidate is resolved
+template <int MAXD, int LARGE>
+__global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_prop_post(const __grid_constant__ Scene sc, RunParams rp, int chainBase, ChainRec<MAXD> *states,
+                                                                typename GenWorkT<MAXD>::type *genWork, const int *list, const int *countp,
+                                                                WaveLists wl) {
+    const int count = *countp;
+    const int stride = gridDim.x * blockDim.x;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        const int i = list[t];
+        ChainState<MAXD> &cs = states[i].cs;
+        MarkovState<MAXD> &cur = cs.st[cs.curIdx], &prop = cs.st[cs.curIdx ^ 1];
+        if (LARGE) {
+            uint32_t tab[64];
+            Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
+            typename GenWorkT<MAXD>::type &gw = genWork[i];
+            gw.n = deferred_compact(gw.c, gw.flag, gw.n);
+            propose_post_large(rp, cur, prop, cs.ch, rng, cs.ss, gw);
+            rng_close(rng, cs);
+        } else {
+            cs.pc.n = deferred_compact(cs.pc.c, cs.pc.flag, cs.pc.n);
+            propose_post_small(sc, rp, cur, prop, cs.ss, cs.pc);
+        }
+        sort_key_set(wl.propGrad, i, cs.ss.needPropGrad ? class_key(prop.sp.camDepth, prop.sp.lightDepth, 0) : -1);
+    }
+}
+
 template <int MAXD>
 __global__ void k_chain_stats(const ChainRec<MAXD> *states, int n, unsigned long long *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,48 +492,101 @@ __global__ void k_chain_stats(const ChainRec<MAXD> *states, int n, unsigned long
 
 
 // launchers (defined by LMC_INSTANTIATE_CHAIN in chain_inst_*.cu)
+struct WaveCfg {
+    WaveQueues wq;
+    void *genWork;
+    int *queueCounts;      // 2 x 4 ray-queue counters + the shadow counter (contiguous)
+    int wavefront;         // 1: per-vertex wavefront proposal; 0: monolithic k_wave_propose (A/B)
+    int smCount;
+};
 #define LMC_DECLARE_CHAIN(MAXD) \
     size_t chain_state_bytes_##MAXD(); \
+    size_t gen_work_bytes_##MAXD(); \
     cudaError_t launch_chain_init_##MAXD(cudaStream_t st, void *states, int n, int chainBase, const float *initLs); \
     cudaError_t launch_chain_run_##MAXD(cudaStream_t st, const Scene &sc, const RunParams &rp, int chainBase, void *states, \
                                         int n, long long numSteps, float *film, unsigned char *trace, float *aTrace, \
-                                        const WaveLists &wl, unsigned long long *launches, H2mcSide *sides); \
+                                        const WaveLists &wl, const WaveCfg &wc, unsigned long long *launches, H2mcSide *sides); \
     cudaError_t launch_chain_stats_##MAXD(cudaStream_t st, const void *states, int n, unsigned long long *out);
 LMC_DECLARE_CHAIN(4)
 LMC_DECLARE_CHAIN(8)
 LMC_DECLARE_CHAIN(12)
 
+// One iteration of the chain loop for all chains = the launch sequence below.
+template <int MAXD>
+cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams &rp, int chainBase, void *states_,
+                               int n, long long numSteps, float *film, unsigned char *trace, float *aTrace,
+                               const WaveLists &wl, const WaveCfg &wc, unsigned long long *launches, H2mcSide *sides) {
+    typedef typename GenWorkT<MAXD>::type GW;
+    ChainRec<MAXD> *states = (ChainRec<MAXD> *)states_;
+    GW *genWork = (GW *)wc.genWork;
+    const int B = LMC_CHAIN_BLOCK, G = (n + B - 1) / B;
+    const int sms = wc.smCount > 0 ? wc.smCount : 148;
+    const int GS = G < sms * LMC_SHADE_MINB ? G : sms * LMC_SHADE_MINB;     // grid-stride kernels: one resident wave of CTAs
+    const int GT = G < sms * 16 ? G : sms * 16;
+    const int maxDepth = sc.opt.maxDepth;
+    for (long long k = 0; k < numSteps; k++) {
+        cudaError_t e = cudaMemsetAsync(wl.largeCount, 0, sizeof(int), st);
+        if (e != cudaSuccess) return e;
+        k_wave_begin<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl);
+        k_sort_scan<<<2, LMC_NKEYS, 0, st>>>(wl.small_, wl.curGrad, 2);
+        k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.small_, wl.curGrad, 2);
+        if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides);
+        else k_wave_grad<MAXD, 1><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides);
+        *launches += 4;
+        if (!wc.wavefront) {
+            k_wave_propose<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.small_.list, wl.small_.count, wl, sides);
+            k_wave_propose<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.large, wl.largeCount, wl, sides);
+            *launches += 2;
+        } else {
+            e = cudaMemsetAsync(wc.queueCounts, 0, 9 * sizeof(int), st);
+            if (e != cudaSuccess) return e;
+            k_prop_start<MAXD, 0><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wl.small_.list, wl.small_.count, wc.wq, sides);
+            k_prop_start<MAXD, 1><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wl.large, wl.largeCount, wc.wq, sides);
+            *launches += 2;
+            // a path has at most maxDepth - 1 light-subpath and maxDepth camera-subpath vertices
+            const int numWaves = 2 * maxDepth - 1;
+            for (int w = 0; w < numWaves; w++) {
+                const int cur = w & 1;
+                k_trace<<<GT, 128, 0, st>>>(sc, wc.wq, cur);
+                if (w < maxDepth - 1) {
+                    k_shade<MAXD, TS_P_LGT><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
+                    k_shade<MAXD, TS_G_LGT><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
+                    *launches += 2;
+                }
+                k_shade<MAXD, TS_P_CAM><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
+                k_shade<MAXD, TS_G_CAM><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
+                *launches += 3;
+                e = cudaMemsetAsync(wc.queueCounts + 4 * cur, 0, 4 * sizeof(int), st);
+                if (e != cudaSuccess) return e;
+            }
+            k_shadow<<<GT, 128, 0, st>>>(sc, wc.wq.sh);
+            k_prop_post<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.small_.list, wl.small_.count, wl);
+            k_prop_post<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.large, wl.largeCount, wl);
+            *launches += 3;
+        }
+        k_sort_scan<<<1, LMC_NKEYS, 0, st>>>(wl.propGrad, wl.propGrad, 1);
+        k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.propGrad, wl.propGrad, 1);
+        if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides);
+        else k_wave_grad<MAXD, 1><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides);
+        k_wave_finish<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides);
+        *launches += 4;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 #define LMC_INSTANTIATE_CHAIN(MAXD) \
     size_t chain_state_bytes_##MAXD() { return sizeof(ChainRec<MAXD>); } \
+    size_t gen_work_bytes_##MAXD() { return sizeof(GenWorkT<MAXD>::type); } \
     cudaError_t launch_chain_init_##MAXD(cudaStream_t st, void *states, int n, int chainBase, const float *initLs) { \
         k_chain_init<MAXD><<<(n + 127) / 128, 128, 0, st>>>((ChainRec<MAXD> *)states, n, chainBase, initLs); \
         return cudaGetLastError(); \
     } \
     cudaError_t launch_chain_run_##MAXD(cudaStream_t st, const Scene &sc, const RunParams &rp, int chainBase, void *states_, \
                                         int n, long long numSteps, float *film, unsigned char *trace, float *aTrace, \
-                                        const WaveLists &wl, unsigned long long *launches, H2mcSide *sides) { \
-        ChainRec<MAXD> *states = (ChainRec<MAXD> *)states_; \
-        const int B = LMC_CHAIN_BLOCK, G = (n + B - 1) / B; \
-        for (long long k = 0; k < numSteps; k++) { \
-            cudaError_t e = cudaMemsetAsync(wl.largeCount, 0, sizeof(int), st); \
-            if (e != cudaSuccess) return e; \
-            k_wave_begin<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl); \
-            k_sort_scan<<<2, LMC_NKEYS, 0, st>>>(wl.small_, wl.curGrad, 2); \
-            k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.small_, wl.curGrad, 2); \
-            if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides); \
-            else k_wave_grad<MAXD, 1><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides); \
-            k_wave_propose<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.small_.list, wl.small_.count, wl, sides); \
-            k_wave_propose<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.large, wl.largeCount, wl, sides); \
-            k_sort_scan<<<1, LMC_NKEYS, 0, st>>>(wl.propGrad, wl.propGrad, 1); \
-            k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.propGrad, wl.propGrad, 1); \
-            if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides); \
-            else k_wave_grad<MAXD, 1><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides); \
-            k_wave_finish<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides); \
-            *launches += 10; \
-            e = cudaGetLastError(); \
-            if (e != cudaSuccess) return e; \
-        } \
-        return cudaSuccess; \
+                                        const WaveLists &wl, const WaveCfg &wc, unsigned long long *launches, H2mcSide *sides) { \
+        return launch_chain_run_t<MAXD>(st, sc, rp, chainBase, states_, n, numSteps, film, trace, aTrace, wl, wc, launches, sides); \
     } \
     cudaError_t launch_chain_stats_##MAXD(cudaStream_t st, const void *states, int n, unsigned long long *out) { \
         k_chain_stats<MAXD><<<(n + 127) / 128, 128, 0, st>>>((const ChainRec<MAXD> *)states, n, out); \

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstddef>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,8 @@ struct lmc_ctx {
     int *listMem = nullptr;
     H2mcSide *sides = nullptr; int sidesCap = 0;
     int listCap = 0;
+    WaveCfg wc{};                   // wavefront queues + large-step workspace
+    void *queueMem = nullptr; int queueCap = 0;
     uint64_t launches = 0;
     double lastMs = 0.0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -121,6 +124,38 @@ int chains_begin(lmc_ctx *c) {
         c->wl.large = p; p += n; c->wl.largeCount = p;
         c->listCap = n;
     }
+    if (c->queueCap < n || !c->wc.genWork) {
+        if (c->queueMem) { cudaFree(c->queueMem); c->queueMem = nullptr; }
+        if (c->wc.genWork) { cudaFree(c->wc.genWork); c->wc.genWork = nullptr; }
+        // 2 sets x 2 step kinds: a buffer of n entries (chain, payload, hit) shared by the light- and the
+        // camera-subpath queue of that kind; a shadow queue of 4n segments; 9 counters
+        const size_t nn = (size_t)n, shCap = 4 * nn;
+        const size_t perBuf = nn * (sizeof(int) + sizeof(Payload) + sizeof(float4)) + 64;
+        const size_t bytes = 4 * perBuf + shCap * (2 * sizeof(float4) + sizeof(int *)) + 256;
+        CK(cudaMalloc(&c->queueMem, bytes));
+        char *p = (char *)c->queueMem;
+        auto take = [&](size_t b) { char *r = p; p += (b + 15) & ~(size_t)15; return r; };
+        for (int s = 0; s < 2; s++) for (int kind = 0; kind < 2; kind++) {
+            uint4 *payload = (uint4 *)take(nn * sizeof(Payload));
+            float4 *hit = (float4 *)take(nn * sizeof(float4));
+            int *chain = (int *)take(nn * sizeof(int));
+            for (int end = 0; end < 2; end++) {       // light-subpath queue grows up, camera-subpath queue grows down
+                RayQueue &q = c->wc.wq.q[s][2 * kind + end];
+                q.payload = payload; q.hit = hit; q.chain = chain; q.cap = n;
+                q.base = end ? n - 1 : 0; q.dirn = end ? -1 : 1;
+            }
+        }
+        c->wc.wq.sh.org = (float4 *)take(shCap * sizeof(float4)); c->wc.wq.sh.dir = (float4 *)take(shCap * sizeof(float4));
+        c->wc.wq.sh.flag = (int **)take(shCap * sizeof(int *));
+        c->wc.queueCounts = (int *)take(16 * sizeof(int));
+        for (int s = 0; s < 2; s++) for (int k = 0; k < 4; k++) c->wc.wq.q[s][k].count = c->wc.queueCounts + 4 * s + k;
+        c->wc.wq.sh.count = c->wc.queueCounts + 8;
+        c->wc.wq.sh.cap = (int)shCap;
+        CK(cudaMemsetAsync(c->wc.queueCounts, 0, 16 * sizeof(int), c->stream));
+        const size_t gwBytes = (d == 4 ? gen_work_bytes_4() : (d == 8 ? gen_work_bytes_8() : gen_work_bytes_12())) * nn;
+        CK(cudaMalloc(&c->wc.genWork, gwBytes));
+        c->queueCap = n;
+    }
     if (c->sc.opt.h2mc) {
         if (c->sidesCap < n) {
             if (c->sides) { cudaFree(c->sides); c->sides = nullptr; }
@@ -144,9 +179,9 @@ int run_chains(lmc_ctx *c, long long numSteps, unsigned char *dTrace, float *dAT
     void *st = c->states;
     CK(cudaEventRecord(c->ev0, c->stream));
     unsigned long long nl = 0;
-    CK(d == 4 ? launch_chain_run_4(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl, c->sides)
-              : (d == 8 ? launch_chain_run_8(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl, c->sides)
-                        : launch_chain_run_12(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, &nl, c->sides)));
+    CK(d == 4 ? launch_chain_run_4(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, c->wc, &nl, c->sides)
+              : (d == 8 ? launch_chain_run_8(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, c->wc, &nl, c->sides)
+                        : launch_chain_run_12(c->stream, c->sc, rp, c->desc.chain_base, st, n, numSteps, c->film, dTrace, dATrace, c->wl, c->wc, &nl, c->sides)));
     c->launches += nl;
     CK(cudaEventRecord(c->ev1, c->stream));
     return LMC_OK;
@@ -259,6 +294,12 @@ int lmc_create(const lmc_scene *scene, int32_t device, lmc_ctx **out) {
         return fail(LMC_ERR_CUDA, "device allocation failed");
     }
     c->filmOwned = true;
+    {
+        const char *wf = getenv("LMC_WAVEFRONT");      // A/B switch for profiling; results are identical
+        c->wc.wavefront = (wf && wf[0] == '0') ? 0 : 1;
+        cudaDeviceProp prop;
+        c->wc.smCount = (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ? prop.multiProcessorCount : 148;
+    }
     *out = c;
     return LMC_OK;
 }
@@ -273,6 +314,8 @@ void lmc_destroy(lmc_ctx *c) {
     if (c->statsDev) cudaFree(c->statsDev);
     if (c->listMem) cudaFree(c->listMem);
     if (c->sides) cudaFree(c->sides);
+    if (c->queueMem) cudaFree(c->queueMem);
+    if (c->wc.genWork) cudaFree(c->wc.genWork);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;

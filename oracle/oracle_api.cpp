@@ -318,6 +318,21 @@ int lmco_rng_stream(unsigned long long seed, int n, unsigned int *raw, float *un
     if (nrm) { rng_seed(r, seed); NormalDist d = normal_make(0.0f, 1.0f); for (int i = 0; i < n; i++) nrm[i] = normal_draw(d, r); }
     return 0;
 }
+// raw draws with the table in lazy mode (lazy = 1) or materialised (0); at draw `zeroAt` (>= 0) the low
+// 32 state bits are cleared first, which forces advance_table() (otherwise a 2^-32 event)
+int lmco_rng_stream2(unsigned long long seed, int n, int lazy, int zeroAt, unsigned int *raw) {
+    uint32_t tab[64]; Rng r; r.tab = tab; r.stride = 1;
+    if (lazy) rng_seed_lazy(r, seed); else rng_seed(r, seed);
+    for (int i = 0; i < n; i++) {
+        if (i == zeroAt) r.state &= ~0xFFFFFFFFULL;
+        raw[i] = rng_next(r);
+        if (lazy && (i % 97) == 96) {      // persist / restore round trip as the kernels do between launches
+            const uint64_t st = r.state; const uint32_t ep = r.epoch;
+            rng_restore_lazy(r, seed, st, ep);
+        }
+    }
+    return (int)r.epoch;
+}
 // deterministic math header probes: fn 0 sin, 1 cos, 2 exp, 3 log, 4 pow(x,y), 5 atan2(x,y), 6 acos, 7 fastlog, 8 fastpow(x,y)
 int lmco_math(int fn, int n, const float *x, const float *y, float *out) {
     for (int i = 0; i < n; i++) {

@@ -61,3 +61,18 @@ def test_deterministic_math_accuracy(oracle):
     x = np.exp(rng.uniform(-20, 20, 1000)).astype(np.float32)
     assert np.abs(run(7, x) - np.log(x)).max() < 1e-3 * 20
     assert np.allclose(run(8, np.full(100, 0.5, np.float32), np.full(100, 2.2, np.float32)), 0.5 ** 2.2, rtol=2e-3)
+
+
+def test_rng_lazy_table_equals_materialised(oracle):
+    """core/rng.h lazy mode (table entries computed on demand from the seed with LCG jump-ahead)
+    against the materialised 64-entry table, across a forced advance_table() and persist/restore
+    round trips."""
+    import ctypes
+    for seed in (0, 1, 12345, 2**31 + 7):
+        for zero_at in (-1, 0, 500):
+            a = np.zeros(3000, np.uint32)
+            b = np.zeros(3000, np.uint32)
+            ea = oracle.L.lmco_rng_stream2(ctypes.c_ulonglong(seed), 3000, 0, zero_at, oracle.p(a))
+            eb = oracle.L.lmco_rng_stream2(ctypes.c_ulonglong(seed), 3000, 1, zero_at, oracle.p(b))
+            assert ea == eb == (0 if zero_at < 0 else 1)
+            assert np.array_equal(a, b)
