@@ -109,15 +109,22 @@ static __global__ void k_sort_scan(SortList a, SortList b, int nb) {
     sl.hist[t] = 0;
     sl.cursor[t] = 0;
 }
+// one atomic per (warp, key): lanes holding the same key reserve a run of slots together
+__device__ __forceinline__ void sort_scatter_one(const SortList &sl, int i, bool inRange) {
+    const int key = inRange ? sl.keys[i] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key < 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(sl.cursor + key, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    sl.list[sl.offsets[key] + base + __popc(peers & ((1u << lane) - 1u))] = i;
+}
 static __global__ void k_sort_scatter(int n, SortList a, SortList b, int nb) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int ka = a.keys[i];
-    if (ka >= 0) a.list[a.offsets[ka] + atomicAdd(a.cursor + ka, 1)] = i;
-    if (nb > 1) {
-        const int kb = b.keys[i];
-        if (kb >= 0) b.list[b.offsets[kb] + atomicAdd(b.cursor + kb, 1)] = i;
-    }
+    sort_scatter_one(a, i, i < n);
+    if (nb > 1) sort_scatter_one(b, i, i < n);
 }
 
 template <int MAXD>
@@ -131,6 +138,17 @@ __device__ __forceinline__ void rng_open(Rng &rng, uint32_t *tab, const Scene &s
 template <int MAXD>
 __device__ __forceinline__ void rng_close(const Rng &rng, ChainState<MAXD> &cs) { cs.rngState = rng.state; cs.rngEpoch = rng.epoch; }
 
+// phase_begin + work-list keys for chain i (shared by k_wave_begin and the fused k_wave_finish)
+template <int MAXD>
+__device__ __forceinline__ int wave_begin_chain(const Scene &sc, const RunParams &rp, ChainState<MAXD> &cs, Rng &rng, int i, const WaveLists &wl) {
+    phase_begin(sc, rp, cs.sampleIdx, cs.st[cs.curIdx], cs.ch, rng, cs.ss);
+    const int kind = cs.ss.kind;
+    const Path<MAXD> &p = cs.st[cs.curIdx].path;
+    sort_key_set(wl.small_, i, kind == STEP_LARGE ? -1 : class_key(p.camDepth, p.lgtDepth, kind == STEP_ISO ? 0 : 1));
+    sort_key_set(wl.curGrad, i, cs.ss.needCurGrad ? class_key(p.camDepth, p.lgtDepth, 0) : -1);
+    return kind;
+}
+
 template <int MAXD>
 __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_begin(const __grid_constant__ Scene sc, RunParams rp, int chainBase,
                                                                  ChainRec<MAXD> *states, int n, WaveLists wl) {
@@ -141,12 +159,8 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_begin(const __grid_con
         uint32_t tab[64];
         ChainState<MAXD> &cs = states[i].cs;     // phases touch a few sectors of the record: work in place
         Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
-        phase_begin(sc, rp, cs.sampleIdx, cs.st[cs.curIdx], cs.ch, rng, cs.ss);
+        kind = wave_begin_chain(sc, rp, cs, rng, i, wl);
         rng_close(rng, cs);
-        kind = cs.ss.kind;
-        const Path<MAXD> &p = cs.st[cs.curIdx].path;
-        sort_key_set(wl.small_, i, kind == STEP_LARGE ? -1 : class_key(p.camDepth, p.lgtDepth, kind == STEP_ISO ? 0 : 1));
-        sort_key_set(wl.curGrad, i, cs.ss.needCurGrad ? class_key(p.camDepth, p.lgtDepth, 0) : -1);
     }
     list_append(wl.large, wl.largeCount, active && kind == STEP_LARGE, i);
 }
@@ -184,23 +198,30 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_PROP_MINB) k_wave_propose
     sort_key_set(wl.propGrad, i, cs.ss.needPropGrad ? class_key(prop.sp.camDepth, prop.sp.lightDepth, 0) : -1);
 }
 
-template <int MAXD>
+// Phase 4 of iteration k and, when THEN_BEGIN, phase 0 of iteration k + 1 in the same pass over the records
+template <int MAXD, int THEN_BEGIN>
 __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_finish(const __grid_constant__ Scene sc, RunParams rp, int chainBase,
                                                                   ChainRec<MAXD> *states, int n, float *film, unsigned char *trace,
-                                                                  float *aTrace, long long numSteps, long long stepInLaunch, H2mcSide *sides) {
+                                                                  float *aTrace, long long numSteps, long long stepInLaunch, H2mcSide *sides,
+                                                                  WaveLists wl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t tab[64];
-    DevFilm df; df.p = film;
-    ChainState<MAXD> &cs = states[i].cs;
-    Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
-    const StepInfo info = phase_finish(sc, rp, chainBase + i, cs.sampleIdx, cs.st, cs.curIdx, cs.ch, rng, df, cs.ss, sides ? sides + i : nullptr);
-    rng_close(rng, cs);
-    cs.nPropose[info.mutationType] += 1u;
-    cs.nAccept[info.mutationType] += (unsigned int)info.accepted;
-    cs.sampleIdx += 1;
-    if (trace) trace[(size_t)i * numSteps + stepInLaunch] = (unsigned char)(info.mutationType | (info.accepted << 2) | ((info.a > 0.0f) ? 8 : 0));
-    if (aTrace) aTrace[(size_t)i * numSteps + stepInLaunch] = info.a;
+    const bool active = i < n;
+    int kind = -1;
+    if (active) {
+        uint32_t tab[64];
+        DevFilm df; df.p = film;
+        ChainState<MAXD> &cs = states[i].cs;
+        Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
+        const StepInfo info = phase_finish(sc, rp, chainBase + i, cs.sampleIdx, cs.st, cs.curIdx, cs.ch, rng, df, cs.ss, sides ? sides + i : nullptr);
+        cs.nPropose[info.mutationType] += 1u;
+        cs.nAccept[info.mutationType] += (unsigned int)info.accepted;
+        cs.sampleIdx += 1;
+        if (trace) trace[(size_t)i * numSteps + stepInLaunch] = (unsigned char)(info.mutationType | (info.accepted << 2) | ((info.a > 0.0f) ? 8 : 0));
+        if (aTrace) aTrace[(size_t)i * numSteps + stepInLaunch] = info.a;
+        if (THEN_BEGIN) kind = wave_begin_chain(sc, rp, cs, rng, i, wl);
+        rng_close(rng, cs);
+    }
+    if (THEN_BEGIN) list_append(wl.large, wl.largeCount, active && kind == STEP_LARGE, i);
 }
 
 // ---- per-vertex wavefront of the proposal phase ------------------------------------------------
@@ -524,15 +545,16 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
     const int GS = G < sms * LMC_SHADE_MINB ? G : sms * LMC_SHADE_MINB;     // grid-stride kernels: one resident wave of CTAs
     const int GT = G < sms * 16 ? G : sms * 16;
     const int maxDepth = sc.opt.maxDepth;
+    cudaError_t e = cudaMemsetAsync(wl.largeCount, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    k_wave_begin<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl);
+    *launches += 1;
     for (long long k = 0; k < numSteps; k++) {
-        cudaError_t e = cudaMemsetAsync(wl.largeCount, 0, sizeof(int), st);
-        if (e != cudaSuccess) return e;
-        k_wave_begin<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl);
         k_sort_scan<<<2, LMC_NKEYS, 0, st>>>(wl.small_, wl.curGrad, 2);
         k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.small_, wl.curGrad, 2);
         if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides);
         else k_wave_grad<MAXD, 1><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides);
-        *launches += 4;
+        *launches += 3;
         if (!wc.wavefront) {
             k_wave_propose<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.small_.list, wl.small_.count, wl, sides);
             k_wave_propose<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.large, wl.largeCount, wl, sides);
@@ -568,7 +590,11 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.propGrad, wl.propGrad, 1);
         if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides);
         else k_wave_grad<MAXD, 1><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides);
-        k_wave_finish<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides);
+        // the large-step list of this iteration is consumed: refill it for the next one in the fused finish + begin
+        e = cudaMemsetAsync(wl.largeCount, 0, sizeof(int), st);
+        if (e != cudaSuccess) return e;
+        if (k + 1 < numSteps) k_wave_finish<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides, wl);
+        else k_wave_finish<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides, wl);
         *launches += 4;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
