@@ -725,6 +725,21 @@ template <class T> LMC_HD_NOINLINE const float *ad_bsdf_sampling(bool adjoint, c
 
 // The path function: log(Luminance(contrib)) of a (camDepth, lightDepth) path.
 // primary: D+1 values (time first); `pss` carries primary[1..D] as T (seeded duals or floats).
+// Lockstep hook.  The evaluator is ~20 k straight-line instructions that a warp walks once per sweep, so
+// the device kernels are bound by instruction fetch, not by arithmetic.  Its control flow between the
+// marks below depends ONLY on (maxCamDepth, maxLightDepth): when every thread of a block evaluates the
+// same path class (cuda/chain_kernels.cuh builds class-pure blocks; k_eval_batch gets the class as a
+// kernel argument), a block-wide barrier at each mark keeps the block's warps inside one
+// instruction-cache window and the fetched code is shared instead of streamed per warp (measured:
+// gradient kernel 4.8 -> 2.9 ms per iteration of 2^20 chains).  Barriers change no arithmetic; the
+// host twin compiles them away.
+#if defined(__CUDA_ARCH__) && !defined(LMC_NO_GRAD_LOCKSTEP)
+#define LMC_VERTEX_SYNC() __syncthreads()
+#else
+#define LMC_VERTEX_SYNC() ((void)0)
+#endif
+#define LMC_VERTEX_SYNC2() LMC_VERTEX_SYNC()
+
 template <class T>
 LMC_HD_NOINLINE T eval_path_loglum(int maxCamDepth, int maxLightDepth, const float *sceneBuf, const float *vertParams, const T *pss) {
     const ADScene scn = ad_scene_deserialize(sceneBuf);
@@ -752,6 +767,7 @@ LMC_HD_NOINLINE T eval_path_loglum(int maxCamDepth, int maxLightDepth, const flo
             else lps.accMISWThis = ad_const<T>(0.0f);
         }
         for (int lgtDepth = 0; lgtDepth < maxLightDepth - 1; lgtDepth++) {
+            LMC_VERTEX_SYNC();
             buffer = ad_intersect(buffer, ray, lps.isect);
             const float bsdfDiscrete = *buffer++;
             const float useAbsoluteParam = *buffer++;
@@ -793,6 +809,7 @@ LMC_HD_NOINLINE T eval_path_loglum(int maxCamDepth, int maxLightDepth, const flo
             }
             const T r0 = pss[pi], r1 = pss[pi + 1];
             pi += 2;
+            LMC_VERTEX_SYNC2();
             buffer = ad_bsdf_sampling(true, buffer, r0, r1, bsdfDiscrete, useAbsoluteParam, lps, ray.dir);
             const float rrWeight = *buffer++;
             lps.throughput = tscalef(lps.throughput, rrWeight);
@@ -816,6 +833,7 @@ LMC_HD_NOINLINE T eval_path_loglum(int maxCamDepth, int maxLightDepth, const flo
             cps.accMISWThis = ad_const<T>(0.0f);
         }
         for (int camDepth = 0; camDepth < maxCamDepth - 1; camDepth++) {
+            LMC_VERTEX_SYNC();
             buffer = ad_intersect(buffer, ray, cps.isect);
             cps.wi = -ray.dir;
             if (camDepth == maxCamDepth - 2 && maxLightDepth == 0) {
@@ -843,6 +861,7 @@ LMC_HD_NOINLINE T eval_path_loglum(int maxCamDepth, int maxLightDepth, const flo
             }
             ad_convert_mis(ray, cps);
             if (camDepth == maxCamDepth - 2) {
+                LMC_VERTEX_SYNC2();
                 if (maxLightDepth == 1) {   // DirectLighting
                     const T r0 = pss[pi], r1 = pss[pi + 1];
                     pi += 2;
@@ -892,6 +911,7 @@ LMC_HD_NOINLINE T eval_path_loglum(int maxCamDepth, int maxLightDepth, const flo
             pi += 2;
             const float bsdfDiscrete = *buffer++;
             const float useAbsoluteParam = *buffer++;
+            LMC_VERTEX_SYNC2();
             buffer = ad_bsdf_sampling(false, buffer, r0, r1, bsdfDiscrete, useAbsoluteParam, cps, ray.dir);
             const float rrWeight = *buffer++;
             cps.throughput = tscalef(cps.throughput, rrWeight);

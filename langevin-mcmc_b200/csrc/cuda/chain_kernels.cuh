@@ -68,6 +68,7 @@ struct SortList {
     int *count;     // 1
 };
 struct WaveLists {
+    int listLen;                 // capacity of every sorted list: n + room for class-alignment gaps
     SortList small_, curGrad, propGrad;
     int *large, *largeCount;     // unsorted
 };
@@ -91,9 +92,12 @@ __device__ __forceinline__ int class_key(int camDepth, int lgtDepth, int kindBit
     return k < LMC_NKEYS ? k : LMC_NKEYS - 1;
 }
 
-// 1 block: exclusive scan of up to 3 histograms; clears hist + cursor for the next use
-static __global__ void k_sort_scan(SortList a, SortList b, int nb) {
+// 1 block per list: exclusive scan of the class histogram; clears hist + cursor for the next use.
+// align > 1 starts every class at a multiple of `align` (class-pure thread blocks for the gradient
+// kernel); the gaps keep the -1 the list was pre-filled with, and *count is the padded length.
+static __global__ void k_sort_scan(SortList a, SortList b, int nb, int alignA, int alignB) {
     SortList sl = (blockIdx.x == 0) ? a : b;
+    const int align = (blockIdx.x == 0) ? alignA : alignB;
     if ((int)blockIdx.x >= nb) return;
     __shared__ int sh[LMC_NKEYS];
     const int t = threadIdx.x;
@@ -101,7 +105,12 @@ static __global__ void k_sort_scan(SortList a, SortList b, int nb) {
     __syncthreads();
     if (t == 0) {
         int acc = 0;
-        for (int k = 0; k < LMC_NKEYS; k++) { const int c = sh[k]; sh[k] = acc; acc += c; }
+        for (int k = 0; k < LMC_NKEYS; k++) {
+            const int c = sh[k];
+            if (c > 0 && align > 1) acc = (acc + align - 1) / align * align;
+            sh[k] = acc; acc += c;
+        }
+        if (align > 1) acc = (acc + align - 1) / align * align;
         *sl.count = acc;
     }
     __syncthreads();
@@ -172,13 +181,28 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_begin(const __grid_con
 #ifndef LMC_PROP_MINB
 #define LMC_PROP_MINB 4
 #endif
+#ifndef LMC_GRAD_BLOCK
+#define LMC_GRAD_BLOCK 256
+#endif
+// The gradient lists are class-aligned to LMC_GRAD_BLOCK (k_sort_scan), so every block evaluates paths
+// of ONE (camDepth, lightDepth) class: the evaluator's vertex loops have the same trip counts in all of
+// its threads, which is what the barriers of core/pathgrad.h (LMC_VERTEX_SYNC) require.  Padding
+// entries (-1) redo the block's first chain into scratch so that they take part in every barrier.
 template <int MAXD, int ORDER>
-__global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_GRAD_MINB) k_wave_grad(const __grid_constant__ Scene sc, ChainRec<MAXD> *states, int n,
-                                                                const int *list, const int *count, int which, H2mcSide *sides) {
+__global__ void __launch_bounds__(LMC_GRAD_BLOCK, (LMC_GRAD_MINB * 128) / LMC_GRAD_BLOCK) k_wave_grad(const __grid_constant__ Scene sc, ChainRec<MAXD> *states, int n,
+                                                                const int *list, const int *count, int which, H2mcSide *sides,
+                                                                H2mcSide *padSide) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= *count) return;
-    const int i = list[t];
+    if (t >= *count) return;                    // *count is a multiple of the block size: whole blocks leave
+    int i = list[t];
+    const bool pad = i < 0;
+    if (pad) i = list[blockIdx.x * blockDim.x]; // class segments start on block boundaries and are filled from the front
     ChainState<MAXD> &cs = states[i].cs;
+    if (pad) {
+        StepScratch<MAXD> scratch; scratch.kind = cs.ss.kind;
+        phase_gradient<MAXD, ORDER>(sc, cs.st[cs.curIdx ^ which], scratch, nullptr, padSide);
+        return;
+    }
     phase_gradient<MAXD, ORDER>(sc, cs.st[cs.curIdx ^ which], cs.ss, cs.gradStats, sides ? sides + i : nullptr);
 }
 
@@ -195,7 +219,7 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_PROP_MINB) k_wave_propose
     phase_propose<MAXD, ONLY>(sc, rp, cs.st[cs.curIdx], cs.st[cs.curIdx ^ 1], cs.ch, rng, cs.ss, sides ? sides + i : nullptr, cs.curIdx);
     rng_close(rng, cs);
     const MarkovState<MAXD> &prop = cs.st[cs.curIdx ^ 1];
-    sort_key_set(wl.propGrad, i, cs.ss.needPropGrad ? class_key(prop.sp.camDepth, prop.sp.lightDepth, 0) : -1);
+    sort_key_set(wl.propGrad, i, cs.ss.needPropGrad ? class_key(prop.path.camDepth, prop.path.lgtDepth, 0) : -1);
 }
 
 // Phase 4 of iteration k and, when THEN_BEGIN, phase 0 of iteration k + 1 in the same pass over the records
@@ -490,7 +514,8 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_prop_post(const __grid_cons
             cs.pc.n = deferred_compact(cs.pc.c, cs.pc.flag, cs.pc.n);
             propose_post_small(sc, rp, cur, prop, cs.ss, cs.pc);
         }
-        sort_key_set(wl.propGrad, i, cs.ss.needPropGrad ? class_key(prop.sp.camDepth, prop.sp.lightDepth, 0) : -1);
+        // key = the class the evaluator will see (path.camDepth / path.lgtDepth): blocks must be class-pure
+        sort_key_set(wl.propGrad, i, cs.ss.needPropGrad ? class_key(prop.path.camDepth, prop.path.lgtDepth, 0) : -1);
     }
 }
 
@@ -517,6 +542,7 @@ struct WaveCfg {
     WaveQueues wq;
     void *genWork;
     int *queueCounts;      // 2 x 4 ray-queue counters + the shadow counter (contiguous)
+    H2mcSide *padSide;     // scratch Hessian for the padding threads of the H2MC gradient kernel
     int wavefront;         // 1: per-vertex wavefront proposal; 0: monolithic k_wave_propose (A/B)
     int smCount;
 };
@@ -545,15 +571,21 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
     const int GS = G < sms * LMC_SHADE_MINB ? G : sms * LMC_SHADE_MINB;     // grid-stride kernels: one resident wave of CTAs
     const int GT = G < sms * 16 ? G : sms * 16;
     const int maxDepth = sc.opt.maxDepth;
+    const int GALIGN = LMC_GRAD_BLOCK;          // gradient lists: class-pure blocks
+    const int GG = (n + LMC_NKEYS * (GALIGN - 1) + LMC_GRAD_BLOCK - 1) / LMC_GRAD_BLOCK;   // gradient grid over the (padded) list
     cudaError_t e = cudaMemsetAsync(wl.largeCount, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     k_wave_begin<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl);
     *launches += 1;
     for (long long k = 0; k < numSteps; k++) {
-        k_sort_scan<<<2, LMC_NKEYS, 0, st>>>(wl.small_, wl.curGrad, 2);
+        k_sort_scan<<<2, LMC_NKEYS, 0, st>>>(wl.small_, wl.curGrad, 2, 1, GALIGN);
+        if (GALIGN > 1) {
+            e = cudaMemsetAsync(wl.curGrad.list, 0xFF, sizeof(int) * (size_t)wl.listLen, st);
+            if (e != cudaSuccess) return e;
+        }
         k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.small_, wl.curGrad, 2);
-        if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides);
-        else k_wave_grad<MAXD, 1><<<G, B, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides);
+        if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide);
+        else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide);
         *launches += 3;
         if (!wc.wavefront) {
             k_wave_propose<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.small_.list, wl.small_.count, wl, sides);
@@ -586,10 +618,14 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             k_prop_post<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.large, wl.largeCount, wl);
             *launches += 3;
         }
-        k_sort_scan<<<1, LMC_NKEYS, 0, st>>>(wl.propGrad, wl.propGrad, 1);
+        k_sort_scan<<<1, LMC_NKEYS, 0, st>>>(wl.propGrad, wl.propGrad, 1, GALIGN, GALIGN);
+        if (GALIGN > 1) {
+            e = cudaMemsetAsync(wl.propGrad.list, 0xFF, sizeof(int) * (size_t)wl.listLen, st);
+            if (e != cudaSuccess) return e;
+        }
         k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.propGrad, wl.propGrad, 1);
-        if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides);
-        else k_wave_grad<MAXD, 1><<<G, B, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides);
+        if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide);
+        else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide);
         // the large-step list of this iteration is consumed: refill it for the next one in the fused finish + begin
         e = cudaMemsetAsync(wl.largeCount, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;

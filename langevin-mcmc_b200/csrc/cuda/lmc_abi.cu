@@ -110,7 +110,9 @@ int chains_begin(lmc_ctx *c) {
     if (c->listCap < n) {
         if (c->listMem) { cudaFree(c->listMem); c->listMem = nullptr; }
         // per sorted list: keys[n] + list[n] + hist/offsets/cursor[NKEYS] + count; plus the large list
-        const size_t per = (size_t)n * 2 + 3 * LMC_NKEYS + 4;
+        const size_t listLen = (size_t)n + (size_t)LMC_NKEYS * 256;      // + class-alignment gaps (k_sort_scan)
+        c->wl.listLen = (int)listLen;
+        const size_t per = (size_t)n + listLen + 3 * LMC_NKEYS + 4;
         const size_t total = per * 3 + (size_t)n + 4;
         CK(cudaMalloc((void **)&c->listMem, sizeof(int) * total));
         CK(cudaMemsetAsync(c->listMem, 0, sizeof(int) * total, c->stream));
@@ -118,7 +120,7 @@ int chains_begin(lmc_ctx *c) {
         SortList *sls[3] = {&c->wl.small_, &c->wl.curGrad, &c->wl.propGrad};
         for (int k = 0; k < 3; k++) {
             SortList &sl = *sls[k];
-            sl.keys = p; p += n; sl.list = p; p += n; sl.hist = p; p += LMC_NKEYS; sl.offsets = p; p += LMC_NKEYS;
+            sl.keys = p; p += n; sl.list = p; p += listLen; sl.hist = p; p += LMC_NKEYS; sl.offsets = p; p += LMC_NKEYS;
             sl.cursor = p; p += LMC_NKEYS; sl.count = p; p += 4;
         }
         c->wl.large = p; p += n; c->wl.largeCount = p;
@@ -163,6 +165,7 @@ int chains_begin(lmc_ctx *c) {
             c->sidesCap = n;
         }
         CK(cudaMemsetAsync(c->sides, 0, sizeof(H2mcSide) * (size_t)n, c->stream));
+        if (!c->wc.padSide) { CK(cudaMalloc((void **)&c->wc.padSide, sizeof(H2mcSide))); CK(cudaMemsetAsync(c->wc.padSide, 0, sizeof(H2mcSide), c->stream)); }
     }
     c->launches++;
     CK(d == 4 ? launch_chain_init_4(c->stream, st, n, c->desc.chain_base, c->initLs)
@@ -272,6 +275,7 @@ int lmc_create(const lmc_scene *scene, int32_t device, lmc_ctx **out) {
     const lmc_host::SceneStore &s = scene->store;
     if (s.head.opt.maxDepth < 2 || s.head.opt.maxDepth > 12) return fail(LMC_ERR_UNSUPPORTED, "maxdepth must be in [2, 12]");
     if (s.head.opt.h2mc && s.head.opt.maxDepth > 8) return fail(LMC_ERR_UNSUPPORTED, "h2mc needs maxdepth <= 8 (dense Gaussians are stored for dim <= 16)");
+    if (s.head.opt.maxDervDepth > 8) return fail(LMC_ERR_UNSUPPORTED, "maxdervdepth must be <= 8 (derivative functions exist for camDepth + lightDepth - 1 <= 8)");
     if (s.head.opt.largeStepMultiplexed) return fail(LMC_ERR_UNSUPPORTED, "largestepmultiplexed is not supported");
     lmc_ctx *c = new lmc_ctx();
     c->device = device;
@@ -316,6 +320,7 @@ void lmc_destroy(lmc_ctx *c) {
     if (c->sides) cudaFree(c->sides);
     if (c->queueMem) cudaFree(c->queueMem);
     if (c->wc.genWork) cudaFree(c->wc.genWork);
+    if (c->wc.padSide) cudaFree(c->wc.padSide);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
