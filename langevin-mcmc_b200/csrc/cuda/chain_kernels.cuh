@@ -6,6 +6,7 @@
 #include <cstddef>
 #include <cstdint>
 #include "../core/chain.h"
+#include "trace_kernels.cuh"
 
 namespace lmc_cuda {
 using namespace lmc;
@@ -461,35 +462,67 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_SHADE_MINB) k_shade(const
     }
 }
 
-// closest hit for the four ray queues of a wave; the ray sits in payload words 6..13
-static __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ Scene sc, WaveQueues wq, int curSet) {
-    const int c0 = *wq.q[curSet][0].count, c1 = c0 + *wq.q[curSet][1].count, c2 = c1 + *wq.q[curSet][2].count,
-              c3 = c2 + *wq.q[curSet][3].count;
-    const int stride = gridDim.x * blockDim.x;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < c3; idx += stride) {
-        const int k = (idx >= c0) + (idx >= c1) + (idx >= c2);
+// closest hit for the four ray queues of a wave (persistent warps, trace_kernels.cuh); the ray sits in
+// payload words 6..13
+struct ClosestSrc {
+    const RayQueue *q;     // the 4 queues of the set
+    int c0, c1, c2, c3;    // running totals of their counts
+    __device__ __forceinline__ int total() const { return c3; }
+    __device__ __forceinline__ void locate(int idx, int &k, int &slot) const {
+        k = (idx >= c0) + (idx >= c1) + (idx >= c2);
         const int pos = idx - (k == 0 ? 0 : (k == 1 ? c0 : (k == 2 ? c1 : c2)));
-        const RayQueue &q = wq.q[curSet][k];
-        const int slot = q.base + q.dirn * pos;
-        const uint4 a = q.payload[(size_t)1 * q.cap + slot], b = q.payload[(size_t)2 * q.cap + slot], c = q.payload[(size_t)3 * q.cap + slot];
-        Ray ray;
+        slot = q[k].base + q[k].dirn * pos;
+    }
+    __device__ __forceinline__ void load(int idx, Ray &ray, float &minT, float &maxT) const {
+        int k, slot; locate(idx, k, slot);
+        const RayQueue &qq = q[k];
+        const uint4 a = qq.payload[(size_t)1 * qq.cap + slot], b = qq.payload[(size_t)2 * qq.cap + slot], c = qq.payload[(size_t)3 * qq.cap + slot];
         ray.org = mk3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z));
         ray.dir = mk3(__uint_as_float(b.w), __uint_as_float(c.x), __uint_as_float(c.y));
-        const Hit h = bvh_traverse<false>(sc, ray, __uint_as_float(a.z), __uint_as_float(a.w));
-        q.hit[slot] = make_float4(__int_as_float(h.tid), h.t, h.u, h.v);
+        minT = __uint_as_float(a.z); maxT = __uint_as_float(a.w);
     }
-}
-// any hit for the queued connection segments
-static __global__ void __launch_bounds__(128) k_shadow(const __grid_constant__ Scene sc, ShadowQueue sh) {
-    int n = *sh.count; if (n > sh.cap) n = sh.cap;
-    const int stride = gridDim.x * blockDim.x;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+    __device__ __forceinline__ void store(int idx, const Hit &h) const {
+        int k, slot; locate(idx, k, slot);
+        q[k].hit[slot] = make_float4(__int_as_float(h.tid), h.t, h.u, h.v);
+    }
+};
+// any hit for the queued connection segments: Occluded(scene, ray, dist), src/scene.cpp:128-149
+struct ShadowSrc {
+    ShadowQueue sh; int n;
+    __device__ __forceinline__ int total() const { return n; }
+    __device__ __forceinline__ void load(int idx, Ray &ray, float &minT, float &maxT) const {
         const float4 o = sh.org[idx], d = sh.dir[idx];
-        Ray ray; ray.org = mk3(o.x, o.y, o.z); ray.dir = mk3(d.x, d.y, d.z);
-        const bool occ = scene_occluded(sc, ray, o.w);
-        int *f = sh.flag[idx];
-        *f = cand_resolve(*f, occ);
+        ray.org = mk3(o.x, o.y, o.z); ray.dir = mk3(d.x, d.y, d.z);
+        minT = LMC_ISECT_EPS;
+        maxT = (o.w == dm_inf()) ? dm_inf() : (1.0f - LMC_SHADOW_EPS) * o.w;
     }
+    __device__ __forceinline__ void store(int idx, const Hit &h) const {
+        int *f = sh.flag[idx];
+        *f = cand_resolve(*f, h.tid >= 0);
+    }
+};
+#ifndef LMC_TRACE_MINB
+#define LMC_TRACE_MINB 6
+#endif
+static __global__ void __launch_bounds__(LMC_TRACE_BLOCK, LMC_TRACE_MINB) k_trace(const __grid_constant__ Scene sc, WaveQueues wq, int curSet, int *cursor) {
+    __shared__ __align__(128) BvhNode top[LMC_TOP_NODES];
+    __shared__ uint64_t bar;
+    const int topCount = sc.numNodes < LMC_TOP_NODES ? sc.numNodes : LMC_TOP_NODES;
+    ClosestSrc src; src.q = wq.q[curSet];
+    src.c0 = *wq.q[curSet][0].count; src.c1 = src.c0 + *wq.q[curSet][1].count; src.c2 = src.c1 + *wq.q[curSet][2].count;
+    src.c3 = src.c2 + *wq.q[curSet][3].count;
+    if ((long long)blockIdx.x * LMC_TRACE_BLOCK >= (long long)src.c3) return;     // more blocks than rays: leave before staging
+    tma_stage_nodes(top, sc.nodes, topCount, &bar);
+    trace_persistent<false>(sc, top, topCount, src, cursor);
+}
+static __global__ void __launch_bounds__(LMC_TRACE_BLOCK, LMC_TRACE_MINB) k_shadow(const __grid_constant__ Scene sc, ShadowQueue sh, int *cursor) {
+    __shared__ __align__(128) BvhNode top[LMC_TOP_NODES];
+    __shared__ uint64_t bar;
+    const int topCount = sc.numNodes < LMC_TOP_NODES ? sc.numNodes : LMC_TOP_NODES;
+    ShadowSrc src; src.sh = sh; src.n = *sh.count; if (src.n > sh.cap) src.n = sh.cap;
+    if ((long long)blockIdx.x * LMC_TRACE_BLOCK >= (long long)src.n) return;
+    tma_stage_nodes(top, sc.nodes, topCount, &bar);
+    trace_persistent<true>(sc, top, topCount, src, cursor);
 }
 
 // POST part of the mutation once every candidate is resolved
@@ -538,10 +571,11 @@ __global__ void k_chain_stats(const ChainRec<MAXD> *states, int n, unsigned long
 
 
 // launchers (defined by LMC_INSTANTIATE_CHAIN in chain_inst_*.cu)
+#define LMC_NCOUNTERS 80        // 9 counters + up to 64 wave cursors (maxdepth <= 12: 23 waves + shadow)
 struct WaveCfg {
     WaveQueues wq;
     void *genWork;
-    int *queueCounts;      // 2 x 4 ray-queue counters + the shadow counter (contiguous)
+    int *queueCounts;      // 2 x 4 ray-queue counters, the shadow counter, then one traversal cursor per wave (LMC_NCOUNTERS ints)
     H2mcSide *padSide;     // scratch Hessian for the padding threads of the H2MC gradient kernel
     int wavefront;         // 1: per-vertex wavefront proposal; 0: monolithic k_wave_propose (A/B)
     int smCount;
@@ -569,7 +603,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
     const int B = LMC_CHAIN_BLOCK, G = (n + B - 1) / B;
     const int sms = wc.smCount > 0 ? wc.smCount : 148;
     const int GS = G < sms * LMC_SHADE_MINB ? G : sms * LMC_SHADE_MINB;     // grid-stride kernels: one resident wave of CTAs
-    const int GT = G < sms * 16 ? G : sms * 16;
+    const int GT = G < sms * LMC_TRACE_MINB ? G : sms * LMC_TRACE_MINB;     // persistent traversal warps
     const int maxDepth = sc.opt.maxDepth;
     const int GALIGN = LMC_GRAD_BLOCK;          // gradient lists: class-pure blocks
     const int GG = (n + LMC_NKEYS * (GALIGN - 1) + LMC_GRAD_BLOCK - 1) / LMC_GRAD_BLOCK;   // gradient grid over the (padded) list
@@ -592,7 +626,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             k_wave_propose<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.large, wl.largeCount, wl, sides);
             *launches += 2;
         } else {
-            e = cudaMemsetAsync(wc.queueCounts, 0, 9 * sizeof(int), st);
+            e = cudaMemsetAsync(wc.queueCounts, 0, LMC_NCOUNTERS * sizeof(int), st);
             if (e != cudaSuccess) return e;
             k_prop_start<MAXD, 0><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wl.small_.list, wl.small_.count, wc.wq, sides);
             k_prop_start<MAXD, 1><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wl.large, wl.largeCount, wc.wq, sides);
@@ -601,7 +635,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             const int numWaves = 2 * maxDepth - 1;
             for (int w = 0; w < numWaves; w++) {
                 const int cur = w & 1;
-                k_trace<<<GT, 128, 0, st>>>(sc, wc.wq, cur);
+                k_trace<<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, wc.wq, cur, wc.queueCounts + 16 + w);
                 if (w < maxDepth - 1) {
                     k_shade<MAXD, TS_P_LGT><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
                     k_shade<MAXD, TS_G_LGT><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
@@ -613,7 +647,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
                 e = cudaMemsetAsync(wc.queueCounts + 4 * cur, 0, 4 * sizeof(int), st);
                 if (e != cudaSuccess) return e;
             }
-            k_shadow<<<GT, 128, 0, st>>>(sc, wc.wq.sh);
+            k_shadow<<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, wc.wq.sh, wc.queueCounts + 16 + 63);
             k_prop_post<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.small_.list, wl.small_.count, wl);
             k_prop_post<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.large, wl.largeCount, wl);
             *launches += 3;

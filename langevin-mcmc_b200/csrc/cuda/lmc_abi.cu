@@ -133,7 +133,7 @@ int chains_begin(lmc_ctx *c) {
         // camera-subpath queue of that kind; a shadow queue of 4n segments; 9 counters
         const size_t nn = (size_t)n, shCap = 4 * nn;
         const size_t perBuf = nn * (sizeof(int) + sizeof(Payload) + sizeof(float4)) + 64;
-        const size_t bytes = 4 * perBuf + shCap * (2 * sizeof(float4) + sizeof(int *)) + 256;
+        const size_t bytes = 4 * perBuf + shCap * (2 * sizeof(float4) + sizeof(int *)) + 1024;
         CK(cudaMalloc(&c->queueMem, bytes));
         char *p = (char *)c->queueMem;
         auto take = [&](size_t b) { char *r = p; p += (b + 15) & ~(size_t)15; return r; };
@@ -149,11 +149,11 @@ int chains_begin(lmc_ctx *c) {
         }
         c->wc.wq.sh.org = (float4 *)take(shCap * sizeof(float4)); c->wc.wq.sh.dir = (float4 *)take(shCap * sizeof(float4));
         c->wc.wq.sh.flag = (int **)take(shCap * sizeof(int *));
-        c->wc.queueCounts = (int *)take(16 * sizeof(int));
+        c->wc.queueCounts = (int *)take(LMC_NCOUNTERS * sizeof(int));
         for (int s = 0; s < 2; s++) for (int k = 0; k < 4; k++) c->wc.wq.q[s][k].count = c->wc.queueCounts + 4 * s + k;
         c->wc.wq.sh.count = c->wc.queueCounts + 8;
         c->wc.wq.sh.cap = (int)shCap;
-        CK(cudaMemsetAsync(c->wc.queueCounts, 0, 16 * sizeof(int), c->stream));
+        CK(cudaMemsetAsync(c->wc.queueCounts, 0, LMC_NCOUNTERS * sizeof(int), c->stream));
         const size_t gwBytes = (d == 4 ? gen_work_bytes_4() : (d == 8 ? gen_work_bytes_8() : gen_work_bytes_12())) * nn;
         CK(cudaMalloc(&c->wc.genWork, gwBytes));
         c->queueCap = n;

@@ -893,6 +893,27 @@ void load_scene_xml(const std::string &xmlPath, SceneStore &out) {
         // an empty right box never passes box_test
         B.nodes.push_back(nd);
     }
+    // Breadth-first node order: the first K nodes are the top levels of the tree (the traversal kernels
+    // stage them in shared memory); child indices are remapped, triangle order (= tid) is untouched.
+    {
+        std::vector<int> bfs; bfs.reserve(B.nodes.size());
+        std::vector<int> newIdx(B.nodes.size(), -1);
+        bfs.push_back(root < 0 ? 0 : root);
+        for (size_t head = 0; head < bfs.size(); head++) {
+            const BvhNode &nd = B.nodes[bfs[head]];
+            newIdx[bfs[head]] = (int)head;
+            if (nd.left >= 0) bfs.push_back(nd.left);
+            if (nd.right >= 0 && nd.right != nd.left) bfs.push_back(nd.right);
+        }
+        std::vector<BvhNode> re(bfs.size());
+        for (size_t k = 0; k < bfs.size(); k++) {
+            BvhNode nd = B.nodes[bfs[k]];
+            if (nd.left >= 0) nd.left = newIdx[nd.left];
+            if (nd.right >= 0) nd.right = newIdx[nd.right];
+            re[k] = nd;
+        }
+        B.nodes.swap(re);
+    }
     out.nodes = B.nodes;
     const int nt = (int)B.order.size();
     out.tris.resize(nt); out.shade.resize(nt);
