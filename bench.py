@@ -13,7 +13,8 @@ MUTATIONS_PER_STEP iterations of the loop at src/mlt.cpp:91-170 (one `lmc_run_ch
 Timed region (device arm): K steps bracketed by barrier + cuda synchronize, CUDA events on the
 launching stream, max over ranks; it includes the final NCCL all-reduce of the fp32 film
 (src/mlt.cpp:57->200 is the span the metric is defined on; MLTInit, scene load, BVH build are
-setup).  Chain state (4.4 KB/chain x 2^20 = 4.6 GB) is far larger than L2, so no explicit flush.
+setup).  Chain records + wavefront queues (4.5 KB + 1.4 KB per chain, x 2^20 = 6 GB) are far larger
+than L2, so no explicit flush.
 """
 import argparse
 import ctypes
@@ -35,9 +36,9 @@ CHAINS_PER_GPU = 1 << 20
 MUTATIONS_PER_STEP = 32
 # canonical state words S_LMC(L) = 14 L + 21; bytes per mutation = 8 S + 48
 ALGO_BYTES_PER_MUTATION = 8 * (14 * MAXDEPTH + 21) + 48   # 1112 B at L = 8
-# dram__bytes_read.sum + dram__bytes_write.sum of the 10 kernels of one iteration over 2^20 chains
-# (ncu, profiles/r01_launches_wavefront_2p20.csv): 10.79 GB / 2^20 mutations
-DRAM_BYTES_PER_MUTATION_NCU = 10.79e9 / (1 << 20)
+# dram__bytes_read.sum + dram__bytes_write.sum of the ~75 kernels of one iteration over 2^20 chains
+# (ncu, profiles/r01_launches_pervertex_2p20.csv / _summary.txt): 13.67 GB / 2^20 mutations
+DRAM_BYTES_PER_MUTATION_NCU = 13.67e9 / (1 << 20)
 
 
 def load_package():
@@ -258,7 +259,7 @@ def main():
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "bundled torus scene (scenes/torus), chains seeded by MLTInit, PCG seeds = chain ids",
                 "config": {"workload": "torus, LMC (mala), maxdepth 8, 2^20 chains per GPU, global cache off",
-                           "chains_per_gpu": n_local, "mutations_per_step": M, "l2": "inputs larger than L2 (4.6 GB chain state)",
+                           "chains_per_gpu": n_local, "mutations_per_step": M, "l2": "inputs larger than L2 (6 GB of chain records + wavefront queues)",
                            "setup_s": round(setup_s, 2), "film_allreduce": world > 1},
                 "e2e": {"value": e2e_value, "unit": "mutations/s", "h2d_bytes_per_step": int(4 * total),
                         "d2h_bytes_per_step": int(film_bytes), "steps": e2e_steps},
@@ -266,7 +267,8 @@ def main():
                 "clocks": sampler.result(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": DRAM_BYTES_PER_MUTATION_NCU * float(n_local) * M,
-                             "kernel": "chain iteration = k_wave_{begin,grad,propose,finish}<8> (one lmc_run_chains call)",
+                             "kernel": "one lmc_run_chains call = M chain-loop iterations of ~75 launches each (k_wave_grad, k_trace, "
+                                       "k_shade<P_CAM/G_CAM>, k_wave_finish+begin ...; shares in profiles/r01_launches_pervertex_2p20_summary.txt)",
                              "algorithmic_bytes_per_mutation": ALGO_BYTES_PER_MUTATION,
                              "kernel_ms_per_launch": k_ms, "peak_source": peak_src,
                              "per_gpu_mutations_per_s": per_gpu_rate},
