@@ -343,14 +343,17 @@ __device__ __forceinline__ void rng_to_payload(const Rng &rng, TraceState &ts) {
     ts.rngLo = (uint32_t)rng.state; ts.rngHi = (uint32_t)(rng.state >> 32); ts.rngEpoch = rng.epoch;
 }
 
+#ifndef LMC_SHADE_BLOCK
+#define LMC_SHADE_BLOCK 256        // 2 blocks of 8 warps per SM; the warps of a block re-align at every queue item
+#endif
 #ifndef LMC_SHADE_MINB
-#define LMC_SHADE_MINB 4
+#define LMC_SHADE_MINB 2
 #endif
 template <int MAXD> struct GenWorkT { typedef GenWork<MAXD, Limits<MAXD>::MAXC> type; };
 
 // first stage of every proposal: PRE part of the mutation + the statements up to the first ray
 template <int MAXD, int LARGE>
-__global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_SHADE_MINB) k_prop_start(const __grid_constant__ Scene sc, int chainBase, ChainRec<MAXD> *states,
+__global__ void __launch_bounds__(LMC_SHADE_BLOCK, LMC_SHADE_MINB) k_prop_start(const __grid_constant__ Scene sc, int chainBase, ChainRec<MAXD> *states,
                                                                  typename GenWorkT<MAXD>::type *genWork, const int *list, const int *countp,
                                                                  WaveQueues wq, H2mcSide *sides) {
     const int count = *countp;
@@ -393,14 +396,62 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_SHADE_MINB) k_prop_start(
     }
 }
 
+// One stage of one proposal: the statements between two ray queries for the chain `i` whose pending ray
+// of stage STAGE was answered with `hit`.  Returns true when the proposal wants another ray (p.ts.stage
+// tells of which kind); on false it has left the wavefront and its head / RNG state are back in the record.
 template <int MAXD, int STAGE>
-__global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_SHADE_MINB) k_shade(const __grid_constant__ Scene sc, int chainBase, ChainRec<MAXD> *states,
+__device__ __forceinline__ bool shade_entry(const Scene &sc, int chainBase, ChainRec<MAXD> *states, typename GenWorkT<MAXD>::type *genWork,
+                                            const WaveQueues &wq, int i, Payload &p, const Hit &hit) {
+    ChainState<MAXD> &cs = states[i].cs;
+    MarkovState<MAXD> &cur = cs.st[p.ts.curIdx], &prop = cs.st[p.ts.curIdx ^ 1];
+    uint32_t tab[64];
+    Rng rng; rng_from_payload(rng, tab, sc, chainBase + i, p.ts);
+    DevShadowSink sink; sink.sh = wq.sh; sink.sc = &sc;
+    DeferredList<DevShadowSink> dl;
+    SurfaceVertex sv;
+    bool more;
+    if (STAGE == TS_P_LGT || STAGE == TS_P_CAM) {
+        OffPair off; off.base = p.ts.offsetId;
+        off.v0 = cs.ss.offset[off.base]; off.v1 = cs.ss.offset[off.base + 1];
+        dl.bind(cs.pc.c, cs.pc.flag, &cs.pc.n, 2, &sink);
+        const int d = p.ts.depth;
+        if (STAGE == TS_P_LGT) {
+            copy_u4<SurfaceVertex>(sv, cur.path.lgt[d]);
+            more = perturb_stage_light(sc, off, p.ph, sv, p.ts, dl, rng, hit);
+            copy_u4<SurfaceVertex>(prop.path.lgt[d], sv);
+        } else {
+            copy_u4<SurfaceVertex>(sv, cur.path.cam[d]);
+            more = perturb_stage_camera(sc, off, p.ph, sv, prop.path.lgt, p.ts, dl, rng, hit);
+            copy_u4<SurfaceVertex>(prop.path.cam[d], sv);
+        }
+    } else {
+        typename GenWorkT<MAXD>::type &gw = genWork[i];
+        dl.bind(gw.c, gw.flag, &gw.n, Limits<MAXD>::MAXC, &sink);
+        const int minDepth = sc.opt.minDepth > 3 ? sc.opt.minDepth : 3;
+        if (STAGE == TS_G_LGT) {
+            const int d = p.ph.nLgt;
+            more = gen_stage_light(sc, minDepth, sc.opt.maxDepth, p.ph, sv, p.ts, gw.ls, dl, rng, hit);
+            copy_u4<SurfaceVertex>(prop.path.lgt[d], sv);
+        } else {
+            const int d = p.ph.nCam;
+            more = gen_stage_camera(sc, minDepth, sc.opt.maxDepth, p.ph, sv, prop.path.lgt, p.ts, gw.ls, dl, rng, hit);
+            copy_u4<SurfaceVertex>(prop.path.cam[d], sv);
+        }
+    }
+    rng_to_payload(rng, p.ts);
+    if (!more) { copy_u4<PathHead>(prop.path, p.ph); rng_close(rng, cs); }   // leaving the wavefront
+    return more;
+}
+
+template <int MAXD, int STAGE>
+__global__ void __launch_bounds__(LMC_SHADE_BLOCK, LMC_SHADE_MINB) k_shade(const __grid_constant__ Scene sc, int chainBase, ChainRec<MAXD> *states,
                                                             typename GenWorkT<MAXD>::type *genWork, WaveQueues wq, int curSet) {
     const RayQueue &qi = wq.q[curSet][STAGE - 1];
     const int count = *qi.count;
     const int stride = gridDim.x * blockDim.x;
     const int nextSet = curSet ^ 1;
     for (int base = blockIdx.x * blockDim.x; base < count; base += stride) {
+        __syncthreads();          // keep the block's warps in the same stretch of code (instruction fetch)
         const int t = base + threadIdx.x;
         bool more = false; int i = -1;
         Payload p;
@@ -410,43 +461,7 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_SHADE_MINB) k_shade(const
             payload_load(qi, slot, p);
             const float4 h4 = qi.hit[slot];
             Hit hit; hit.tid = __float_as_int(h4.x); hit.t = h4.y; hit.u = h4.z; hit.v = h4.w;
-            ChainState<MAXD> &cs = states[i].cs;
-            MarkovState<MAXD> &cur = cs.st[p.ts.curIdx], &prop = cs.st[p.ts.curIdx ^ 1];
-            uint32_t tab[64];
-            Rng rng; rng_from_payload(rng, tab, sc, chainBase + i, p.ts);
-            DevShadowSink sink; sink.sh = wq.sh; sink.sc = &sc;
-            DeferredList<DevShadowSink> dl;
-            SurfaceVertex sv;
-            if (STAGE == TS_P_LGT || STAGE == TS_P_CAM) {
-                OffPair off; off.base = p.ts.offsetId;
-                off.v0 = cs.ss.offset[off.base]; off.v1 = cs.ss.offset[off.base + 1];
-                dl.bind(cs.pc.c, cs.pc.flag, &cs.pc.n, 2, &sink);
-                const int d = p.ts.depth;
-                if (STAGE == TS_P_LGT) {
-                    copy_u4<SurfaceVertex>(sv, cur.path.lgt[d]);
-                    more = perturb_stage_light(sc, off, p.ph, sv, p.ts, dl, rng, hit);
-                    copy_u4<SurfaceVertex>(prop.path.lgt[d], sv);
-                } else {
-                    copy_u4<SurfaceVertex>(sv, cur.path.cam[d]);
-                    more = perturb_stage_camera(sc, off, p.ph, sv, prop.path.lgt, p.ts, dl, rng, hit);
-                    copy_u4<SurfaceVertex>(prop.path.cam[d], sv);
-                }
-            } else {
-                typename GenWorkT<MAXD>::type &gw = genWork[i];
-                dl.bind(gw.c, gw.flag, &gw.n, Limits<MAXD>::MAXC, &sink);
-                const int minDepth = sc.opt.minDepth > 3 ? sc.opt.minDepth : 3;
-                if (STAGE == TS_G_LGT) {
-                    const int d = p.ph.nLgt;
-                    more = gen_stage_light(sc, minDepth, sc.opt.maxDepth, p.ph, sv, p.ts, gw.ls, dl, rng, hit);
-                    copy_u4<SurfaceVertex>(prop.path.lgt[d], sv);
-                } else {
-                    const int d = p.ph.nCam;
-                    more = gen_stage_camera(sc, minDepth, sc.opt.maxDepth, p.ph, sv, prop.path.lgt, p.ts, gw.ls, dl, rng, hit);
-                    copy_u4<SurfaceVertex>(prop.path.cam[d], sv);
-                }
-            }
-            rng_to_payload(rng, p.ts);
-            if (!more) { copy_u4<PathHead>(prop.path, p.ph); rng_close(rng, cs); }   // leaving the wavefront
+            more = shade_entry<MAXD, STAGE>(sc, chainBase, states, genWork, wq, i, p, hit);
         }
         if (STAGE == TS_P_LGT) {
             ray_push(wq.q[nextSet][TS_P_LGT - 1], more && p.ts.stage == TS_P_LGT, i, p);
@@ -458,6 +473,38 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_SHADE_MINB) k_shade(const
             ray_push(wq.q[nextSet][TS_G_CAM - 1], more && p.ts.stage == TS_G_CAM, i, p);
         } else {
             ray_push(wq.q[nextSet][TS_G_CAM - 1], more, i, p);
+        }
+    }
+}
+
+// Tail of the wavefront: after LMC_FULL_WAVES waves only the few long paths are still alive (< 10 % of the
+// rays of an iteration, spread over up to 2 * maxDepth - 6 more waves of nearly empty launches).  This
+// kernel finishes them in one launch, one thread per proposal looping "closest hit, next stage" to the end.
+#ifndef LMC_FULL_WAVES
+#define LMC_FULL_WAVES 5
+#endif
+template <int MAXD>
+__global__ void __launch_bounds__(128) k_shade_tail(const __grid_constant__ Scene sc, int chainBase, ChainRec<MAXD> *states,
+                                                    typename GenWorkT<MAXD>::type *genWork, WaveQueues wq, int curSet) {
+    const RayQueue *q = wq.q[curSet];
+    const int c0 = *q[0].count, c1 = c0 + *q[1].count, c2 = c1 + *q[2].count, c3 = c2 + *q[3].count;
+    const int stride = gridDim.x * blockDim.x;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < c3; idx += stride) {
+        const int k = (idx >= c0) + (idx >= c1) + (idx >= c2);
+        const int pos = idx - (k == 0 ? 0 : (k == 1 ? c0 : (k == 2 ? c1 : c2)));
+        const int slot = q[k].base + q[k].dirn * pos;
+        const int i = q[k].chain[slot];
+        Payload p;
+        payload_load(q[k], slot, p);
+        bool more = true;
+        while (more) {
+            const Hit hit = bvh_traverse<false>(sc, p.ts.ray, p.ts.minT, p.ts.maxT);
+            switch (p.ts.stage) {
+                case TS_P_LGT: more = shade_entry<MAXD, TS_P_LGT>(sc, chainBase, states, genWork, wq, i, p, hit); break;
+                case TS_P_CAM: more = shade_entry<MAXD, TS_P_CAM>(sc, chainBase, states, genWork, wq, i, p, hit); break;
+                case TS_G_LGT: more = shade_entry<MAXD, TS_G_LGT>(sc, chainBase, states, genWork, wq, i, p, hit); break;
+                default:       more = shade_entry<MAXD, TS_G_CAM>(sc, chainBase, states, genWork, wq, i, p, hit); break;
+            }
         }
     }
 }
@@ -602,7 +649,8 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
     GW *genWork = (GW *)wc.genWork;
     const int B = LMC_CHAIN_BLOCK, G = (n + B - 1) / B;
     const int sms = wc.smCount > 0 ? wc.smCount : 148;
-    const int GS = G < sms * LMC_SHADE_MINB ? G : sms * LMC_SHADE_MINB;     // grid-stride kernels: one resident wave of CTAs
+    const int GSmax = (n + LMC_SHADE_BLOCK - 1) / LMC_SHADE_BLOCK;
+    const int GS = GSmax < sms * LMC_SHADE_MINB ? GSmax : sms * LMC_SHADE_MINB;     // grid-stride kernels: one resident wave of CTAs
     const int GT = G < sms * LMC_TRACE_MINB ? G : sms * LMC_TRACE_MINB;     // persistent traversal warps
     const int maxDepth = sc.opt.maxDepth;
     const int GALIGN = LMC_GRAD_BLOCK;          // gradient lists: class-pure blocks
@@ -628,24 +676,29 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         } else {
             e = cudaMemsetAsync(wc.queueCounts, 0, LMC_NCOUNTERS * sizeof(int), st);
             if (e != cudaSuccess) return e;
-            k_prop_start<MAXD, 0><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wl.small_.list, wl.small_.count, wc.wq, sides);
-            k_prop_start<MAXD, 1><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wl.large, wl.largeCount, wc.wq, sides);
+            k_prop_start<MAXD, 0><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wl.small_.list, wl.small_.count, wc.wq, sides);
+            k_prop_start<MAXD, 1><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wl.large, wl.largeCount, wc.wq, sides);
             *launches += 2;
             // a path has at most maxDepth - 1 light-subpath and maxDepth camera-subpath vertices
             const int numWaves = 2 * maxDepth - 1;
-            for (int w = 0; w < numWaves; w++) {
+            const int fullWaves = numWaves < LMC_FULL_WAVES ? numWaves : LMC_FULL_WAVES;
+            for (int w = 0; w < fullWaves; w++) {
                 const int cur = w & 1;
                 k_trace<<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, wc.wq, cur, wc.queueCounts + 16 + w);
                 if (w < maxDepth - 1) {
-                    k_shade<MAXD, TS_P_LGT><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
-                    k_shade<MAXD, TS_G_LGT><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
+                    k_shade<MAXD, TS_P_LGT><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
+                    k_shade<MAXD, TS_G_LGT><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
                     *launches += 2;
                 }
-                k_shade<MAXD, TS_P_CAM><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
-                k_shade<MAXD, TS_G_CAM><<<GS, B, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
+                k_shade<MAXD, TS_P_CAM><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
+                k_shade<MAXD, TS_G_CAM><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
                 *launches += 3;
                 e = cudaMemsetAsync(wc.queueCounts + 4 * cur, 0, 4 * sizeof(int), st);
                 if (e != cudaSuccess) return e;
+            }
+            if (fullWaves < numWaves) {
+                k_shade_tail<MAXD><<<G, 128, 0, st>>>(sc, chainBase, states, genWork, wc.wq, fullWaves & 1);
+                *launches += 1;
             }
             k_shadow<<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, wc.wq.sh, wc.queueCounts + 16 + 63);
             k_prop_post<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.small_.list, wl.small_.count, wl);
