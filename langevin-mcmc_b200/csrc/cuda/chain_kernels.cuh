@@ -477,11 +477,11 @@ __global__ void __launch_bounds__(LMC_SHADE_BLOCK, LMC_SHADE_MINB) k_shade(const
     }
 }
 
-// Tail of the wavefront: after LMC_FULL_WAVES waves only the few long paths are still alive (< 10 % of the
+// Tail of the wavefront: after LMC_FULL_WAVES waves only the few long paths are still alive (< 5 % of the
 // rays of an iteration, spread over up to 2 * maxDepth - 6 more waves of nearly empty launches).  This
 // kernel finishes them in one launch, one thread per proposal looping "closest hit, next stage" to the end.
 #ifndef LMC_FULL_WAVES
-#define LMC_FULL_WAVES 5
+#define LMC_FULL_WAVES 6
 #endif
 template <int MAXD>
 __global__ void __launch_bounds__(128) k_shade_tail(const __grid_constant__ Scene sc, int chainBase, ChainRec<MAXD> *states,

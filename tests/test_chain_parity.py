@@ -146,3 +146,29 @@ def test_cuda_full_size_properties(lmc, torus_xml):
     ctx.begin(1024, norm, init_ls, total_chains=chains, samples_per_chain=steps)
     t_small, _ = ctx.run(steps, trace=True)
     assert ((t_small[:, 0] & 3) == 0).all()
+
+
+@pytest.mark.gpu
+def test_cuda_per_vertex_wavefront_equals_monolithic_propose(lmc, torus_xml, door_xml, monkeypatch):
+    """The two device forms of the proposal phase -- per-vertex wavefront (k_prop_start / k_trace /
+    k_shade<stage> / k_shade_tail / k_shadow / k_prop_post, the default) and the monolithic
+    k_wave_propose kept as an A/B switch (LMC_WAVEFRONT=0) -- give the same chains bit for bit."""
+    for xml, depth in ((torus_xml, 8), (door_xml, 10)):
+        out = []
+        for wf in ("1", "0"):
+            monkeypatch.setenv("LMC_WAVEFRONT", wf)
+            sc = lmc.ParseScene(xml)
+            sc.options["maxdepth"] = depth
+            chains, steps = 2048, 24
+            norm, init_ls = lmc.MLTInit(sc, 100000, chains, 32)
+            ctx = lmc.ChainContext(sc, 0)
+            ctx.begin(chains, norm, init_ls, samples_per_chain=steps)
+            trace, a = ctx.run(steps, trace=True, a_trace=True)
+            out.append((trace, a, ctx.film(), ctx.stats()))
+            ctx.close()
+        (t1, a1, f1, s1), (t0, a0, f0, s0) = out
+        assert np.array_equal(t1, t0) and np.array_equal(a1.view(np.uint32), a0.view(np.uint32))
+        assert s1["proposed"] == s0["proposed"] and s1["accepted"] == s0["accepted"]
+        assert s1["gradient_evals"] == s0["gradient_evals"]
+        assert s1["kernel_launches"] > s0["kernel_launches"]      # really two different launch sequences
+        assert np.allclose(f1, f0, rtol=1e-4, atol=1e-5 * max(1.0, float(f0.max())))
