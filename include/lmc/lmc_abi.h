@@ -9,7 +9,7 @@
  *
  *   lmc_scene_load / _free / options     ParseScene(filename)            src/parsescene.h:8, src/parsescene.cpp:627-639
  *                                        DptOptions                      src/dptoptions.h:7-34
- *   lmc_mlt_init                         MLTInit(...)                    src/mlt.h:41-154 (host phase before the loop)
+ *   lmc_mlt_init / lmc_mlt_init_device   MLTInit(...)                    src/mlt.h:41-154 (phase before the loop; host / device paths)
  *   lmc_create / lmc_destroy             Scene::Scene (Embree build)     src/scene.cpp:8-46, src/trianglemesh.cpp:107-143
  *   lmc_chains_begin + lmc_run_chains    the ParallelFor chain lambda    src/mlt.cpp:60-196, called with
  *                                        Mutation::Mutate plugins        src/mutation.h:16-26
@@ -94,6 +94,13 @@ int lmc_create(const lmc_scene *scene, int32_t device, lmc_ctx **out);
 void lmc_destroy(lmc_ctx *ctx);
 /* cudaStream_t to launch on (default: the legacy default stream); pass torch's current stream */
 int lmc_set_stream(lmc_ctx *ctx, void *cuda_stream);
+
+/* MLTInit with the init paths generated on the device: logical thread t = one CUDA
+ * thread running GeneratePathBidir for its share of the samples (src/mlt.h:51-99); the score sum, CDF and
+ * equal-spaced seeding (src/mlt.h:107-153) stay sequential on the host.  Same results, bit for bit, as
+ * lmc_mlt_init with the same logical_threads; use a large thread count (e.g. 65536) to fill the GPU. */
+int lmc_mlt_init_device(lmc_ctx *ctx, int64_t num_init_samples, int32_t num_chains, int32_t logical_threads,
+                        float *normalization, float *init_ls_score);
 
 /* Allocate + initialise chain state for desc->num_chains chains and clear the film.
  * init_ls_score: HOST pointer to total_chains floats (or NULL = zeros). */

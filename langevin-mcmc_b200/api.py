@@ -60,6 +60,7 @@ def load_library():
         "lmc_scene_set_option": (i32, [vp, cp, dbl]), "lmc_scene_get_option": (i32, [vp, cp, ctypes.POINTER(dbl)]),
         "lmc_scene_serialized": (i32, [vp, vp]),
         "lmc_mlt_init": (i32, [vp, i64, i32, i32, ctypes.POINTER(f32), vp]),
+        "lmc_mlt_init_device": (i32, [vp, i64, i32, i32, ctypes.POINTER(f32), vp]),
         "lmc_create": (i32, [vp, i32, ctypes.POINTER(vp)]), "lmc_destroy": (None, [vp]),
         "lmc_set_stream": (i32, [vp, vp]),
         "lmc_chains_begin": (i32, [vp, ctypes.POINTER(_RunDesc), vp]),
@@ -169,6 +170,15 @@ class ChainContext:
         if stream is not None:
             _check(load_library().lmc_set_stream(self._c, ctypes.c_void_p(int(stream))))
         self.num_chains = 0
+
+    def mlt_init(self, numInitSamples, numChains, logicalThreads=65536):
+        """MLTInit with the init paths generated on this GPU (lmc_mlt_init_device; src/mlt.h:41-154) ->
+        (normalization, initLsScore[numChains]).  Bit-identical to MLTInit(scene, ..., logicalThreads)."""
+        norm = ctypes.c_float()
+        init_ls = np.zeros(int(numChains), np.float32)
+        _check(load_library().lmc_mlt_init_device(self._c, int(numInitSamples), int(numChains), int(logicalThreads),
+                                                  ctypes.byref(norm), _ptr(init_ls)))
+        return norm.value, init_ls
 
     def begin(self, num_chains, normalization, init_ls_score=None, chain_base=0, total_chains=None,
               samples_per_chain=0):

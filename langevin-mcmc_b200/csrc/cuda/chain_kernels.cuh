@@ -549,7 +549,7 @@ struct ShadowSrc {
     }
 };
 #ifndef LMC_TRACE_MINB
-#define LMC_TRACE_MINB 6
+#define LMC_TRACE_MINB 2
 #endif
 static __global__ void __launch_bounds__(LMC_TRACE_BLOCK, LMC_TRACE_MINB) k_trace(const __grid_constant__ Scene sc, WaveQueues wq, int curSet, int *cursor) {
     __shared__ __align__(128) BvhNode top[LMC_TOP_NODES];
@@ -599,6 +599,38 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_prop_post(const __grid_cons
     }
 }
 
+// ---- MLTInit on the device (src/mlt.h:41-106): the init paths ---------------------------------
+// Logical thread t = one CUDA thread: RNG(t + seedOffset), its share of the init samples generated
+// back to back with GeneratePathBidir exactly like the host restatement (host/mlt_init.h).  Pass 1
+// (EMIT = 0) counts the contributions of every logical thread, the host turns the counts into
+// offsets, pass 2 (EMIT = 1) regenerates the same paths and writes their lsScores in
+// (logical thread, sample, contribution) order.  The fp32 running sums over that list (CDF,
+// normalisation) stay sequential on the host so that both forms agree bit for bit.
+template <int MAXD, int EMIT>
+__global__ void __launch_bounds__(128) k_mlt_init_paths(const __grid_constant__ Scene sc, long long numInitSamples, int logicalThreads,
+                                                        int *counts, const long long *offsets, float *scores) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= logicalThreads) return;
+    uint32_t tab[64];
+    Rng rng; rng.tab = tab; rng.stride = 1;
+    rng_seed_lazy(rng, (uint64_t)(long long)(t + sc.opt.seedOffset));
+    const long long perT = numInitSamples / logicalThreads, extra = numInitSamples % logicalThreads;
+    const long long n = perT + ((t < extra) ? 1 : 0);
+    const int minPathLength = sc.opt.minDepth > 3 ? sc.opt.minDepth : 3;
+    Path<MAXD> path;
+    ContribList<Limits<MAXD>::MAXC> contribs;
+    int count = 0;
+    long long pos = EMIT ? offsets[t] : 0;
+    for (long long s = 0; s < n; s++) {
+        contribs.clear();
+        path_clear(path);
+        generate_path_bidir(sc, minPathLength, sc.opt.maxDepth, path, contribs, rng);
+        if (EMIT) for (int i = 0; i < contribs.n; i++) scores[pos++] = contribs.c[i].lsScore;
+        count += contribs.n;
+    }
+    if (!EMIT) counts[t] = count;
+}
+
 template <int MAXD>
 __global__ void k_chain_stats(const ChainRec<MAXD> *states, int n, unsigned long long *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -634,7 +666,9 @@ struct WaveCfg {
     cudaError_t launch_chain_run_##MAXD(cudaStream_t st, const Scene &sc, const RunParams &rp, int chainBase, void *states, \
                                         int n, long long numSteps, float *film, unsigned char *trace, float *aTrace, \
                                         const WaveLists &wl, const WaveCfg &wc, unsigned long long *launches, H2mcSide *sides); \
-    cudaError_t launch_chain_stats_##MAXD(cudaStream_t st, const void *states, int n, unsigned long long *out);
+    cudaError_t launch_chain_stats_##MAXD(cudaStream_t st, const void *states, int n, unsigned long long *out); \
+    cudaError_t launch_mlt_init_paths_##MAXD(cudaStream_t st, const Scene &sc, long long numInitSamples, int logicalThreads, \
+                                             int emit, int *counts, const long long *offsets, float *scores);
 LMC_DECLARE_CHAIN(4)
 LMC_DECLARE_CHAIN(8)
 LMC_DECLARE_CHAIN(12)
@@ -651,7 +685,8 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
     const int sms = wc.smCount > 0 ? wc.smCount : 148;
     const int GSmax = (n + LMC_SHADE_BLOCK - 1) / LMC_SHADE_BLOCK;
     const int GS = GSmax < sms * LMC_SHADE_MINB ? GSmax : sms * LMC_SHADE_MINB;     // grid-stride kernels: one resident wave of CTAs
-    const int GT = G < sms * LMC_TRACE_MINB ? G : sms * LMC_TRACE_MINB;     // persistent traversal warps
+    const int GTmax = (n + LMC_TRACE_BLOCK - 1) / LMC_TRACE_BLOCK;
+    const int GT = GTmax < sms * LMC_TRACE_MINB ? GTmax : sms * LMC_TRACE_MINB;     // persistent traversal warps
     const int maxDepth = sc.opt.maxDepth;
     const int GALIGN = LMC_GRAD_BLOCK;          // gradient lists: class-pure blocks
     const int GG = (n + LMC_NKEYS * (GALIGN - 1) + LMC_GRAD_BLOCK - 1) / LMC_GRAD_BLOCK;   // gradient grid over the (padded) list
@@ -739,6 +774,13 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
     } \
     cudaError_t launch_chain_stats_##MAXD(cudaStream_t st, const void *states, int n, unsigned long long *out) { \
         k_chain_stats<MAXD><<<(n + 127) / 128, 128, 0, st>>>((const ChainRec<MAXD> *)states, n, out); \
+        return cudaGetLastError(); \
+    } \
+    cudaError_t launch_mlt_init_paths_##MAXD(cudaStream_t st, const Scene &sc, long long numInitSamples, int logicalThreads, \
+                                             int emit, int *counts, const long long *offsets, float *scores) { \
+        const int g = (logicalThreads + 127) / 128; \
+        if (emit) k_mlt_init_paths<MAXD, 1><<<g, 128, 0, st>>>(sc, numInitSamples, logicalThreads, counts, offsets, scores); \
+        else k_mlt_init_paths<MAXD, 0><<<g, 128, 0, st>>>(sc, numInitSamples, logicalThreads, counts, offsets, scores); \
         return cudaGetLastError(); \
     }
 

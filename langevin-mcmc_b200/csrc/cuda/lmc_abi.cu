@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "../../../include/lmc/lmc_abi.h"
 #include "chain_kernels.cuh"
@@ -262,6 +263,50 @@ int lmc_mlt_init(const lmc_scene *scene, int64_t num_init_samples, int32_t num_c
         *normalization = r.normalization;
         if (init_ls_score) memcpy(init_ls_score, r.initLsScore.data(), sizeof(float) * (size_t)num_chains);
     } catch (const std::exception &e) { return fail(LMC_ERR_STATE, e.what()); }
+    return LMC_OK;
+}
+
+int lmc_mlt_init_device(lmc_ctx *c, int64_t num_init_samples, int32_t num_chains, int32_t logical_threads,
+                        float *normalization, float *init_ls_score) {
+    if (!c || !normalization || num_chains <= 0 || num_init_samples <= 0 || logical_threads <= 0) return fail(LMC_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    const int d = c->maxdTemplate;
+    const int T = logical_threads;
+    int *dCounts = nullptr; long long *dOffsets = nullptr; float *dScores = nullptr;
+    CK(cudaMalloc((void **)&dCounts, sizeof(int) * (size_t)T));
+    CK(cudaMalloc((void **)&dOffsets, sizeof(long long) * (size_t)T));
+    auto launch = [&](int emit) {
+        return d == 4 ? launch_mlt_init_paths_4(c->stream, c->sc, num_init_samples, T, emit, dCounts, dOffsets, dScores)
+                      : (d == 8 ? launch_mlt_init_paths_8(c->stream, c->sc, num_init_samples, T, emit, dCounts, dOffsets, dScores)
+                                : launch_mlt_init_paths_12(c->stream, c->sc, num_init_samples, T, emit, dCounts, dOffsets, dScores));
+    };
+    int rc = LMC_OK;
+    std::vector<int> counts(T);
+    std::vector<long long> offsets(T);
+    std::vector<float> scores;
+    cudaError_t e = launch(0);
+    c->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts.data(), dCounts, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    long long total = 0;
+    if (e == cudaSuccess) {
+        for (int t = 0; t < T; t++) { offsets[t] = total; total += counts[t]; }
+        scores.resize((size_t)total);
+        e = cudaMalloc((void **)&dScores, sizeof(float) * (size_t)std::max<long long>(total, 1));
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dOffsets, offsets.data(), sizeof(long long) * (size_t)T, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) { e = launch(1); c->launches++; }
+    if (e == cudaSuccess && total > 0) e = cudaMemcpyAsync(scores.data(), dScores, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = fail(LMC_ERR_CUDA, std::string("lmc_mlt_init_device: ") + cudaGetErrorString(e));
+    cudaFree(dCounts); cudaFree(dOffsets); if (dScores) cudaFree(dScores);
+    if (rc) return rc;
+    try {
+        lmc_host::InitResult r;
+        lmc_host::mlt_init_finish(scores, num_init_samples, num_chains, r);
+        *normalization = r.normalization;
+        if (init_ls_score) memcpy(init_ls_score, r.initLsScore.data(), sizeof(float) * (size_t)num_chains);
+    } catch (const std::exception &ex) { return fail(LMC_ERR_STATE, ex.what()); }
     return LMC_OK;
 }
 

@@ -9,7 +9,7 @@
 // the last one finishes idles most of its lanes (measured 6-10 of 32 active).  Instead every warp keeps
 // pulling rays from the queue cursor: whenever a quarter of its lanes have retired their ray they fetch
 // new ones, and the while-while loop (descend to a leaf / intersect the leaf) keeps running on full
-// warps.  The top LMC_TOP_NODES nodes of the tree (breadth-first order, host_scene.cpp) are staged in
+// warps (and leaves the descent loop early when only a few stragglers are still descending).  The top LMC_TOP_NODES nodes of the tree (breadth-first order, host_scene.cpp) are staged in
 // shared memory with one TMA bulk copy per block (cp.async.bulk + mbarrier); deeper nodes and the
 // triangles come through the read-only L1/L2 path.
 #pragma once
@@ -21,10 +21,13 @@ namespace lmc_cuda {
 using namespace lmc;
 
 #ifndef LMC_TOP_NODES
-#define LMC_TOP_NODES 512          // 32 KB of shared memory per block
+#define LMC_TOP_NODES 256          // 16 KB of shared memory per block (2 blocks per SM)
 #endif
 #ifndef LMC_TRACE_BLOCK
-#define LMC_TRACE_BLOCK 128
+#define LMC_TRACE_BLOCK 512        // few, large blocks: shared memory taken from the L1 hurts (measured: 6 x 32 KB -> 2 x 16 KB = +4 %)
+#endif
+#ifndef LMC_TRACE_DESC_MIN
+#define LMC_TRACE_DESC_MIN 12      // leave the descent loop when fewer lanes than this are still descending
 #endif
 #ifndef LMC_TRACE_REFILL
 #define LMC_TRACE_REFILL 8         // refill when at least this many lanes are idle
@@ -108,31 +111,41 @@ __device__ __forceinline__ void trace_persistent(const Scene &sc, const BvhNode 
         }
         if (__ballot_sync(FULL, rayIdx >= 0) == 0u) break;
 #ifndef LMC_TRACE_IFIF
-        // ---- descend to the next leaf
-        while (cur >= 0) {
-            const F4s a = ld_node4(top, topCount, sc.nodes, cur, 0);     // lmin.xyz, lmax.x
-            const F4s b = ld_node4(top, topCount, sc.nodes, cur, 1);     // lmax.yz, rmin.xy
-            const F4s c = ld_node4(top, topCount, sc.nodes, cur, 2);     // rmin.z, rmax.xyz
-            const F4s d = ld_node4(top, topCount, sc.nodes, cur, 3);     // left, right
-            float tl, tr;
-            const bool hl = box_test(a.x, a.y, a.z, a.w, b.x, b.y, invDir, negOrgInv, minT, best.t, tl);
-            const bool hr = box_test(b.z, b.w, c.x, c.y, c.z, c.w, invDir, negOrgInv, minT, best.t, tr);
-            const int left = __float_as_int(d.x), right = __float_as_int(d.y);
-            if (hl && hr) {
-                const bool swap = tr < tl;
-                const int nearC = swap ? right : left, farC = swap ? left : right;
-                if (sp < LMC_BVH_STACK) stack[sp++] = farC;
-                cur = nearC;
-            } else if (hl) {
-                cur = left;
-            } else if (hr) {
-                cur = right;
-            } else {
-                cur = (sp > 0) ? stack[--sp] : LMC_BVH_DONE;
+        // ---- descend to the next leaf.  The number of node visits until a lane reaches its next leaf is
+        // heavy-tailed (measured: 7 of 32 lanes active in a plain `while (cur >= 0)` loop), so the warp leaves
+        // the loop as soon as fewer than LMC_TRACE_DESC_MIN lanes are still descending while others hold a
+        // leaf; the stragglers simply keep descending in the next turn, next to the lanes that come back
+        // from their leaves.
+        for (;;) {
+            const bool desc = cur >= 0;
+            const unsigned dm = __ballot_sync(FULL, desc);
+            if (dm == 0u) break;
+            if (__popc(dm) < LMC_TRACE_DESC_MIN && __ballot_sync(FULL, cur < 0 && cur != LMC_BVH_DONE) != 0u) break;
+            if (desc) {
+                const F4s a = ld_node4(top, topCount, sc.nodes, cur, 0);     // lmin.xyz, lmax.x
+                const F4s b = ld_node4(top, topCount, sc.nodes, cur, 1);     // lmax.yz, rmin.xy
+                const F4s c = ld_node4(top, topCount, sc.nodes, cur, 2);     // rmin.z, rmax.xyz
+                const F4s d = ld_node4(top, topCount, sc.nodes, cur, 3);     // left, right
+                float tl, tr;
+                const bool hl = box_test(a.x, a.y, a.z, a.w, b.x, b.y, invDir, negOrgInv, minT, best.t, tl);
+                const bool hr = box_test(b.z, b.w, c.x, c.y, c.z, c.w, invDir, negOrgInv, minT, best.t, tr);
+                const int left = __float_as_int(d.x), right = __float_as_int(d.y);
+                if (hl && hr) {
+                    const bool swap = tr < tl;
+                    const int nearC = swap ? right : left, farC = swap ? left : right;
+                    if (sp < LMC_BVH_STACK) stack[sp++] = farC;
+                    cur = nearC;
+                } else if (hl) {
+                    cur = left;
+                } else if (hr) {
+                    cur = right;
+                } else {
+                    cur = (sp > 0) ? stack[--sp] : LMC_BVH_DONE;
+                }
             }
         }
         // ---- intersect the leaf
-        if (cur != LMC_BVH_DONE) {
+        if (cur < 0 && cur != LMC_BVH_DONE) {
             const int enc = ~cur;
             const int first = enc >> 3;
             const int count = (enc & 7) + 1;

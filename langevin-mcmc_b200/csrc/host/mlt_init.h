@@ -31,6 +31,41 @@ struct InitResult {
     long long numInitContribs;
 };
 
+// The sequential part of MLTInit: score sum, CDF and equal-spaced seeding (src/mlt.h:107-153) over the
+// lsScores of all init contributions in (logical thread, sample, contribution) order.  Shared by the host
+// path generator below and the device one (lmc_mlt_init_device: the kernel produces `scores`, the fp32
+// running sums stay sequential so both give the same bits).
+inline void mlt_init_finish(const std::vector<float> &scores, long long numInitSamples, int numChains, InitResult &res) {
+    using namespace lmc;
+    float totalScore = 0.0f;
+    for (float s : scores) totalScore += s;
+    res.numInitContribs = (long long)scores.size();
+    if ((long long)scores.size() < (long long)numChains)
+        throw std::runtime_error("MLT initialization failed, consider using a larger number of initial samples or smaller number of chains");
+
+    // Equal-spaced seeding (src/mlt.h:107-148)
+    std::vector<float> cdf(scores.size() + 1);
+    cdf[0] = 0.0f;
+    for (size_t i = 0; i < scores.size(); i++) cdf[i + 1] = cdf[i] + scores[i];
+    const float interval = cdf.back() / (float)numChains;
+    uint32_t tab[64];
+    Rng rng; rng.tab = tab; rng.stride = 1;
+    rng_seed(rng, (uint64_t)scores.size());
+    float pos = rng_uniform_ab(rng, 0.0f, interval);
+    int cdfPos = 0;
+    res.initLsScore.resize(numChains);
+    for (int i = 0; i < numChains; i++) {
+        while (pos > cdf[cdfPos]) {
+            if (cdfPos == (int)scores.size() - 1) break;   // guard: the reference would spin forever here
+            cdfPos = std::min(cdfPos + 1, (int)scores.size() - 1);
+        }
+        // sic: mStates[cdfPos - 1]; cdfPos >= 1 whenever pos > 0
+        res.initLsScore[i] = scores[cdfPos > 0 ? cdfPos - 1 : 0];
+        pos += interval;
+    }
+    res.normalization = totalScore * (1.0f / (float)numInitSamples);
+}
+
 template <int MAXD>
 inline void mlt_init(const lmc::Scene &sc, long long numInitSamples, int numChains, int logicalThreads,
                      InitResult &res) {
@@ -76,37 +111,12 @@ inline void mlt_init(const lmc::Scene &sc, long long numInitSamples, int numChai
 
     std::vector<float> scores;
     res.lengthContrib.clear();
-    float totalScore = 0.0f;
     for (int t = 0; t < logicalThreads; t++) {
-        for (float s : perThread[t]) { totalScore += s; scores.push_back(s); }
+        for (float s : perThread[t]) scores.push_back(s);
         if (perThreadLen[t].size() > res.lengthContrib.size()) res.lengthContrib.resize(perThreadLen[t].size(), 0.0f);
         for (size_t i = 0; i < perThreadLen[t].size(); i++) res.lengthContrib[i] += perThreadLen[t][i];
     }
-    res.numInitContribs = (long long)scores.size();
-    if ((long long)scores.size() < (long long)numChains)
-        throw std::runtime_error("MLT initialization failed, consider using a larger number of initial samples or smaller number of chains");
-
-    // Equal-spaced seeding (src/mlt.h:107-148)
-    std::vector<float> cdf(scores.size() + 1);
-    cdf[0] = 0.0f;
-    for (size_t i = 0; i < scores.size(); i++) cdf[i + 1] = cdf[i] + scores[i];
-    const float interval = cdf.back() / (float)numChains;
-    uint32_t tab[64];
-    Rng rng; rng.tab = tab; rng.stride = 1;
-    rng_seed(rng, (uint64_t)scores.size());
-    float pos = rng_uniform_ab(rng, 0.0f, interval);
-    int cdfPos = 0;
-    res.initLsScore.resize(numChains);
-    for (int i = 0; i < numChains; i++) {
-        while (pos > cdf[cdfPos]) {
-            if (cdfPos == (int)scores.size() - 1) break;   // guard: the reference would spin forever here
-            cdfPos = std::min(cdfPos + 1, (int)scores.size() - 1);
-        }
-        // sic: mStates[cdfPos - 1]; cdfPos >= 1 whenever pos > 0
-        res.initLsScore[i] = scores[cdfPos > 0 ? cdfPos - 1 : 0];
-        pos += interval;
-    }
-    res.normalization = totalScore * (1.0f / (float)numInitSamples);
+    mlt_init_finish(scores, numInitSamples, numChains, res);
 }
 
 }  // namespace lmc_host

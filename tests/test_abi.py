@@ -92,3 +92,22 @@ def test_no_cpu_fallback(lmc, torus_xml):
     sc = lmc.ParseScene(torus_xml)
     with pytest.raises(lmc.LmcError, match="no CUDA device|CUDA"):
         lmc.ChainContext(sc, 0)
+
+
+@pytest.mark.gpu
+def test_cuda_mlt_init_device_equals_host(lmc, torus_xml, door_xml):
+    """lmc_mlt_init_device (init paths generated on the GPU, one CUDA thread per logical thread) against
+    lmc_mlt_init (host restatement of MLTInit, src/mlt.h:41-154) with the same logical thread count:
+    normalisation and per-chain init scores bit-equal."""
+    import numpy as np
+    for xml, depth, samples, chains, threads in ((torus_xml, 8, 60000, 4096, 1024), (door_xml, 6, 30000, 1000, 777),
+                                                  (torus_xml, 4, 5000, 256, 32)):
+        sc = lmc.ParseScene(xml)
+        sc.options["maxdepth"] = depth
+        norm_h, ls_h = lmc.MLTInit(sc, samples, chains, threads)
+        ctx = lmc.ChainContext(sc, 0)
+        norm_d, ls_d = ctx.mlt_init(samples, chains, threads)
+        ctx.close()
+        assert np.float32(norm_h).tobytes() == np.float32(norm_d).tobytes()
+        assert np.array_equal(ls_h.view(np.uint32), ls_d.view(np.uint32))
+        assert norm_d > 0 and (ls_d > 0).all()
