@@ -174,11 +174,13 @@ def main():
     total = n_local * world
     M, K, W = args.mutations_per_step, args.steps, args.warmup
 
-    # ---- setup (untimed): MLTInit on the host (rank 0), broadcast ----
+    # ---- setup (untimed): MLTInit (init paths generated on rank 0's GPU, lmc_mlt_init_device), broadcast ----
     t_setup = time.time()
+    stream = torch.cuda.current_stream()
+    ctx = lmc.ChainContext(scene, local, stream=stream.cuda_stream)
     init_t = torch.zeros(total + 1, dtype=torch.float32, device="cuda")
     if rank == 0:
-        norm, init_ls = lmc.MLTInit(scene, max(300000, 4 * total), total, 32)
+        norm, init_ls = ctx.mlt_init(max(300000, 4 * total), total, 65536)
         init_t[0] = norm
         init_t[1:] = torch.from_numpy(init_ls).cuda()
     if world > 1:
@@ -187,8 +189,6 @@ def main():
     init_ls = init_t[1:].cpu().numpy()
     setup_s = time.time() - t_setup
 
-    stream = torch.cuda.current_stream()
-    ctx = lmc.ChainContext(scene, local, stream=stream.cuda_stream)
     film_t = torch.zeros(scene.height, scene.width, 3, dtype=torch.float32, device="cuda")
     ctx.film_bind(film_t.data_ptr())
     total_mut_per_chain = M * (K + W)
