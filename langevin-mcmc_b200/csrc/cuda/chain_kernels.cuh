@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include "../core/chain.h"
 #include "trace_kernels.cuh"
 
@@ -59,12 +61,17 @@ __global__ void k_chain_init(ChainRec<MAXD> *states, int n, int chainBase, const
 // loop body, (ii) divergent work runs on COMPACTED chain lists with full warps, and (iii) the
 // lists of the expensive phases are SORTED by path class (camDepth, lightDepth, step kind) with
 // an on-device counting sort, so the warps of a block walk the same control flow.
-#define LMC_NKEYS 256
+#define LMC_NKEYS 256            // path classes
+#ifndef LMC_TILES
+#define LMC_TILES 16             // the small-step list is also sorted by screen tile (LMC_TILES x LMC_TILES)
+#endif
+#define LMC_NKEYS_SMALL (LMC_NKEYS * LMC_TILES * LMC_TILES)
 struct SortList {
-    int *keys;      // n: class key of each chain for this list, or -1 = not in the list
-    int *hist;      // LMC_NKEYS (zero between uses)
-    int *offsets;   // LMC_NKEYS
-    int *cursor;    // LMC_NKEYS
+    int nkeys;      // LMC_NKEYS, or LMC_NKEYS_SMALL for the small-step list
+    int *keys;      // n: key of each chain for this list, or -1 = not in the list
+    int *hist;      // nkeys (zero between uses)
+    int *offsets;   // nkeys
+    int *cursor;    // nkeys
     int *list;      // n
     int *count;     // 1
 };
@@ -93,31 +100,53 @@ __device__ __forceinline__ int class_key(int camDepth, int lgtDepth, int kindBit
     return k < LMC_NKEYS ? k : LMC_NKEYS - 1;
 }
 
-// 1 block per list: exclusive scan of the class histogram; clears hist + cursor for the next use.
-// align > 1 starts every class at a multiple of `align` (class-pure thread blocks for the gradient
-// kernel); the gaps keep the -1 the list was pre-filled with, and *count is the padded length.
-static __global__ void k_sort_scan(SortList a, SortList b, int nb, int alignA, int alignB) {
+// 1 block (1024 threads) per list: exclusive scan of the key histogram; clears hist + cursor for the
+// next use.  align > 1 (class-keyed lists only) starts every class at a multiple of `align` (class-pure
+// thread blocks for the gradient kernel); the gaps keep the -1 the list was pre-filled with, and *count is
+// the padded length.
+static __global__ void __launch_bounds__(1024) k_sort_scan(SortList a, SortList b, int nb, int alignA, int alignB) {
     SortList sl = (blockIdx.x == 0) ? a : b;
     const int align = (blockIdx.x == 0) ? alignA : alignB;
     if ((int)blockIdx.x >= nb) return;
-    __shared__ int sh[LMC_NKEYS];
+    __shared__ int part[1024];
     const int t = threadIdx.x;
-    sh[t] = sl.hist[t];
-    __syncthreads();
-    if (t == 0) {
-        int acc = 0;
-        for (int k = 0; k < LMC_NKEYS; k++) {
-            const int c = sh[k];
-            if (c > 0 && align > 1) acc = (acc + align - 1) / align * align;
-            sh[k] = acc; acc += c;
+    const int nkeys = sl.nkeys;
+    if (align > 1) {            // few keys (<= 1024), non-associative rounding: serial over shared memory
+        if (t < nkeys) part[t] = sl.hist[t];
+        __syncthreads();
+        if (t == 0) {
+            int acc = 0;
+            for (int k = 0; k < nkeys; k++) {
+                const int c = part[k];
+                if (c > 0) acc = (acc + align - 1) / align * align;
+                part[k] = acc; acc += c;
+            }
+            acc = (acc + align - 1) / align * align;
+            *sl.count = acc;
         }
-        if (align > 1) acc = (acc + align - 1) / align * align;
-        *sl.count = acc;
+        __syncthreads();
+        if (t < nkeys) { sl.offsets[t] = part[t]; sl.hist[t] = 0; sl.cursor[t] = 0; }
+        return;
     }
+    const int per = (nkeys + 1023) / 1024;
+    const int k0 = t * per, k1 = (k0 + per < nkeys) ? k0 + per : nkeys;
+    int sum = 0;
+    for (int k = k0; k < k1; k++) sum += sl.hist[k];
+    part[t] = sum;
     __syncthreads();
-    sl.offsets[t] = sh[t];
-    sl.hist[t] = 0;
-    sl.cursor[t] = 0;
+    for (int off = 1; off < 1024; off <<= 1) {          // Hillis-Steele inclusive scan of the 1024 partial sums
+        const int v = (t >= off) ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int acc = part[t] - sum;
+    for (int k = k0; k < k1; k++) {
+        const int c = sl.hist[k];
+        sl.offsets[k] = acc; acc += c;
+        sl.hist[k] = 0; sl.cursor[k] = 0;
+    }
+    if (t == 1023) *sl.count = part[1023];
 }
 // one atomic per (warp, key): lanes holding the same key reserve a run of slots together
 __device__ __forceinline__ void sort_scatter_one(const SortList &sl, int i, bool inRange) {
@@ -154,7 +183,11 @@ __device__ __forceinline__ int wave_begin_chain(const Scene &sc, const RunParams
     phase_begin(sc, rp, cs.sampleIdx, cs.st[cs.curIdx], cs.ch, rng, cs.ss);
     const int kind = cs.ss.kind;
     const Path<MAXD> &p = cs.st[cs.curIdx].path;
-    sort_key_set(wl.small_, i, kind == STEP_LARGE ? -1 : class_key(p.camDepth, p.lgtDepth, kind == STEP_ISO ? 0 : 1));
+    // small steps: (class, screen tile) -- chains of a warp then perturb paths through the same part of the
+    // scene: coherent primary rays, neighbouring hit points, the same materials
+    const int tx = dm_clampi((int)(p.screenPos.x * (float)LMC_TILES), 0, LMC_TILES - 1);
+    const int ty = dm_clampi((int)(p.screenPos.y * (float)LMC_TILES), 0, LMC_TILES - 1);
+    sort_key_set(wl.small_, i, kind == STEP_LARGE ? -1 : class_key(p.camDepth, p.lgtDepth, kind == STEP_ISO ? 0 : 1) * (LMC_TILES * LMC_TILES) + ty * LMC_TILES + tx);
     sort_key_set(wl.curGrad, i, cs.ss.needCurGrad ? class_key(p.camDepth, p.lgtDepth, 0) : -1);
     return kind;
 }
@@ -673,6 +706,27 @@ LMC_DECLARE_CHAIN(4)
 LMC_DECLARE_CHAIN(8)
 LMC_DECLARE_CHAIN(12)
 
+// LMC_PHASE_TIMING=1: CUDA-event timing of the phase groups of the LAST iteration of a launch, printed to
+// stderr (development aid; events are only recorded when the variable is set).
+struct PhaseTimer {
+    enum { MAXP = 12 };
+    cudaEvent_t ev[MAXP]; const char *name[MAXP]; int n; bool on; cudaStream_t st;
+    PhaseTimer(cudaStream_t s) : n(0), on(false), st(s) { const char *v = getenv("LMC_PHASE_TIMING"); on = v && v[0] == '1'; }
+    void arm(bool last) { if (on && last) n = 0; else if (on) n = -1; }
+    void mark(const char *what) {
+        if (!on || n < 0 || n >= MAXP) return;
+        cudaEventCreate(&ev[n]); cudaEventRecord(ev[n], st); name[n] = what; n++;
+    }
+    void report() {
+        if (!on || n <= 1) return;
+        cudaEventSynchronize(ev[n - 1]);
+        float tot = 0.0f;
+        for (int i = 1; i < n; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); tot += ms; fprintf(stderr, "[lmc phase] %-22s %8.3f ms\n", name[i], ms); }
+        fprintf(stderr, "[lmc phase] %-22s %8.3f ms\n", "iteration", tot);
+        for (int i = 0; i < n; i++) cudaEventDestroy(ev[i]);
+    }
+};
+
 // One iteration of the chain loop for all chains = the launch sequence below.
 template <int MAXD>
 cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams &rp, int chainBase, void *states_,
@@ -694,8 +748,11 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
     if (e != cudaSuccess) return e;
     k_wave_begin<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl);
     *launches += 1;
+    PhaseTimer pt(st);
     for (long long k = 0; k < numSteps; k++) {
-        k_sort_scan<<<2, LMC_NKEYS, 0, st>>>(wl.small_, wl.curGrad, 2, 1, GALIGN);
+        pt.arm(k + 1 == numSteps);
+        pt.mark("start");
+        k_sort_scan<<<2, 1024, 0, st>>>(wl.small_, wl.curGrad, 2, 1, GALIGN);
         if (GALIGN > 1) {
             e = cudaMemsetAsync(wl.curGrad.list, 0xFF, sizeof(int) * (size_t)wl.listLen, st);
             if (e != cudaSuccess) return e;
@@ -704,6 +761,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide);
         else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide);
         *launches += 3;
+        pt.mark("sort + grad(cur)");
         if (!wc.wavefront) {
             k_wave_propose<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.small_.list, wl.small_.count, wl, sides);
             k_wave_propose<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.large, wl.largeCount, wl, sides);
@@ -714,6 +772,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             k_prop_start<MAXD, 0><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wl.small_.list, wl.small_.count, wc.wq, sides);
             k_prop_start<MAXD, 1><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wl.large, wl.largeCount, wc.wq, sides);
             *launches += 2;
+            pt.mark("prop_start");
             // a path has at most maxDepth - 1 light-subpath and maxDepth camera-subpath vertices
             const int numWaves = 2 * maxDepth - 1;
             const int fullWaves = numWaves < LMC_FULL_WAVES ? numWaves : LMC_FULL_WAVES;
@@ -731,16 +790,19 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
                 e = cudaMemsetAsync(wc.queueCounts + 4 * cur, 0, 4 * sizeof(int), st);
                 if (e != cudaSuccess) return e;
             }
+            pt.mark("waves (trace + shade)");
             if (fullWaves < numWaves) {
                 k_shade_tail<MAXD><<<G, 128, 0, st>>>(sc, chainBase, states, genWork, wc.wq, fullWaves & 1);
                 *launches += 1;
             }
+            pt.mark("tail");
             k_shadow<<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, wc.wq.sh, wc.queueCounts + 16 + 63);
             k_prop_post<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.small_.list, wl.small_.count, wl);
             k_prop_post<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.large, wl.largeCount, wl);
             *launches += 3;
+            pt.mark("shadow + post");
         }
-        k_sort_scan<<<1, LMC_NKEYS, 0, st>>>(wl.propGrad, wl.propGrad, 1, GALIGN, GALIGN);
+        k_sort_scan<<<1, 1024, 0, st>>>(wl.propGrad, wl.propGrad, 1, GALIGN, GALIGN);
         if (GALIGN > 1) {
             e = cudaMemsetAsync(wl.propGrad.list, 0xFF, sizeof(int) * (size_t)wl.listLen, st);
             if (e != cudaSuccess) return e;
@@ -748,15 +810,18 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.propGrad, wl.propGrad, 1);
         if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide);
         else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide);
+        pt.mark("sort + grad(prop)");
         // the large-step list of this iteration is consumed: refill it for the next one in the fused finish + begin
         e = cudaMemsetAsync(wl.largeCount, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;
         if (k + 1 < numSteps) k_wave_finish<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides, wl);
         else k_wave_finish<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides, wl);
         *launches += 4;
+        pt.mark("finish (+ begin)");
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
+    pt.report();
     return cudaSuccess;
 }
 

@@ -113,16 +113,18 @@ int chains_begin(lmc_ctx *c) {
         // per sorted list: keys[n] + list[n] + hist/offsets/cursor[NKEYS] + count; plus the large list
         const size_t listLen = (size_t)n + (size_t)LMC_NKEYS * 256;      // + class-alignment gaps (k_sort_scan)
         c->wl.listLen = (int)listLen;
-        const size_t per = (size_t)n + listLen + 3 * LMC_NKEYS + 4;
-        const size_t total = per * 3 + (size_t)n + 4;
+        const int nkeys[3] = {LMC_NKEYS_SMALL, LMC_NKEYS, LMC_NKEYS};
+        size_t total = (size_t)n + 4;
+        for (int k = 0; k < 3; k++) total += (size_t)n + listLen + 3 * (size_t)nkeys[k] + 4;
         CK(cudaMalloc((void **)&c->listMem, sizeof(int) * total));
         CK(cudaMemsetAsync(c->listMem, 0, sizeof(int) * total, c->stream));
         int *p = c->listMem;
         SortList *sls[3] = {&c->wl.small_, &c->wl.curGrad, &c->wl.propGrad};
         for (int k = 0; k < 3; k++) {
             SortList &sl = *sls[k];
-            sl.keys = p; p += n; sl.list = p; p += listLen; sl.hist = p; p += LMC_NKEYS; sl.offsets = p; p += LMC_NKEYS;
-            sl.cursor = p; p += LMC_NKEYS; sl.count = p; p += 4;
+            sl.nkeys = nkeys[k];
+            sl.keys = p; p += n; sl.list = p; p += listLen; sl.hist = p; p += nkeys[k]; sl.offsets = p; p += nkeys[k];
+            sl.cursor = p; p += nkeys[k]; sl.count = p; p += 4;
         }
         c->wl.large = p; p += n; c->wl.largeCount = p;
         c->listCap = n;
