@@ -128,25 +128,31 @@ static __global__ void __launch_bounds__(1024) k_sort_scan(SortList a, SortList 
         if (t < nkeys) { sl.offsets[t] = part[t]; sl.hist[t] = 0; sl.cursor[t] = 0; }
         return;
     }
-    const int per = (nkeys + 1023) / 1024;
-    const int k0 = t * per, k1 = (k0 + per < nkeys) ? k0 + per : nkeys;
-    int sum = 0;
-    for (int k = k0; k < k1; k++) sum += sl.hist[k];
-    part[t] = sum;
+    // tiles of 1024 keys: coalesced loads, warp-shuffle scan, running offset carried from tile to tile
+    __shared__ int running;
+    if (t == 0) running = 0;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {          // Hillis-Steele inclusive scan of the 1024 partial sums
-        const int v = (t >= off) ? part[t - off] : 0;
+    const int lane = t & 31, warp = t >> 5;
+    for (int k0 = 0; k0 < nkeys; k0 += 1024) {
+        const int k = k0 + t;
+        const int c = (k < nkeys) ? sl.hist[k] : 0;
+        int v = c;
+        for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, off); if (lane >= off) v += u; }
+        if (lane == 31) part[warp] = v;
         __syncthreads();
-        part[t] += v;
+        if (warp == 0) {
+            int w = part[lane];
+            for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += u; }
+            part[32 + lane] = w;          // inclusive scan of the warp totals
+        }
+        __syncthreads();
+        const int base = running + (warp > 0 ? part[32 + warp - 1] : 0);
+        if (k < nkeys) { sl.offsets[k] = base + v - c; sl.hist[k] = 0; sl.cursor[k] = 0; }
+        __syncthreads();
+        if (t == 0) running += part[32 + 31];
         __syncthreads();
     }
-    int acc = part[t] - sum;
-    for (int k = k0; k < k1; k++) {
-        const int c = sl.hist[k];
-        sl.offsets[k] = acc; acc += c;
-        sl.hist[k] = 0; sl.cursor[k] = 0;
-    }
-    if (t == 1023) *sl.count = part[1023];
+    if (t == 0) *sl.count = running;
 }
 // one atomic per (warp, key): lanes holding the same key reserve a run of slots together
 __device__ __forceinline__ void sort_scatter_one(const SortList &sl, int i, bool inRange) {
