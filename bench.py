@@ -235,11 +235,17 @@ def main():
     torch.cuda.synchronize()
     t0 = time.time()
     for _ in range(e2e_steps):
+        ta = time.time()
         ctx.begin(n_local, norm, pinned_init.numpy(), chain_base=rank * n_local, total_chains=total, samples_per_chain=M)
+        tb = time.time()
         ctx.run(M)
         if world > 1:
             dist.all_reduce(film_t)
+        tc = time.time()
         host_film.copy_(film_t, non_blocking=False)
+        if os.environ.get("LMC_BENCH_VERBOSE"):
+            print("e2e step: begin call %.1f ms, run call %.1f ms, film copy (incl. wait) %.1f ms" % (
+                (tb - ta) * 1e3, (tc - tb) * 1e3, (time.time() - tc) * 1e3), file=sys.stderr)
     torch.cuda.synchronize()
     e2e_s = time.time() - t0
     if world > 1:

@@ -84,7 +84,7 @@ struct lmc_ctx {
     // chains
     void *states = nullptr; size_t stateBytes = 0;
     lmc_run_desc desc{};
-    float *initLs = nullptr;
+    float *initLs = nullptr; int initLsCap = 0;
     bool begun = false;
     // film
     float *film = nullptr; bool filmOwned = false;
@@ -385,8 +385,8 @@ int lmc_chains_begin(lmc_ctx *c, const lmc_run_desc *desc, const float *init_ls_
         desc->chain_base + desc->num_chains > desc->total_chains) return fail(LMC_ERR_ARG, "inconsistent run descriptor");
     CK(cudaSetDevice(c->device));
     c->desc = *desc;
-    if (c->initLs) { cudaFree(c->initLs); c->initLs = nullptr; }
-    CK(cudaMalloc((void **)&c->initLs, sizeof(float) * (size_t)desc->total_chains));
+    if (c->initLs && c->initLsCap < desc->total_chains) { cudaFree(c->initLs); c->initLs = nullptr; }
+    if (!c->initLs) { CK(cudaMalloc((void **)&c->initLs, sizeof(float) * (size_t)desc->total_chains)); c->initLsCap = desc->total_chains; }
     if (init_ls_score) CK(cudaMemcpyAsync(c->initLs, init_ls_score, sizeof(float) * (size_t)desc->total_chains, cudaMemcpyHostToDevice, c->stream));
     else CK(cudaMemsetAsync(c->initLs, 0, sizeof(float) * (size_t)desc->total_chains, c->stream));
     const int rc = chains_begin(c);
