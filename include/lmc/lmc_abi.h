@@ -14,6 +14,7 @@
  *   lmc_chains_begin + lmc_run_chains    the ParallelFor chain lambda    src/mlt.cpp:60-196, called with
  *                                        Mutation::Mutate plugins        src/mutation.h:16-26
  *   lmc_film_* / lmc_stats               SampleBuffer indirectBuffer     src/mlt.cpp:55, src/image.h:54-77
+ *   lmc_direct_lighting                  DirectLighting(scene, buffer)   src/direct.cpp:4-54 (pre-pass of MLT(), src/mlt.cpp:30-34)
  *   lmc_eval_batch                       PathFunc / PathFuncDerv         src/path.h:121-125 (dlsym'd
  *                                        evaluate_path_bidir_mala_<c>_<l>_static[_derv], src/path.cpp:3389-3417)
  *   lmc_bvh_probe                        Intersect / Occluded            src/scene.cpp:106-149 (rtcIntersect1 / rtcOccluded1)
@@ -101,6 +102,12 @@ int lmc_set_stream(lmc_ctx *ctx, void *cuda_stream);
  * lmc_mlt_init with the same logical_threads; use a large thread count (e.g. 65536) to fill the GPU. */
 int lmc_mlt_init_device(lmc_ctx *ctx, int64_t num_init_samples, int32_t num_chains, int32_t logical_threads,
                         float *normalization, float *init_ls_score);
+
+/* DirectLighting(scene, buffer) (src/direct.cpp:4-54): the direct-illumination pre-pass of
+ * MLT(), direct_spp samples per pixel (the scene's <integer name="directspp">), one RNG per 16 x 16 tile as in
+ * the reference.  host_rgb receives the UNWEIGHTED sample buffer (W*H*3 floats); the caller merges it with the
+ * chain film as MergeBuffer does: direct / directSpp + indirect / spp (src/mlt.cpp:203-207). */
+int lmc_direct_lighting(lmc_ctx *ctx, int32_t direct_spp, float *host_rgb);
 
 /* Allocate + initialise chain state for desc->num_chains chains and clear the film.
  * init_ls_score: HOST pointer to total_chains floats (or NULL = zeros). */

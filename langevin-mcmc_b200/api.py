@@ -61,6 +61,7 @@ def load_library():
         "lmc_scene_serialized": (i32, [vp, vp]),
         "lmc_mlt_init": (i32, [vp, i64, i32, i32, ctypes.POINTER(f32), vp]),
         "lmc_mlt_init_device": (i32, [vp, i64, i32, i32, ctypes.POINTER(f32), vp]),
+        "lmc_direct_lighting": (i32, [vp, i32, vp]),
         "lmc_create": (i32, [vp, i32, ctypes.POINTER(vp)]), "lmc_destroy": (None, [vp]),
         "lmc_set_stream": (i32, [vp, vp]),
         "lmc_chains_begin": (i32, [vp, ctypes.POINTER(_RunDesc), vp]),
@@ -154,6 +155,11 @@ def MLTInit(scene, numInitSamples=None, numChains=None, logicalThreads=32):
     return norm.value, init_ls
 
 
+def MergeBuffer(buffer1, b1Weight, buffer2, b2Weight):
+    """src/image.h:79-98 followed by BufferToFilm (:100-105): film = b1Weight * buffer1 + b2Weight * buffer2."""
+    return np.float32(b1Weight) * np.asarray(buffer1, np.float32) + np.float32(b2Weight) * np.asarray(buffer2, np.float32)
+
+
 def decode_trace(trace):
     """trace byte -> (mutationType, accepted, a>0)."""
     t = np.asarray(trace)
@@ -179,6 +185,14 @@ class ChainContext:
         _check(load_library().lmc_mlt_init_device(self._c, int(numInitSamples), int(numChains), int(logicalThreads),
                                                   ctypes.byref(norm), _ptr(init_ls)))
         return norm.value, init_ls
+
+    def direct_lighting(self, direct_spp=None):
+        """DirectLighting(scene, buffer), src/direct.cpp:4-54 -> unweighted H x W x 3 sample buffer."""
+        if direct_spp is None:
+            direct_spp = self.scene.info["direct_spp"]
+        out = np.zeros((self.scene.height, self.scene.width, 3), np.float32)
+        _check(load_library().lmc_direct_lighting(self._c, int(direct_spp), _ptr(out)))
+        return out
 
     def begin(self, num_chains, normalization, init_ls_score=None, chain_base=0, total_chains=None,
               samples_per_chain=0):

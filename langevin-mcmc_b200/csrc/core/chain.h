@@ -5,6 +5,7 @@
 // :61-62; currentState = initStates[chainId], valid = false :68, src/mlt.h:124; loop :91-170).
 #pragma once
 #include "mutation.h"
+#include "direct.h"
 
 namespace lmc {
 

@@ -66,6 +66,19 @@ __global__ void __launch_bounds__(64) k_eval_batch_hess(int camDepth, int lightD
                                  vertParams + (size_t)i * vertStride, grad + (size_t)i * dim, hess + (size_t)i * dim * dim);
 }
 
+// DirectLighting(scene, buffer) (src/direct.cpp:4-54): one CUDA thread per 16 x 16 tile, the tile's RNG and
+// sample order as in the reference, so the buffer is reproducible bit for bit (a tile only splats into its
+// own pixels)
+__global__ void __launch_bounds__(64) k_direct_lighting(const __grid_constant__ Scene sc, int nXTiles, int nYTiles, int directSpp, float *buffer) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= nXTiles * nYTiles) return;
+    uint32_t tab[64];
+    Rng rng; rng.tab = tab; rng.stride = 1;
+    rng_seed_lazy(rng, (uint64_t)(long long)(tile + sc.opt.seedOffset));
+    DevFilm df; df.p = buffer;
+    direct_lighting_tile(sc, tile % nXTiles, tile / nXTiles, directSpp, rng, df);
+}
+
 template <class T> int upload(const std::vector<T> &v, T **out) {
     *out = nullptr;
     const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
@@ -309,6 +322,28 @@ int lmc_mlt_init_device(lmc_ctx *c, int64_t num_init_samples, int32_t num_chains
         *normalization = r.normalization;
         if (init_ls_score) memcpy(init_ls_score, r.initLsScore.data(), sizeof(float) * (size_t)num_chains);
     } catch (const std::exception &ex) { return fail(LMC_ERR_STATE, ex.what()); }
+    return LMC_OK;
+}
+
+int lmc_direct_lighting(lmc_ctx *c, int32_t direct_spp, float *host_rgb) {
+    if (!c || !host_rgb || direct_spp < 0) return fail(LMC_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    const int W = c->sc.cam.width, H = c->sc.cam.height;
+    const size_t bytes = (size_t)W * H * 3 * sizeof(float);
+    if (direct_lighting_skipped(c->sc) || direct_spp == 0) { memset(host_rgb, 0, bytes); return LMC_OK; }
+    float *dBuf = nullptr;
+    CK(cudaMalloc((void **)&dBuf, bytes));
+    cudaError_t e = cudaMemsetAsync(dBuf, 0, bytes, c->stream);
+    const int nX = (W + LMC_DIRECT_TILE - 1) / LMC_DIRECT_TILE, nY = (H + LMC_DIRECT_TILE - 1) / LMC_DIRECT_TILE;
+    if (e == cudaSuccess) {
+        k_direct_lighting<<<(nX * nY + 63) / 64, 64, 0, c->stream>>>(c->sc, nX, nY, direct_spp, dBuf);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_rgb, dBuf, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dBuf);
+    if (e != cudaSuccess) return fail(LMC_ERR_CUDA, std::string("lmc_direct_lighting: ") + cudaGetErrorString(e));
     return LMC_OK;
 }
 

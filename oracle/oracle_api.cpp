@@ -208,6 +208,31 @@ int lmco_use_reference_gradient(const char *libPath, int enable) {
     return n;
 }
 
+// DirectLighting(scene, buffer) (src/direct.cpp:4-54): film gets the unweighted sample buffer
+int lmco_direct_lighting(void *h, int directSpp, float *film, int threads) {
+    LMCO_TRY
+    const Scene sc = ((OScene *)h)->store.view();
+    const int W = sc.cam.width, H = sc.cam.height;
+    if (direct_lighting_skipped(sc) || directSpp <= 0) return 0;
+    const int nX = (W + LMC_DIRECT_TILE - 1) / LMC_DIRECT_TILE, nY = (H + LMC_DIRECT_TILE - 1) / LMC_DIRECT_TILE;
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        HostFilm hf; hf.p = film;           // a tile only splats into its own pixels: no races
+        uint32_t tab[64];
+        for (;;) {
+            const int tile = next.fetch_add(1);
+            if (tile >= nX * nY) break;
+            Rng rng; rng.tab = tab; rng.stride = 1;
+            rng_seed(rng, (uint64_t)(long long)(tile + sc.opt.seedOffset));
+            direct_lighting_tile(sc, tile % nX, tile / nX, directSpp, rng, hf);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 0; w < (threads < 1 ? 1 : threads); w++) pool.emplace_back(work);
+    for (auto &t : pool) t.join();
+    LMCO_CATCH
+}
+
 // 1: lmco_run_chains runs every proposal through the staged (wavefront) path functions
 int lmco_use_staged(int enable) { g_staged = enable != 0; return 0; }
 

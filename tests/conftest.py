@@ -95,6 +95,13 @@ class Oracle:
             return -1
         return self.L.lmco_use_reference_gradient(path.encode(), 1 if enable else 0)
 
+    def direct_lighting(self, h, direct_spp, threads=8):
+        """DirectLighting(scene, buffer), src/direct.cpp:4-54 -> unweighted sample buffer."""
+        info = self.info(h)
+        film = np.zeros((info["height"], info["width"], 3), np.float32)
+        assert self.L.lmco_direct_lighting(h, int(direct_spp), self.p(film), threads) == 0, self.L.lmco_last_error()
+        return film
+
     def use_staged(self, enable):
         """Run the proposal phase through the staged (per-vertex wavefront) path functions."""
         return self.L.lmco_use_staged(1 if enable else 0)
