@@ -110,7 +110,6 @@ __device__ __forceinline__ void trace_persistent(const Scene &sc, const BvhNode 
             }
         }
         if (__ballot_sync(FULL, rayIdx >= 0) == 0u) break;
-#ifndef LMC_TRACE_IFIF
         // ---- descend to the next leaf.  The number of node visits until a lane reaches its next leaf is
         // heavy-tailed (measured: 7 of 32 lanes active in a plain `while (cur >= 0)` loop), so the warp leaves
         // the loop as soon as fewer than LMC_TRACE_DESC_MIN lanes are still descending while others hold a
@@ -160,41 +159,6 @@ __device__ __forceinline__ void trace_persistent(const Scene &sc, const BvhNode 
             }
             cur = (ANY_HIT && found) ? LMC_BVH_DONE : ((sp > 0) ? stack[--sp] : LMC_BVH_DONE);
         }
-#else
-        // ---- "if-if": every lane does one node visit OR one triangle test per turn, a few turns per refill check
-#pragma unroll 1
-        for (int turn = 0; turn < LMC_TRACE_IFIF; ++turn) {
-            if (cur >= 0) {
-                const F4s a = ld_node4(top, topCount, sc.nodes, cur, 0);
-                const F4s b = ld_node4(top, topCount, sc.nodes, cur, 1);
-                const F4s c = ld_node4(top, topCount, sc.nodes, cur, 2);
-                const F4s d = ld_node4(top, topCount, sc.nodes, cur, 3);
-                float tl, tr;
-                const bool hl = box_test(a.x, a.y, a.z, a.w, b.x, b.y, invDir, negOrgInv, minT, best.t, tl);
-                const bool hr = box_test(b.z, b.w, c.x, c.y, c.z, c.w, invDir, negOrgInv, minT, best.t, tr);
-                const int left = __float_as_int(d.x), right = __float_as_int(d.y);
-                const bool swap = tr < tl;
-                const int nearC = (hl && hr) ? (swap ? right : left) : (hl ? left : right);
-                if (hl && hr) { if (sp < LMC_BVH_STACK) stack[sp++] = swap ? left : right; cur = nearC; }
-                else if (hl || hr) cur = nearC;
-                else cur = (sp > 0) ? stack[--sp] : LMC_BVH_DONE;
-            } else if (cur != LMC_BVH_DONE) {
-                // leaf reference: ~cur = (first << 3) | (count - 1); consume its first triangle
-                const int enc = ~cur;
-                const int tid = enc >> 3;
-                const int rem = enc & 7;
-                float t, u, v;
-                bool found = false;
-                if (tri_test(sc.tris[tid], ray, minT, best.t, t, u, v)) {
-                    if (ANY_HIT) { best.tid = tid; best.t = t; best.u = u; best.v = v; found = true; }
-                    else if (t < best.t || best.tid < 0 || tid < best.tid) { best.tid = tid; best.t = t; best.u = u; best.v = v; }
-                }
-                if (ANY_HIT && found) cur = LMC_BVH_DONE;
-                else if (rem > 0) cur = ~(((tid + 1) << 3) | (rem - 1));
-                else cur = (sp > 0) ? stack[--sp] : LMC_BVH_DONE;
-            }
-        }
-#endif
         // ---- retire finished rays
         if (rayIdx >= 0 && cur == LMC_BVH_DONE) {
             src.store(rayIdx, best);
