@@ -15,6 +15,7 @@ struct ChainState {
     ChainVars<MAXD> ch;
     StepScratch<MAXD> ss;
     PropCand pc;                 // small step: the proposal's candidate contribution (wavefront, stages.h)
+    LpsFull lpsFull;             // small step with a light subpath: its final state, parked for ConnectVertex
     int curIdx;
     unsigned long long rngState;
     unsigned int rngEpoch;

@@ -101,6 +101,9 @@ struct alignas(16) TraceState {
     int tsPad2[2];
 };
 
+// BidirPathState padded to 16 bytes (the device parks the light-subpath state of a perturbation in it)
+struct alignas(16) LpsFull { BidirPathState s; float pad; };
+
 // Candidate contribution(s) of a small step: at most one (+ a conditional clear)
 struct PropCand {
     int n;

@@ -304,8 +304,54 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_finish(const __grid_co
 // one path vertex it works on.  A chain has at most one pending ray, so the two queues of a step
 // kind (light / camera subpath) share one buffer of `cap` = numChains slots and grow towards each
 // other from its two ends.
-struct alignas(16) Payload { TraceState ts; PathHead ph; };
-#define LMC_PAYLOAD_U4 ((int)(sizeof(Payload) / 16))
+struct alignas(16) Payload { TraceState ts; PathHead ph; };     // working form inside a kernel
+// Wire form in the queues: only what the NEXT stage reads.  A stage overwrites the intersection record and
+// wi of its subpath state before using them, lastBsdfPdf is never read, and of the PathHead only the
+// counters, the light id and the screen position are consulted after the first stage -- so 160 B travel
+// instead of 320.  The rest of the head is written to the proposal's record by the first stage (fields a
+// later stage sets -- envLight, lensVertexPos -- go straight to the record), and the full light-subpath
+// state a connection needs at the last camera vertex is parked in the record (ChainState::lpsFull) by the
+// last light-subpath stage.  The ray stays at words 6..13 (k_trace).
+struct alignas(16) PayloadLite {
+    int stage, depth, offsetId, nLightStates;
+    float ndSaved; int ndAvail; float minT, maxT;
+    float orgx, orgy, orgz, dirx;
+    float diry, dirz; uint32_t rngLo, rngHi;
+    uint32_t rngEpoch; int curIdx; float cAccPrev, cAccThis;
+    float cThrX, cThrY, cThrZ, cSsJ;
+    float lAccPrev, lAccThis, lThrX, lThrY;
+    float lThrZ, lSsJ; int lgtLight, lgtPrim;
+    int nCam, nLgt, camDepth, lgtDepth;
+    float screenX, screenY; int pad0, pad1;
+};
+#define LMC_PAYLOAD_U4 ((int)(sizeof(PayloadLite) / 16))
+#define LMC_ENV_SENTINEL (-2)
+__device__ __forceinline__ void payload_pack(const Payload &p, PayloadLite &l) {
+    const TraceState &t = p.ts;
+    l.stage = t.stage; l.depth = t.depth; l.offsetId = t.offsetId; l.nLightStates = t.nLightStates;
+    l.ndSaved = t.ndSaved; l.ndAvail = t.ndAvail; l.minT = t.minT; l.maxT = t.maxT;
+    l.orgx = t.ray.org.x; l.orgy = t.ray.org.y; l.orgz = t.ray.org.z; l.dirx = t.ray.dir.x;
+    l.diry = t.ray.dir.y; l.dirz = t.ray.dir.z; l.rngLo = t.rngLo; l.rngHi = t.rngHi;
+    l.rngEpoch = t.rngEpoch; l.curIdx = t.curIdx; l.cAccPrev = t.cps.accMISWPrev; l.cAccThis = t.cps.accMISWThis;
+    l.cThrX = t.cps.throughput.x; l.cThrY = t.cps.throughput.y; l.cThrZ = t.cps.throughput.z; l.cSsJ = t.cps.ssJacobian;
+    l.lAccPrev = t.lps.accMISWPrev; l.lAccThis = t.lps.accMISWThis; l.lThrX = t.lps.throughput.x; l.lThrY = t.lps.throughput.y;
+    l.lThrZ = t.lps.throughput.z; l.lSsJ = t.lps.ssJacobian; l.lgtLight = p.ph.lgtLight; l.lgtPrim = p.ph.lgtPrim;
+    l.nCam = p.ph.nCam; l.nLgt = p.ph.nLgt; l.camDepth = p.ph.camDepth; l.lgtDepth = p.ph.lgtDepth;
+    l.screenX = p.ph.screenPos.x; l.screenY = p.ph.screenPos.y; l.pad0 = 0; l.pad1 = 0;
+}
+__device__ __forceinline__ void payload_unpack(const PayloadLite &l, Payload &p) {
+    memset(&p, 0, sizeof(p));
+    TraceState &t = p.ts;
+    t.stage = l.stage; t.depth = l.depth; t.offsetId = l.offsetId; t.nLightStates = l.nLightStates;
+    t.ndSaved = l.ndSaved; t.ndAvail = l.ndAvail; t.minT = l.minT; t.maxT = l.maxT;
+    t.ray.org = mk3(l.orgx, l.orgy, l.orgz); t.ray.dir = mk3(l.dirx, l.diry, l.dirz);
+    t.rngLo = l.rngLo; t.rngHi = l.rngHi; t.rngEpoch = l.rngEpoch; t.curIdx = l.curIdx;
+    t.cps.accMISWPrev = l.cAccPrev; t.cps.accMISWThis = l.cAccThis; t.cps.throughput = mk3(l.cThrX, l.cThrY, l.cThrZ); t.cps.ssJacobian = l.cSsJ;
+    t.lps.accMISWPrev = l.lAccPrev; t.lps.accMISWThis = l.lAccThis; t.lps.throughput = mk3(l.lThrX, l.lThrY, l.lThrZ); t.lps.ssJacobian = l.lSsJ;
+    p.ph.lgtLight = l.lgtLight; p.ph.lgtPrim = l.lgtPrim;
+    p.ph.nCam = l.nCam; p.ph.nLgt = l.nLgt; p.ph.camDepth = l.camDepth; p.ph.lgtDepth = l.lgtDepth;
+    p.ph.screenPos = mk2(l.screenX, l.screenY);
+}
 struct RayQueue {
     int *chain;       // chain slot of entry s
     uint4 *payload;   // [LMC_PAYLOAD_U4][cap]
@@ -342,9 +388,11 @@ struct DevShadowSink {
 };
 
 __device__ __forceinline__ void payload_load(const RayQueue &q, int slot, Payload &p) {
-    uint4 *d = reinterpret_cast<uint4 *>(&p);
+    PayloadLite l;
+    uint4 *d = reinterpret_cast<uint4 *>(&l);
 #pragma unroll
     for (int k = 0; k < LMC_PAYLOAD_U4; k++) d[k] = q.payload[(size_t)k * q.cap + slot];
+    payload_unpack(l, p);
 }
 __device__ __forceinline__ void ray_push(const RayQueue &q, bool pred, int chain, const Payload &p) {
     const unsigned mask = __ballot_sync(__activemask(), pred);
@@ -356,7 +404,9 @@ __device__ __forceinline__ void ray_push(const RayQueue &q, bool pred, int chain
     base = __shfl_sync(mask, base, leader);
     const int slot = q.base + q.dirn * (base + __popc(mask & ((1u << lane) - 1u)));
     q.chain[slot] = chain;
-    const uint4 *s = reinterpret_cast<const uint4 *>(&p);
+    PayloadLite l;
+    payload_pack(p, l);
+    const uint4 *s = reinterpret_cast<const uint4 *>(&l);
 #pragma unroll
     for (int k = 0; k < LMC_PAYLOAD_U4; k++) q.payload[(size_t)k * q.cap + slot] = s[k];
 }
@@ -424,7 +474,8 @@ __global__ void __launch_bounds__(LMC_SHADE_BLOCK, LMC_SHADE_MINB) k_prop_start(
                 more = perturb_stage_begin(sc, offset, p.ph, p.ts, rng);
             }
             rng_to_payload(rng, p.ts);
-            if (!more) { copy_u4<PathHead>(prop.path, p.ph); rng_close(rng, cs); }
+            copy_u4<PathHead>(prop.path, p.ph);        // the whole head now; later stages update single fields
+            if (!more) rng_close(rng, cs);
         }
         if (LARGE) {
             ray_push(wq.q[0][TS_G_LGT - 1], more, i, p);
@@ -449,6 +500,9 @@ __device__ __forceinline__ bool shade_entry(const Scene &sc, int chainBase, Chai
     DeferredList<DevShadowSink> dl;
     SurfaceVertex sv;
     bool more;
+    // head fields a stage may SET are detected through sentinels and written straight to the record
+    p.ph.envLight = LMC_ENV_SENTINEL;
+    p.ph.lensVertexPos.x = __int_as_float(0x7fc00000);
     if (STAGE == TS_P_LGT || STAGE == TS_P_CAM) {
         OffPair off; off.base = p.ts.offsetId;
         off.v0 = cs.ss.offset[off.base]; off.v1 = cs.ss.offset[off.base + 1];
@@ -458,8 +512,12 @@ __device__ __forceinline__ bool shade_entry(const Scene &sc, int chainBase, Chai
             copy_u4<SurfaceVertex>(sv, cur.path.lgt[d]);
             more = perturb_stage_light(sc, off, p.ph, sv, p.ts, dl, rng, hit);
             copy_u4<SurfaceVertex>(prop.path.lgt[d], sv);
+            // light subpath complete: park its state for the connection at the end of the camera subpath
+            if (more && p.ts.stage == TS_P_CAM) cs.lpsFull.s = p.ts.lps;
         } else {
             copy_u4<SurfaceVertex>(sv, cur.path.cam[d]);
+            // the connection at the last camera vertex needs the whole light-subpath state
+            if (p.ph.lgtDepth > 1 && d == p.ph.nCam - 1) p.ts.lps = cs.lpsFull.s;
             more = perturb_stage_camera(sc, off, p.ph, sv, prop.path.lgt, p.ts, dl, rng, hit);
             copy_u4<SurfaceVertex>(prop.path.cam[d], sv);
         }
@@ -478,7 +536,12 @@ __device__ __forceinline__ bool shade_entry(const Scene &sc, int chainBase, Chai
         }
     }
     rng_to_payload(rng, p.ts);
-    if (!more) { copy_u4<PathHead>(prop.path, p.ph); rng_close(rng, cs); }   // leaving the wavefront
+    if (p.ph.envLight != LMC_ENV_SENTINEL) { prop.path.envLight = p.ph.envLight; prop.path.envPrim = p.ph.envPrim; }
+    if (p.ph.lensVertexPos.x == p.ph.lensVertexPos.x) prop.path.lensVertexPos = p.ph.lensVertexPos;
+    if (!more) {      // leaving the wavefront: counters, screen position and RNG state back to the record
+        prop.path.nCam = p.ph.nCam; prop.path.nLgt = p.ph.nLgt; prop.path.screenPos = p.ph.screenPos;
+        rng_close(rng, cs);
+    }
     return more;
 }
 

@@ -148,13 +148,13 @@ int chains_begin(lmc_ctx *c) {
         // 2 sets x 2 step kinds: a buffer of n entries (chain, payload, hit) shared by the light- and the
         // camera-subpath queue of that kind; a shadow queue of 4n segments; 9 counters
         const size_t nn = (size_t)n, shCap = 4 * nn;
-        const size_t perBuf = nn * (sizeof(int) + sizeof(Payload) + sizeof(float4)) + 64;
+        const size_t perBuf = nn * (sizeof(int) + sizeof(PayloadLite) + sizeof(float4)) + 64;
         const size_t bytes = 4 * perBuf + shCap * (2 * sizeof(float4) + sizeof(int *)) + 1024;
         CK(cudaMalloc(&c->queueMem, bytes));
         char *p = (char *)c->queueMem;
         auto take = [&](size_t b) { char *r = p; p += (b + 15) & ~(size_t)15; return r; };
         for (int s = 0; s < 2; s++) for (int kind = 0; kind < 2; kind++) {
-            uint4 *payload = (uint4 *)take(nn * sizeof(Payload));
+            uint4 *payload = (uint4 *)take(nn * sizeof(PayloadLite));
             float4 *hit = (float4 *)take(nn * sizeof(float4));
             int *chain = (int *)take(nn * sizeof(int));
             for (int end = 0; end < 2; end++) {       // light-subpath queue grows up, camera-subpath queue grows down
