@@ -570,7 +570,11 @@ LMC_HD void phase_propose(const Scene &sc, const RunParams &rp, MarkovState<MAXD
 // The same phase through the staged path functions (stages.h), ray queries answered on the spot:
 // the host-side model of the device wavefront (tests/test_staged.py compares it with phase_propose).
 struct ImmediateShadowSink {
+    static const bool kDeferConnections = false;
     const Scene *sc;
+    template <class LS>
+    LMC_HD void emit_connection(const Scene &, int, int, int, const LS *, const SurfaceVertex *, const LS &, const SurfaceVertex &, V2,
+                                SubpathContrib *, int *) {}
     LMC_HD void emit(const Ray &ray, float dist, int, int *flag) { *flag = cand_resolve(*flag, scene_occluded(*sc, ray, dist)); }
 };
 template <int MAXD>

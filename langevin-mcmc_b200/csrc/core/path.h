@@ -195,6 +195,11 @@ struct ContribList {
     // visibility of a connection segment: traced on the spot (see DeferredList in stages.h for
     // the wavefront variant, which queues the shadow ray and resolves the contribution later)
     LMC_HD bool occluded(const Scene &sc, const Ray &ray, float dist) { return scene_occluded(sc, ray, dist); }
+    // ConnectVertex for one (camera vertex, light vertex) pair of GeneratePathBidir (src/path.cpp:1417-1431);
+    // the wavefront's DeferredList may hand the pair to a dedicated kernel instead (stages.h)
+    template <class LS>
+    LMC_HD void connect(const Scene &sc, int camDepth, int lgtDepth, const LS *ls, const SurfaceVertex *lgtVerts,
+                        const LS &cps, const SurfaceVertex &camVertex, V2 screenPos);
 };
 
 template <class CL>
@@ -397,6 +402,14 @@ LMC_HD_NOINLINE void connect_vertex(const Scene &sc, int camDepth, int lgtDepth,
     }
 }
 
+template <int CAP>
+template <class LS>
+LMC_HD void ContribList<CAP>::connect(const Scene &sc, int camDepth, int lgtDepth, const LS *ls, const SurfaceVertex *lgtVerts,
+                                      const LS &cps, const SurfaceVertex &camVertex, V2 screenPos) {
+    const SurfaceVertex lv = lgtVerts[lgtDepth];
+    connect_vertex(sc, camDepth, lgtDepth, ls[lgtDepth], lv, cps, camVertex, screenPos, *this);
+}
+
 LMC_HD bool russian_roulette(int depth, V3 bsdfContrib, float &rrWeight, V3 &throughput, Rng &rng) {
     float rrProb = 1.0f;
     if (depth >= 3) rrProb = dm_min(max_coeff(bsdfContrib), 0.95f);
@@ -495,8 +508,7 @@ LMC_HD_NOINLINE void generate_path_bidir(const Scene &sc, int minDepth, int maxD
         }
         for (int lgtDepth = 0; lgtDepth <= maxLgtDepth; lgtDepth++) {
             if (camDepth + lgtDepth + 3 >= minDepth) {
-                connect_vertex(sc, camDepth, lgtDepth, lightStates[lgtDepth], path.lgt[lgtDepth], cps, sv,
-                               path.screenPos, contribs);
+                contribs.connect(sc, camDepth, lgtDepth, lightStates, path.lgt, cps, sv, path.screenPos);
             }
         }
         sv.bsdfRndParam.x = rng_uniform(rng); sv.bsdfRndParam.y = rng_uniform(rng);

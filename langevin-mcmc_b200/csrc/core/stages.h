@@ -49,6 +49,24 @@ struct DeferredList {
         }
         pend = false;
     }
+    // ConnectVertex of GeneratePathBidir: evaluated on the spot, or -- when the sink wants it
+    // (SINK::kDeferConnections) -- a slot is reserved in push order (flagged OCCLUDED = "nothing here" until
+    // somebody fills it) and the pair is handed to the sink, which evaluates it later into that slot.
+    template <class LS>
+    LMC_HD void connect(const Scene &sc, int camDepth, int lgtDepth, const LS *ls, const SurfaceVertex *lgtVerts,
+                        const LS &cps, const SurfaceVertex &camVertex, V2 screenPos) {
+        if (SINK::kDeferConnections) {
+            const int n = *np;
+            if (n < cap) {
+                flag[n] = CAND_OCCLUDED;
+                *np = n + 1;
+                sink->emit_connection(sc, camDepth, lgtDepth, n, ls, lgtVerts, cps, camVertex, screenPos, c + n, flag + n);
+            }
+        } else {
+            const SurfaceVertex lv = lgtVerts[lgtDepth];
+            connect_vertex(sc, camDepth, lgtDepth, ls[lgtDepth], lv, cps, camVertex, screenPos, *this);
+        }
+    }
     // clear() right after a visibility query = "clear if that segment is visible"
     LMC_HD void clear() {
         if (pend) {
@@ -63,6 +81,25 @@ struct DeferredList {
             *np = 0;
         }
     }
+};
+
+// Contribution sink bound to ONE reserved slot (a deferred ConnectVertex evaluates into it)
+template <class SINK>
+struct SlotList {
+    SubpathContrib *c;
+    int *flag;
+    SINK *sink;
+    bool pend;
+    Ray pray;
+    float pdist;
+    LMC_HD bool occluded(const Scene &, const Ray &ray, float dist) { pend = true; pray = ray; pdist = dist; return false; }
+    LMC_HD void push(const SubpathContrib &x) {
+        *c = x;
+        *flag = pend ? CAND_PENDING : CAND_VISIBLE;
+        if (pend) sink->emit(pray, pdist, 0, flag);
+        pend = false;
+    }
+    LMC_HD void clear() {}      // ConnectVertex never clears
 };
 
 // what the shadow-ray kernel does with its answer
@@ -111,9 +148,19 @@ struct PropCand {
     SubpathContrib c[2];
 };
 
+// Camera-subpath vertex as a deferred ConnectVertex needs it (device: written once per camera vertex)
+struct alignas(16) CamSnap {
+    BidirPathState cps;
+    int tid; V2 st;          // the camera vertex (shapeInst, st)
+    V2 screenPos;
+    int curIdx;
+    int pad[3];
+};
+
 // Large-step workspace: light subpath states and the contribution candidates.
 template <int MAXD, int MAXC>
 struct GenWork {
+    CamSnap snap[MAXD];
     BidirPathState ls[MAXD];
     int n;
     int flag[MAXC];
@@ -324,8 +371,7 @@ LMC_HD bool gen_stage_camera(const Scene &sc, int minDepth, int maxDepth, PathHe
     }
     for (int lgtDepth = 0; lgtDepth <= maxLgtDepth; lgtDepth++) {
         if (camDepth + lgtDepth + 3 >= minDepth) {
-            const SurfaceVertex lv = lgtVerts[lgtDepth];
-            connect_vertex(sc, camDepth, lgtDepth, ls[lgtDepth], lv, cps, sv, ph.screenPos, contribs);
+            contribs.connect(sc, camDepth, lgtDepth, ls, lgtVerts, cps, sv, ph.screenPos);
         }
     }
     sv.bsdfRndParam.x = rng_uniform(rng); sv.bsdfRndParam.y = rng_uniform(rng);

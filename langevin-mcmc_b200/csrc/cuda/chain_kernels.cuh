@@ -367,14 +367,44 @@ struct ShadowQueue {
     int *count;
     int cap;
 };
+// deferred ConnectVertex work items: (chain, camDepth, lgtDepth, slot)
+struct ConnQueue {
+    int4 *item;
+    int *count;
+    int cap;
+};
 struct WaveQueues {
     RayQueue q[2][4]; // [set][stage - 1]
     ShadowQueue sh;
+    ConnQueue cq;
 };
 
 struct DevShadowSink {
+    static const bool kDeferConnections = true;
     ShadowQueue sh;
+    ConnQueue cq;
+    CamSnap *snaps;      // GenWork::snap of this chain
+    int chain, curIdx;
     const Scene *sc;
+    // ConnectVertex of a large step: snapshot the camera vertex once, queue one work item per light vertex;
+    // k_connect evaluates the pair into the reserved slot.  Queue full: evaluate here.
+    __device__ __forceinline__ void emit_connection(const Scene &scn, int camDepth, int lgtDepth, int slot, const BidirPathState *ls,
+                                                    const SurfaceVertex *lgtVerts, const BidirPathState &cps, const SurfaceVertex &camVertex,
+                                                    V2 screenPos, SubpathContrib *c, int *flag) {
+        const int pos = atomicAdd(cq.count, 1);
+        if (pos < cq.cap) {
+            CamSnap &sn = snaps[camDepth];
+            if (sn.pad[0] != camDepth + 1) {       // first pair of this camera vertex (pad[0] is reset by k_prop_start)
+                sn.cps = cps; sn.tid = camVertex.tid; sn.st = camVertex.st; sn.screenPos = screenPos; sn.curIdx = curIdx;
+                sn.pad[0] = camDepth + 1;
+            }
+            cq.item[pos] = make_int4(chain, camDepth, lgtDepth, slot);
+        } else {
+            SlotList<DevShadowSink> sl; sl.c = c; sl.flag = flag; sl.sink = this; sl.pend = false;
+            const SurfaceVertex lv = lgtVerts[lgtDepth];
+            connect_vertex(scn, camDepth, lgtDepth, ls[lgtDepth], lv, cps, camVertex, screenPos, sl);
+        }
+    }
     __device__ __forceinline__ void emit(const Ray &ray, float dist, int, int *flag) {
         const int pos = atomicAdd(sh.count, 1);
         if (pos < sh.cap) {
@@ -465,6 +495,7 @@ __global__ void __launch_bounds__(LMC_SHADE_BLOCK, LMC_SHADE_MINB) k_prop_start(
                 copy_u4<PathHead>(p.ph, prop.path);
                 path_clear(p.ph);
                 genWork[i].n = 0;
+                for (int d = 0; d < MAXD; d++) genWork[i].snap[d].pad[0] = 0;
                 more = gen_stage_begin(sc, p.ph, p.ts, genWork[i].ls, rng);
             } else {
                 propose_pre_small<MAXD, false>(sc, cur, prop, cs.ch, rng, cs.ss, sides ? sides + i : nullptr, curIdx);
@@ -496,7 +527,8 @@ __device__ __forceinline__ bool shade_entry(const Scene &sc, int chainBase, Chai
     MarkovState<MAXD> &cur = cs.st[p.ts.curIdx], &prop = cs.st[p.ts.curIdx ^ 1];
     uint32_t tab[64];
     Rng rng; rng_from_payload(rng, tab, sc, chainBase + i, p.ts);
-    DevShadowSink sink; sink.sh = wq.sh; sink.sc = &sc;
+    DevShadowSink sink; sink.sh = wq.sh; sink.sc = &sc; sink.cq = wq.cq; sink.chain = i; sink.curIdx = p.ts.curIdx;
+    sink.snaps = genWork ? genWork[i].snap : nullptr;
     DeferredList<DevShadowSink> dl;
     SurfaceVertex sv;
     bool more;
@@ -583,7 +615,10 @@ __global__ void __launch_bounds__(LMC_SHADE_BLOCK, LMC_SHADE_MINB) k_shade(const
 // rays of an iteration, spread over up to 2 * maxDepth - 6 more waves of nearly empty launches).  This
 // kernel finishes them in one launch, one thread per proposal looping "closest hit, next stage" to the end.
 #ifndef LMC_FULL_WAVES
-#define LMC_FULL_WAVES 6
+#define LMC_FULL_WAVES 6          // before the calibration iteration
+#endif
+#ifndef LMC_TAIL_DIV
+#define LMC_TAIL_DIV 16           // measured: 12..32 are equivalent on torus L8 (6..8 waves) and door L12 (16..18)
 #endif
 template <int MAXD>
 __global__ void __launch_bounds__(128) k_shade_tail(const __grid_constant__ Scene sc, int chainBase, ChainRec<MAXD> *states,
@@ -674,6 +709,24 @@ static __global__ void __launch_bounds__(LMC_TRACE_BLOCK, LMC_TRACE_MINB) k_shad
     trace_persistent<true>(sc, top, topCount, src, cursor);
 }
 
+// deferred ConnectVertex of the large steps: one thread per (camera vertex, light vertex) pair
+template <int MAXD>
+__global__ void __launch_bounds__(128) k_connect(const __grid_constant__ Scene sc, ChainRec<MAXD> *states, typename GenWorkT<MAXD>::type *genWork,
+                                                 WaveQueues wq) {
+    int n = *wq.cq.count; if (n > wq.cq.cap) n = wq.cq.cap;
+    const int stride = gridDim.x * blockDim.x;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+        const int4 it = wq.cq.item[idx];
+        typename GenWorkT<MAXD>::type &gw = genWork[it.x];
+        const CamSnap &sn = gw.snap[it.y];
+        DevShadowSink sink; sink.sh = wq.sh; sink.sc = &sc; sink.cq = wq.cq; sink.chain = it.x; sink.curIdx = sn.curIdx; sink.snaps = gw.snap;
+        SlotList<DevShadowSink> sl; sl.c = gw.c + it.w; sl.flag = gw.flag + it.w; sl.sink = &sink; sl.pend = false;
+        const SurfaceVertex lv = states[it.x].cs.st[sn.curIdx ^ 1].path.lgt[it.z];
+        SurfaceVertex cv; cv.tid = sn.tid; cv.st = sn.st;
+        connect_vertex(sc, it.y, it.z, gw.ls[it.z], lv, sn.cps, cv, sn.screenPos, sl);
+    }
+}
+
 // POST part of the mutation once every candidate is resolved
 template <int MAXD, int LARGE>
 __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_prop_post(const __grid_constant__ Scene sc, RunParams rp, int chainBase, ChainRec<MAXD> *states,
@@ -760,6 +813,11 @@ struct WaveCfg {
     H2mcSide *padSide;     // scratch Hessian for the padding threads of the H2MC gradient kernel
     int wavefront;         // 1: per-vertex wavefront proposal; 0: monolithic k_wave_propose (A/B)
     int smCount;
+    // Number of full waves before the tail kernel takes over: calibrated once per lmc_chains_begin from the
+    // measured ray counts of one steady-state iteration (0 = not calibrated yet).  Pure scheduling: results do
+    // not depend on it.
+    int *fullWavesTuned;
+    long long *iterationsSinceBegin;
 };
 #define LMC_DECLARE_CHAIN(MAXD) \
     size_t chain_state_bytes_##MAXD(); \
@@ -844,7 +902,12 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             pt.mark("prop_start");
             // a path has at most maxDepth - 1 light-subpath and maxDepth camera-subpath vertices
             const int numWaves = 2 * maxDepth - 1;
-            const int fullWaves = numWaves < LMC_FULL_WAVES ? numWaves : LMC_FULL_WAVES;
+            // calibration iteration (the 4th after begin: step mix and path lengths have settled): all waves are
+            // full waves and the host reads the number of rays left after each one
+            const bool calibrate = *wc.fullWavesTuned == 0 && *wc.iterationsSinceBegin == 3;
+            int fullWaves = *wc.fullWavesTuned > 0 ? *wc.fullWavesTuned : LMC_FULL_WAVES;
+            if (calibrate || fullWaves > numWaves) fullWaves = numWaves;
+            int calibrated = numWaves;
             for (int w = 0; w < fullWaves; w++) {
                 const int cur = w & 1;
                 k_trace<<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, wc.wq, cur, wc.queueCounts + 16 + w);
@@ -858,6 +921,18 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
                 *launches += 3;
                 e = cudaMemsetAsync(wc.queueCounts + 4 * cur, 0, 4 * sizeof(int), st);
                 if (e != cudaSuccess) return e;
+                if (calibrate && calibrated == numWaves) {
+                    int left[4];
+                    e = cudaMemcpyAsync(left, wc.queueCounts + 4 * (cur ^ 1), sizeof(left), cudaMemcpyDeviceToHost, st);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                    if (e != cudaSuccess) return e;
+                    // hand over to the tail kernel once less than 1/LMC_TAIL_DIV of the chains still have a ray in flight
+                    if ((long long)left[0] + left[1] + left[2] + left[3] < (long long)n / LMC_TAIL_DIV && w + 1 >= 3) calibrated = w + 1;
+                }
+            }
+            if (calibrate) {
+                *wc.fullWavesTuned = calibrated;
+                if (pt.on) fprintf(stderr, "[lmc phase] calibrated: %d full waves of %d, then the tail kernel\n", calibrated, numWaves);
             }
             pt.mark("waves (trace + shade)");
             if (fullWaves < numWaves) {
@@ -865,6 +940,9 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
                 *launches += 1;
             }
             pt.mark("tail");
+            k_connect<MAXD><<<G, 128, 0, st>>>(sc, states, genWork, wc.wq);
+            *launches += 1;
+            pt.mark("connect");
             k_shadow<<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, wc.wq.sh, wc.queueCounts + 16 + 63);
             k_prop_post<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.small_.list, wl.small_.count, wl);
             k_prop_post<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.large, wl.largeCount, wl);
@@ -887,6 +965,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         else k_wave_finish<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides, wl);
         *launches += 4;
         pt.mark("finish (+ begin)");
+        *wc.iterationsSinceBegin += 1;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

@@ -107,6 +107,7 @@ struct lmc_ctx {
     H2mcSide *sides = nullptr; int sidesCap = 0;
     int listCap = 0;
     WaveCfg wc{};                   // wavefront queues + large-step workspace
+    int fullWavesTuned = 0; long long iterationsSinceBegin = 0;
     void *queueMem = nullptr; int queueCap = 0;
     uint64_t launches = 0;
     double lastMs = 0.0;
@@ -149,7 +150,8 @@ int chains_begin(lmc_ctx *c) {
         // camera-subpath queue of that kind; a shadow queue of 4n segments; 9 counters
         const size_t nn = (size_t)n, shCap = 4 * nn;
         const size_t perBuf = nn * (sizeof(int) + sizeof(PayloadLite) + sizeof(float4)) + 64;
-        const size_t bytes = 4 * perBuf + shCap * (2 * sizeof(float4) + sizeof(int *)) + 1024;
+        const size_t cqCap = 4 * nn;
+        const size_t bytes = 4 * perBuf + shCap * (2 * sizeof(float4) + sizeof(int *)) + cqCap * sizeof(int4) + 1024;
         CK(cudaMalloc(&c->queueMem, bytes));
         char *p = (char *)c->queueMem;
         auto take = [&](size_t b) { char *r = p; p += (b + 15) & ~(size_t)15; return r; };
@@ -165,9 +167,12 @@ int chains_begin(lmc_ctx *c) {
         }
         c->wc.wq.sh.org = (float4 *)take(shCap * sizeof(float4)); c->wc.wq.sh.dir = (float4 *)take(shCap * sizeof(float4));
         c->wc.wq.sh.flag = (int **)take(shCap * sizeof(int *));
+        c->wc.wq.cq.item = (int4 *)take(cqCap * sizeof(int4));
+        c->wc.wq.cq.cap = (int)cqCap;
         c->wc.queueCounts = (int *)take(LMC_NCOUNTERS * sizeof(int));
         for (int s = 0; s < 2; s++) for (int k = 0; k < 4; k++) c->wc.wq.q[s][k].count = c->wc.queueCounts + 4 * s + k;
         c->wc.wq.sh.count = c->wc.queueCounts + 8;
+        c->wc.wq.cq.count = c->wc.queueCounts + 12;
         c->wc.wq.sh.cap = (int)shCap;
         CK(cudaMemsetAsync(c->wc.queueCounts, 0, LMC_NCOUNTERS * sizeof(int), c->stream));
         const size_t gwBytes = (d == 4 ? gen_work_bytes_4() : (d == 8 ? gen_work_bytes_8() : gen_work_bytes_12())) * nn;
@@ -183,6 +188,8 @@ int chains_begin(lmc_ctx *c) {
         CK(cudaMemsetAsync(c->sides, 0, sizeof(H2mcSide) * (size_t)n, c->stream));
         if (!c->wc.padSide) { CK(cudaMalloc((void **)&c->wc.padSide, sizeof(H2mcSide))); CK(cudaMemsetAsync(c->wc.padSide, 0, sizeof(H2mcSide), c->stream)); }
     }
+    c->fullWavesTuned = 0; c->iterationsSinceBegin = 0;
+    c->wc.fullWavesTuned = &c->fullWavesTuned; c->wc.iterationsSinceBegin = &c->iterationsSinceBegin;
     c->launches++;
     CK(d == 4 ? launch_chain_init_4(c->stream, st, n, c->desc.chain_base, c->initLs)
               : (d == 8 ? launch_chain_init_8(c->stream, st, n, c->desc.chain_base, c->initLs)
