@@ -805,13 +805,16 @@ __global__ void k_chain_stats(const ChainRec<MAXD> *states, int n, unsigned long
 
 
 // launchers (defined by LMC_INSTANTIATE_CHAIN in chain_inst_*.cu)
+#ifndef LMC_WAVEFRONT_MIN_CHAINS
+#define LMC_WAVEFRONT_MIN_CHAINS 393216     // measured crossover on B200 (torus, maxdepth 8): 2^18 -> monolithic, 2^19 -> wavefront
+#endif
 #define LMC_NCOUNTERS 80        // 9 counters + up to 64 wave cursors (maxdepth <= 12: 23 waves + shadow)
 struct WaveCfg {
     WaveQueues wq;
     void *genWork;
     int *queueCounts;      // 2 x 4 ray-queue counters, the shadow counter, then one traversal cursor per wave (LMC_NCOUNTERS ints)
     H2mcSide *padSide;     // scratch Hessian for the padding threads of the H2MC gradient kernel
-    int wavefront;         // 1: per-vertex wavefront proposal; 0: monolithic k_wave_propose (A/B)
+    int wavefront;         // 1: per-vertex wavefront proposal; 0: monolithic k_wave_propose; -1: by chain count
     int smCount;
     // Number of full waves before the tail kernel takes over: calibrated once per lmc_chains_begin from the
     // measured ray counts of one steady-state iteration (0 = not calibrated yet).  Pure scheduling: results do
@@ -869,6 +872,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
     const int GTmax = (n + LMC_TRACE_BLOCK - 1) / LMC_TRACE_BLOCK;
     const int GT = GTmax < sms * LMC_TRACE_MINB ? GTmax : sms * LMC_TRACE_MINB;     // persistent traversal warps
     const int maxDepth = sc.opt.maxDepth;
+    const bool useWavefront = wc.wavefront < 0 ? (n >= LMC_WAVEFRONT_MIN_CHAINS) : (wc.wavefront != 0);
     const int GALIGN = LMC_GRAD_BLOCK;          // gradient lists: class-pure blocks
     const int GG = (n + LMC_NKEYS * (GALIGN - 1) + LMC_GRAD_BLOCK - 1) / LMC_GRAD_BLOCK;   // gradient grid over the (padded) list
     cudaError_t e = cudaMemsetAsync(wl.largeCount, 0, sizeof(int), st);
@@ -889,7 +893,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide);
         *launches += 3;
         pt.mark("sort + grad(cur)");
-        if (!wc.wavefront) {
+        if (!useWavefront) {
             k_wave_propose<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.small_.list, wl.small_.count, wl, sides);
             k_wave_propose<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl.large, wl.largeCount, wl, sides);
             *launches += 2;

@@ -388,8 +388,11 @@ int lmc_create(const lmc_scene *scene, int32_t device, lmc_ctx **out) {
     }
     c->filmOwned = true;
     {
-        const char *wf = getenv("LMC_WAVEFRONT");      // A/B switch for profiling; results are identical
-        c->wc.wavefront = (wf && wf[0] == '0') ? 0 : 1;
+        // Both device forms of the proposal phase give identical chains; which one is faster depends on the
+        // chain count (tools/smalln.sh: the per-vertex wavefront wins from ~4e5 chains up, below that its ~50
+        // small launches per iteration cost more than its SIMD efficiency gains).  LMC_WAVEFRONT=0/1 forces one.
+        const char *wf = getenv("LMC_WAVEFRONT");
+        c->wc.wavefront = wf ? ((wf[0] == '0') ? 0 : 1) : -1;
         cudaDeviceProp prop;
         c->wc.smCount = (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ? prop.multiProcessorCount : 148;
     }

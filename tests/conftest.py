@@ -13,6 +13,13 @@ SCENES = os.path.join(ROOT, "scenes")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+# The library picks the device form of the proposal phase by chain count (per-vertex wavefront from ~4e5
+# chains, monolithic kernel below); the parity tests run small jobs, so they force the wavefront -- the path
+# the full-size configurations use.  test_cuda_per_vertex_wavefront_equals_monolithic_propose covers the other
+# form and test_cuda_proposal_path_is_chosen_by_chain_count the automatic choice.
+os.environ.setdefault("LMC_WAVEFRONT", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

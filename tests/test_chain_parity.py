@@ -217,3 +217,27 @@ def test_cuda_full_size_other_configs(lmc, torus_xml, door_xml, scene, opts, ste
     assert np.allclose(film, film2, rtol=1e-3, atol=1e-4 * max(1.0, float(film.max())))
     assert ((t_small[:, 0] & 3) == 0).all()
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_cuda_proposal_path_is_chosen_by_chain_count(lmc, torus_xml, monkeypatch):
+    """Without LMC_WAVEFRONT the library runs small jobs through the monolithic proposal kernel (about 11 launches
+    per iteration) and large ones through the per-vertex wavefront (about 50); both agree with a forced run."""
+    sc = lmc.ParseScene(torus_xml)
+    sc.options["maxdepth"] = 8
+    chains, steps = 4096, 8
+    norm, init_ls = lmc.MLTInit(sc, 100000, chains, 32)
+    runs = {}
+    for mode in ("auto", "1"):
+        if mode == "auto":
+            monkeypatch.delenv("LMC_WAVEFRONT", raising=False)
+        else:
+            monkeypatch.setenv("LMC_WAVEFRONT", mode)
+        ctx = lmc.ChainContext(sc, 0)
+        ctx.begin(chains, norm, init_ls, samples_per_chain=steps)
+        l0 = ctx.stats()["kernel_launches"]
+        trace, _ = ctx.run(steps, trace=True)
+        runs[mode] = (trace, (ctx.stats()["kernel_launches"] - l0) / steps)
+        ctx.close()
+    assert np.array_equal(runs["auto"][0], runs["1"][0])
+    assert runs["auto"][1] < 15 < runs["1"][1]
