@@ -1,6 +1,14 @@
-// chain_kernels.cuh -- the persistent-chain kernels (one CUDA thread = one Markov chain) and their
-// host launchers.  Instantiated once per MAXD in chain_inst_<MAXD>.cu so the three variants build
-// in parallel.
+// chain_kernels.cuh -- the kernels of the chain loop (src/mlt.cpp:91-170) and their host launcher.
+//
+//   bookkeeping phases   k_wave_begin, k_wave_finish<THEN_BEGIN>, k_prop_start, k_prop_post   (thread = chain)
+//   work lists           k_sort_scan, k_sort_scatter (counting sort by path class / screen tile)
+//   gradient / Hessian   k_wave_grad<ORDER> (class-pure blocks in lockstep)
+//   proposal, per-vertex wavefront (>= ~4e5 chains):  k_trace / k_shadow (trace_kernels.cuh), k_shade<stage>,
+//                        k_shade_tail, k_connect        (thread = pending ray / queue entry)
+//   proposal, monolithic (small jobs):                k_wave_propose<ONLY>
+//   set-up               k_chain_init, k_mlt_init_paths; k_chain_stats
+// launch_chain_run_t() is one lmc_run_chains call.  Instantiated once per MAXD in chain_inst_<MAXD>.cu so
+// the three variants build in parallel.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstddef>

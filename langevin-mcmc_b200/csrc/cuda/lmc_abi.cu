@@ -1,11 +1,9 @@
 // lmc_abi.cu -- the C ABI (include/lmc/lmc_abi.h) and the sm_100a kernels behind it.
 //
-// Kernels (one CUDA thread = one Markov chain; DESIGN.md "Kernels"):
-//   k_chain_init   chain_state_init for every chain                     (src/mlt.cpp:61-90)
-//   k_chain_run    K iterations of the chain loop per launch            (src/mlt.cpp:91-170 + mutations + path replay)
-//   k_chain_stats  reduce per-chain counters
-//   k_bvh_probe    closest-hit / any-hit harness                        (src/scene.cpp:106-149)
-//   k_eval_batch   log-luminance + PSS gradient of serialized paths     (src/path.h:121-125 ABI)
+// The chain-loop kernels live in chain_kernels.cuh / trace_kernels.cuh (DESIGN.md "Kernels"); here:
+//   k_bvh_probe         closest-hit / any-hit harness                       (src/scene.cpp:106-149)
+//   k_eval_batch[_hess] log-luminance + PSS gradient (+ Hessian) of serialized paths   (src/path.h:121-125 ABI)
+//   k_direct_lighting   DirectLighting(scene, buffer), one thread per tile  (src/direct.cpp:4-54)
 // Host code here is glue only: device memory, launches, error translation.  No CPU fallback.
 #include <cuda_runtime.h>
 #include <cstdio>
