@@ -829,6 +829,10 @@ struct WaveCfg {
     // not depend on it.
     int *fullWavesTuned;
     long long *iterationsSinceBegin;
+    // Small-step and large-step chains are disjoint, so their start / post kernels (DRAM-latency bound, < 2 %
+    // issue utilisation each) run side by side: the large-step one goes to this auxiliary stream.
+    cudaStream_t aux;
+    cudaEvent_t evFork, evJoin;
 };
 #define LMC_DECLARE_CHAIN(MAXD) \
     size_t chain_state_bytes_##MAXD(); \
@@ -908,8 +912,12 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         } else {
             e = cudaMemsetAsync(wc.queueCounts, 0, LMC_NCOUNTERS * sizeof(int), st);
             if (e != cudaSuccess) return e;
+            cudaStream_t sa = wc.aux ? wc.aux : st;
+            if (wc.aux) { cudaEventRecord(wc.evFork, st); cudaStreamWaitEvent(wc.aux, wc.evFork, 0); }
+            k_prop_start<MAXD, 1><<<GS, LMC_SHADE_BLOCK, 0, sa>>>(sc, chainBase, states, genWork, wl.large, wl.largeCount, wc.wq, sides);
+            if (wc.aux) cudaEventRecord(wc.evJoin, wc.aux);
             k_prop_start<MAXD, 0><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wl.small_.list, wl.small_.count, wc.wq, sides);
-            k_prop_start<MAXD, 1><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wl.large, wl.largeCount, wc.wq, sides);
+            if (wc.aux) cudaStreamWaitEvent(st, wc.evJoin, 0);
             *launches += 2;
             pt.mark("prop_start");
             // a path has at most maxDepth - 1 light-subpath and maxDepth camera-subpath vertices
@@ -956,8 +964,11 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             *launches += 1;
             pt.mark("connect");
             k_shadow<<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, wc.wq.sh, wc.queueCounts + 16 + 63);
+            if (wc.aux) { cudaEventRecord(wc.evFork, st); cudaStreamWaitEvent(wc.aux, wc.evFork, 0); }
+            k_prop_post<MAXD, 1><<<G, B, 0, sa>>>(sc, rp, chainBase, states, genWork, wl.large, wl.largeCount, wl);
+            if (wc.aux) cudaEventRecord(wc.evJoin, wc.aux);
             k_prop_post<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.small_.list, wl.small_.count, wl);
-            k_prop_post<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.large, wl.largeCount, wl);
+            if (wc.aux) cudaStreamWaitEvent(st, wc.evJoin, 0);
             *launches += 3;
             pt.mark("shadow + post");
         }

@@ -389,6 +389,13 @@ int lmc_create(const lmc_scene *scene, int32_t device, lmc_ctx **out) {
         // Both device forms of the proposal phase give identical chains; which one is faster depends on the
         // chain count (tools/smalln.sh: the per-vertex wavefront wins from ~4e5 chains up, below that its ~50
         // small launches per iteration cost more than its SIMD efficiency gains).  LMC_WAVEFRONT=0/1 forces one.
+        if (!getenv("LMC_NO_AUX_STREAM") &&
+            (cudaStreamCreateWithFlags(&c->wc.aux, cudaStreamNonBlocking) != cudaSuccess ||
+             cudaEventCreateWithFlags(&c->wc.evFork, cudaEventDisableTiming) != cudaSuccess ||
+             cudaEventCreateWithFlags(&c->wc.evJoin, cudaEventDisableTiming) != cudaSuccess)) {
+            lmc_destroy(c);
+            return fail(LMC_ERR_CUDA, "stream / event creation failed");
+        }
         const char *wf = getenv("LMC_WAVEFRONT");
         c->wc.wavefront = wf ? ((wf[0] == '0') ? 0 : 1) : -1;
         cudaDeviceProp prop;
@@ -411,6 +418,9 @@ void lmc_destroy(lmc_ctx *c) {
     if (c->queueMem) cudaFree(c->queueMem);
     if (c->wc.genWork) cudaFree(c->wc.genWork);
     if (c->wc.padSide) cudaFree(c->wc.padSide);
+    if (c->wc.aux) cudaStreamDestroy(c->wc.aux);
+    if (c->wc.evFork) cudaEventDestroy(c->wc.evFork);
+    if (c->wc.evJoin) cudaEventDestroy(c->wc.evJoin);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     delete c;
