@@ -372,6 +372,8 @@ struct ShadowQueue {
     float4 *org;      // xyz, w = dist
     float4 *dir;
     int **flag;       // candidate flag to resolve
+    int *chain;       // small steps: the chain whose (only) candidate this is -- its POST part runs right after the
+                      // flag is resolved; -1 for large-step candidates (k_prop_post<large> handles those)
     int *count;
     int cap;
 };
@@ -385,6 +387,8 @@ struct WaveQueues {
     RayQueue q[2][4]; // [set][stage - 1]
     ShadowQueue sh;
     ConnQueue cq;
+    RunParams rp;          // for the POST part of small steps (filled per lmc_run_chains call)
+    SortList propGrad;
 };
 
 struct DevShadowSink {
@@ -393,6 +397,7 @@ struct DevShadowSink {
     ConnQueue cq;
     CamSnap *snaps;      // GenWork::snap of this chain
     int chain, curIdx;
+    int postChain;       // = chain for small-step candidates, -1 for large steps
     const Scene *sc;
     // ConnectVertex of a large step: snapshot the camera vertex once, queue one work item per light vertex;
     // k_connect evaluates the pair into the reserved slot.  Queue full: evaluate here.
@@ -419,6 +424,7 @@ struct DevShadowSink {
             sh.org[pos] = make_float4(ray.org.x, ray.org.y, ray.org.z, dist);
             sh.dir[pos] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, 0.0f);
             sh.flag[pos] = flag;
+            sh.chain[pos] = postChain;
         } else {
             *flag = cand_resolve(*flag, scene_occluded(*sc, ray, dist));    // queue full: resolve on the spot
         }
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(LMC_SHADE_BLOCK, LMC_SHADE_MINB) k_prop_start(
             }
             rng_to_payload(rng, p.ts);
             copy_u4<PathHead>(prop.path, p.ph);        // the whole head now; later stages update single fields
-            if (!more) rng_close(rng, cs);
+            if (!more) { rng_close(rng, cs); if (!LARGE) post_small_now(sc, wq, cs, i); }
         }
         if (LARGE) {
             ray_push(wq.q[0][TS_G_LGT - 1], more, i, p);
@@ -523,6 +529,24 @@ __global__ void __launch_bounds__(LMC_SHADE_BLOCK, LMC_SHADE_MINB) k_prop_start(
             ray_push(wq.q[0][TS_P_CAM - 1], more && p.ts.stage == TS_P_CAM, i, p);
         }
     }
+}
+
+// POST part of a small step (mutation.h propose_post_small) + its proposal-gradient key.  Runs as soon as the
+// chain's candidate contribution is resolved: in the stage that ends the proposal when no shadow ray is
+// pending, else in k_shadow right after the ray has been traced.
+template <int MAXD>
+__device__ __forceinline__ void post_small_now(const Scene &sc, const WaveQueues &wq, ChainState<MAXD> &cs, int i) {
+    MarkovState<MAXD> &cur = cs.st[cs.curIdx], &prop = cs.st[cs.curIdx ^ 1];
+    cs.pc.n = deferred_compact(cs.pc.c, cs.pc.flag, cs.pc.n);
+    propose_post_small(sc, wq.rp, cur, prop, cs.ss, cs.pc);
+    // key = the class the evaluator will see (path.camDepth / path.lgtDepth): blocks must be class-pure
+    sort_key_set(wq.propGrad, i, cs.ss.needPropGrad ? class_key(prop.path.camDepth, prop.path.lgtDepth, 0) : -1);
+}
+template <int MAXD>
+__device__ __forceinline__ bool small_candidate_pending(const ChainState<MAXD> &cs) {
+    bool pending = false;
+    for (int k = 0; k < cs.pc.n; k++) pending = pending || ((cs.pc.flag[k] & CAND_PENDING) != 0);
+    return pending;
 }
 
 // One stage of one proposal: the statements between two ray queries for the chain `i` whose pending ray
@@ -537,6 +561,7 @@ __device__ __forceinline__ bool shade_entry(const Scene &sc, int chainBase, Chai
     Rng rng; rng_from_payload(rng, tab, sc, chainBase + i, p.ts);
     DevShadowSink sink; sink.sh = wq.sh; sink.sc = &sc; sink.cq = wq.cq; sink.chain = i; sink.curIdx = p.ts.curIdx;
     sink.snaps = genWork ? genWork[i].snap : nullptr;
+    sink.postChain = (STAGE == TS_P_LGT || STAGE == TS_P_CAM) ? i : -1;
     DeferredList<DevShadowSink> dl;
     SurfaceVertex sv;
     bool more;
@@ -581,6 +606,7 @@ __device__ __forceinline__ bool shade_entry(const Scene &sc, int chainBase, Chai
     if (!more) {      // leaving the wavefront: counters, screen position and RNG state back to the record
         prop.path.nCam = p.ph.nCam; prop.path.nLgt = p.ph.nLgt; prop.path.screenPos = p.ph.screenPos;
         rng_close(rng, cs);
+        if ((STAGE == TS_P_LGT || STAGE == TS_P_CAM) && !small_candidate_pending(cs)) post_small_now(sc, wq, cs, i);
     }
     return more;
 }
@@ -679,18 +705,21 @@ struct ClosestSrc {
     }
 };
 // any hit for the queued connection segments: Occluded(scene, ray, dist), src/scene.cpp:128-149
+template <int MAXD>
 struct ShadowSrc {
-    ShadowQueue sh; int n;
+    const Scene *sc; const WaveQueues *wq; ChainRec<MAXD> *states; int n;
     __device__ __forceinline__ int total() const { return n; }
     __device__ __forceinline__ void load(int idx, Ray &ray, float &minT, float &maxT) const {
-        const float4 o = sh.org[idx], d = sh.dir[idx];
+        const float4 o = wq->sh.org[idx], d = wq->sh.dir[idx];
         ray.org = mk3(o.x, o.y, o.z); ray.dir = mk3(d.x, d.y, d.z);
         minT = LMC_ISECT_EPS;
         maxT = (o.w == dm_inf()) ? dm_inf() : (1.0f - LMC_SHADOW_EPS) * o.w;
     }
     __device__ __forceinline__ void store(int idx, const Hit &h) const {
-        int *f = sh.flag[idx];
+        int *f = wq->sh.flag[idx];
         *f = cand_resolve(*f, h.tid >= 0);
+        const int chain = wq->sh.chain[idx];
+        if (chain >= 0) post_small_now(*sc, *wq, states[chain].cs, chain);      // a small step has exactly one pending candidate
     }
 };
 #ifndef LMC_TRACE_MINB
@@ -707,11 +736,14 @@ static __global__ void __launch_bounds__(LMC_TRACE_BLOCK, LMC_TRACE_MINB) k_trac
     tma_stage_nodes(top, sc.nodes, topCount, &bar);
     trace_persistent<false>(sc, top, topCount, src, cursor);
 }
-static __global__ void __launch_bounds__(LMC_TRACE_BLOCK, LMC_TRACE_MINB) k_shadow(const __grid_constant__ Scene sc, ShadowQueue sh, int *cursor) {
+template <int MAXD>
+__global__ void __launch_bounds__(LMC_TRACE_BLOCK, LMC_TRACE_MINB) k_shadow(const __grid_constant__ Scene sc, ChainRec<MAXD> *states,
+                                                                          const __grid_constant__ WaveQueues wq, int *cursor) {
     __shared__ __align__(128) BvhNode top[LMC_TOP_NODES];
     __shared__ uint64_t bar;
     const int topCount = sc.numNodes < LMC_TOP_NODES ? sc.numNodes : LMC_TOP_NODES;
-    ShadowSrc src; src.sh = sh; src.n = *sh.count; if (src.n > sh.cap) src.n = sh.cap;
+    ShadowSrc<MAXD> src; src.sc = &sc; src.wq = &wq; src.states = states;
+    src.n = *wq.sh.count; if (src.n > wq.sh.cap) src.n = wq.sh.cap;
     if ((long long)blockIdx.x * LMC_TRACE_BLOCK >= (long long)src.n) return;
     tma_stage_nodes(top, sc.nodes, topCount, &bar);
     trace_persistent<true>(sc, top, topCount, src, cursor);
@@ -728,6 +760,7 @@ __global__ void __launch_bounds__(128) k_connect(const __grid_constant__ Scene s
         typename GenWorkT<MAXD>::type &gw = genWork[it.x];
         const CamSnap &sn = gw.snap[it.y];
         DevShadowSink sink; sink.sh = wq.sh; sink.sc = &sc; sink.cq = wq.cq; sink.chain = it.x; sink.curIdx = sn.curIdx; sink.snaps = gw.snap;
+        sink.postChain = -1;         // large-step candidate: k_prop_post<large> finishes the proposal
         SlotList<DevShadowSink> sl; sl.c = gw.c + it.w; sl.flag = gw.flag + it.w; sl.sink = &sink; sl.pend = false;
         const SurfaceVertex lv = states[it.x].cs.st[sn.curIdx ^ 1].path.lgt[it.z];
         SurfaceVertex cv; cv.tid = sn.tid; cv.st = sn.st;
@@ -875,6 +908,8 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
                                int n, long long numSteps, float *film, unsigned char *trace, float *aTrace,
                                const WaveLists &wl, const WaveCfg &wc, unsigned long long *launches, H2mcSide *sides) {
     typedef typename GenWorkT<MAXD>::type GW;
+    WaveQueues wq = wc.wq;       // + what the POST part of the small steps needs
+    wq.rp = rp; wq.propGrad = wl.propGrad;
     ChainRec<MAXD> *states = (ChainRec<MAXD> *)states_;
     GW *genWork = (GW *)wc.genWork;
     const int B = LMC_CHAIN_BLOCK, G = (n + B - 1) / B;
@@ -914,9 +949,9 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             if (e != cudaSuccess) return e;
             cudaStream_t sa = wc.aux ? wc.aux : st;
             if (wc.aux) { cudaEventRecord(wc.evFork, st); cudaStreamWaitEvent(wc.aux, wc.evFork, 0); }
-            k_prop_start<MAXD, 1><<<GS, LMC_SHADE_BLOCK, 0, sa>>>(sc, chainBase, states, genWork, wl.large, wl.largeCount, wc.wq, sides);
+            k_prop_start<MAXD, 1><<<GS, LMC_SHADE_BLOCK, 0, sa>>>(sc, chainBase, states, genWork, wl.large, wl.largeCount, wq, sides);
             if (wc.aux) cudaEventRecord(wc.evJoin, wc.aux);
-            k_prop_start<MAXD, 0><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wl.small_.list, wl.small_.count, wc.wq, sides);
+            k_prop_start<MAXD, 0><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wl.small_.list, wl.small_.count, wq, sides);
             if (wc.aux) cudaStreamWaitEvent(st, wc.evJoin, 0);
             *launches += 2;
             pt.mark("prop_start");
@@ -930,14 +965,14 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             int calibrated = numWaves;
             for (int w = 0; w < fullWaves; w++) {
                 const int cur = w & 1;
-                k_trace<<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, wc.wq, cur, wc.queueCounts + 16 + w);
+                k_trace<<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, wq, cur, wc.queueCounts + 16 + w);
                 if (w < maxDepth - 1) {
-                    k_shade<MAXD, TS_P_LGT><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
-                    k_shade<MAXD, TS_G_LGT><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
+                    k_shade<MAXD, TS_P_LGT><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wq, cur);
+                    k_shade<MAXD, TS_G_LGT><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wq, cur);
                     *launches += 2;
                 }
-                k_shade<MAXD, TS_P_CAM><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
-                k_shade<MAXD, TS_G_CAM><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wc.wq, cur);
+                k_shade<MAXD, TS_P_CAM><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wq, cur);
+                k_shade<MAXD, TS_G_CAM><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wq, cur);
                 *launches += 3;
                 e = cudaMemsetAsync(wc.queueCounts + 4 * cur, 0, 4 * sizeof(int), st);
                 if (e != cudaSuccess) return e;
@@ -956,20 +991,17 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             }
             pt.mark("waves (trace + shade)");
             if (fullWaves < numWaves) {
-                k_shade_tail<MAXD><<<G, 128, 0, st>>>(sc, chainBase, states, genWork, wc.wq, fullWaves & 1);
+                k_shade_tail<MAXD><<<G, 128, 0, st>>>(sc, chainBase, states, genWork, wq, fullWaves & 1);
                 *launches += 1;
             }
             pt.mark("tail");
-            k_connect<MAXD><<<G, 128, 0, st>>>(sc, states, genWork, wc.wq);
+            k_connect<MAXD><<<G, 128, 0, st>>>(sc, states, genWork, wq);
             *launches += 1;
             pt.mark("connect");
-            k_shadow<<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, wc.wq.sh, wc.queueCounts + 16 + 63);
-            if (wc.aux) { cudaEventRecord(wc.evFork, st); cudaStreamWaitEvent(wc.aux, wc.evFork, 0); }
-            k_prop_post<MAXD, 1><<<G, B, 0, sa>>>(sc, rp, chainBase, states, genWork, wl.large, wl.largeCount, wl);
-            if (wc.aux) cudaEventRecord(wc.evJoin, wc.aux);
-            k_prop_post<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.small_.list, wl.small_.count, wl);
-            if (wc.aux) cudaStreamWaitEvent(st, wc.evJoin, 0);
-            *launches += 3;
+            k_shadow<MAXD><<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, states, wq, wc.queueCounts + 16 + 63);
+            // (the POST part of the small steps ran where their candidate was resolved: k_shade / k_shadow)
+            k_prop_post<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.large, wl.largeCount, wl);
+            *launches += 2;
             pt.mark("shadow + post");
         }
         k_sort_scan<<<1, 1024, 0, st>>>(wl.propGrad, wl.propGrad, 1, GALIGN, GALIGN);

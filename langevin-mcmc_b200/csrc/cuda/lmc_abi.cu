@@ -149,7 +149,7 @@ int chains_begin(lmc_ctx *c) {
         const size_t nn = (size_t)n, shCap = 4 * nn;
         const size_t perBuf = nn * (sizeof(int) + sizeof(PayloadLite) + sizeof(float4)) + 64;
         const size_t cqCap = 4 * nn;
-        const size_t bytes = 4 * perBuf + shCap * (2 * sizeof(float4) + sizeof(int *)) + cqCap * sizeof(int4) + 1024;
+        const size_t bytes = 4 * perBuf + shCap * (2 * sizeof(float4) + sizeof(int *) + sizeof(int)) + cqCap * sizeof(int4) + 1024;
         CK(cudaMalloc(&c->queueMem, bytes));
         char *p = (char *)c->queueMem;
         auto take = [&](size_t b) { char *r = p; p += (b + 15) & ~(size_t)15; return r; };
@@ -165,6 +165,7 @@ int chains_begin(lmc_ctx *c) {
         }
         c->wc.wq.sh.org = (float4 *)take(shCap * sizeof(float4)); c->wc.wq.sh.dir = (float4 *)take(shCap * sizeof(float4));
         c->wc.wq.sh.flag = (int **)take(shCap * sizeof(int *));
+        c->wc.wq.sh.chain = (int *)take(shCap * sizeof(int));
         c->wc.wq.cq.item = (int4 *)take(cqCap * sizeof(int4));
         c->wc.wq.cq.cap = (int)cqCap;
         c->wc.queueCounts = (int *)take(LMC_NCOUNTERS * sizeof(int));
