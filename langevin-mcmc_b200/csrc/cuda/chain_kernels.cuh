@@ -1,6 +1,6 @@
 // chain_kernels.cuh -- the kernels of the chain loop (src/mlt.cpp:91-170) and their host launcher.
 //
-//   bookkeeping phases   k_wave_begin, k_wave_finish<THEN_BEGIN>, k_prop_start, k_prop_post   (thread = chain)
+//   bookkeeping phases   k_wave_begin, k_wave_finish<THEN_BEGIN>, k_prop_start, k_prop_post_large   (thread = chain)
 //   work lists           k_sort_scan, k_sort_scatter (counting sort by path class / screen tile)
 //   gradient / Hessian   k_wave_grad<ORDER> (class-pure blocks in lockstep)
 //   proposal, per-vertex wavefront (>= ~4e5 chains):  k_trace / k_shadow (trace_kernels.cuh), k_shade<stage>,
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_finish(const __grid_co
 //                set and the shadow rays of candidate contributions into the shadow queue
 // and after the last wave
 //   k_shadow     any-hit for all queued connection segments -> candidate flags
-//   k_prop_post  contribution choice / acceptance bookkeeping (mutation.h propose_post_*)
+//   k_prop_post_large  contribution choice / acceptance bookkeeping of the large steps (small steps: post_small_now)
 //
 // A queue entry carries the whole between-stage state of its proposal (TraceState + PathHead =
 // LMC_PAYLOAD_U4 x 16 B) as chunk-major SoA, payload[chunk * cap + slot], so a warp moves it with
@@ -373,7 +373,7 @@ struct ShadowQueue {
     float4 *dir;
     int **flag;       // candidate flag to resolve
     int *chain;       // small steps: the chain whose (only) candidate this is -- its POST part runs right after the
-                      // flag is resolved; -1 for large-step candidates (k_prop_post<large> handles those)
+                      // flag is resolved; -1 for large-step candidates (k_prop_post_large handles those)
     int *count;
     int cap;
 };
@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(128) k_connect(const __grid_constant__ Scene s
         typename GenWorkT<MAXD>::type &gw = genWork[it.x];
         const CamSnap &sn = gw.snap[it.y];
         DevShadowSink sink; sink.sh = wq.sh; sink.sc = &sc; sink.cq = wq.cq; sink.chain = it.x; sink.curIdx = sn.curIdx; sink.snaps = gw.snap;
-        sink.postChain = -1;         // large-step candidate: k_prop_post<large> finishes the proposal
+        sink.postChain = -1;         // large-step candidate: k_prop_post_large finishes the proposal
         SlotList<DevShadowSink> sl; sl.c = gw.c + it.w; sl.flag = gw.flag + it.w; sl.sink = &sink; sl.pend = false;
         const SurfaceVertex lv = states[it.x].cs.st[sn.curIdx ^ 1].path.lgt[it.z];
         SurfaceVertex cv; cv.tid = sn.tid; cv.st = sn.st;
@@ -768,30 +768,25 @@ __global__ void __launch_bounds__(128) k_connect(const __grid_constant__ Scene s
     }
 }
 
-// POST part of the mutation once every candidate is resolved
-template <int MAXD, int LARGE>
-__global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_prop_post(const __grid_constant__ Scene sc, RunParams rp, int chainBase, ChainRec<MAXD> *states,
-                                                                typename GenWorkT<MAXD>::type *genWork, const int *list, const int *countp,
-                                                                WaveLists wl) {
+// POST part of the large steps once every candidate is resolved (mutation.h propose_post_large): candidate
+// compaction, contribution choice, acceptance.  (Small steps: post_small_now, above.)
+template <int MAXD>
+__global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_prop_post_large(const __grid_constant__ Scene sc, RunParams rp, int chainBase, ChainRec<MAXD> *states,
+                                                                      typename GenWorkT<MAXD>::type *genWork, const int *list, const int *countp,
+                                                                      WaveLists wl) {
     const int count = *countp;
     const int stride = gridDim.x * blockDim.x;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
         const int i = list[t];
         ChainState<MAXD> &cs = states[i].cs;
         MarkovState<MAXD> &cur = cs.st[cs.curIdx], &prop = cs.st[cs.curIdx ^ 1];
-        if (LARGE) {
-            uint32_t tab[64];
-            Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
-            typename GenWorkT<MAXD>::type &gw = genWork[i];
-            gw.n = deferred_compact(gw.c, gw.flag, gw.n);
-            propose_post_large(rp, cur, prop, cs.ch, rng, cs.ss, gw);
-            rng_close(rng, cs);
-        } else {
-            cs.pc.n = deferred_compact(cs.pc.c, cs.pc.flag, cs.pc.n);
-            propose_post_small(sc, rp, cur, prop, cs.ss, cs.pc);
-        }
-        // key = the class the evaluator will see (path.camDepth / path.lgtDepth): blocks must be class-pure
-        sort_key_set(wl.propGrad, i, cs.ss.needPropGrad ? class_key(prop.path.camDepth, prop.path.lgtDepth, 0) : -1);
+        uint32_t tab[64];
+        Rng rng; rng_open(rng, tab, sc, chainBase + i, cs);
+        typename GenWorkT<MAXD>::type &gw = genWork[i];
+        gw.n = deferred_compact(gw.c, gw.flag, gw.n);
+        propose_post_large(rp, cur, prop, cs.ch, rng, cs.ss, gw);
+        rng_close(rng, cs);
+        sort_key_set(wl.propGrad, i, -1);          // a large step evaluates no proposal gradient
     }
 }
 
@@ -1000,7 +995,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             pt.mark("connect");
             k_shadow<MAXD><<<GT, LMC_TRACE_BLOCK, 0, st>>>(sc, states, wq, wc.queueCounts + 16 + 63);
             // (the POST part of the small steps ran where their candidate was resolved: k_shade / k_shadow)
-            k_prop_post<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.large, wl.largeCount, wl);
+            k_prop_post_large<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, genWork, wl.large, wl.largeCount, wl);
             *launches += 2;
             pt.mark("shadow + post");
         }
