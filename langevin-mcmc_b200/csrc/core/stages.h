@@ -78,7 +78,11 @@ struct DeferredList {
             }
             pend = false;
         } else {
-            *np = 0;
+            // unconditional clear: recorded as an already-visible CLEAR entry rather than by rewinding the
+            // list, so that slots whose shadow rays are still in flight are never reused
+            const int n = *np;
+            if (n < cap) { flag[n] = CAND_VISIBLE | CAND_CLEAR; *np = n + 1; }
+            else *np = 0;
         }
     }
 };

@@ -130,6 +130,17 @@ void bdpt_t(const Scene &sc, int spp, int minDepth, float *film, int threads) {
 }
 }  // namespace
 
+// sink of the DeferredList probe (lmco_deferred_probe): records which flag belongs to which scripted event
+namespace {
+struct ProbeSink {
+    static const bool kDeferConnections = false;
+    std::vector<int *> flags; std::vector<int> event; int cur;
+    void emit(const Ray &, float, int, int *flag) { flags.push_back(flag); event.push_back(cur); }
+    template <class LS> void emit_connection(const Scene &, int, int, int, const LS *, const SurfaceVertex *, const LS &, const SurfaceVertex &, V2,
+                                             SubpathContrib *, int *) {}
+};
+}
+
 #define LMCO_TRY try {
 #define LMCO_CATCH } catch (const std::exception &e) { g_err = e.what(); return -1; } return 0;
 
@@ -231,6 +242,40 @@ int lmco_direct_lighting(void *h, int directSpp, float *film, int threads) {
     for (int w = 0; w < (threads < 1 ? 1 : threads); w++) pool.emplace_back(work);
     for (auto &t : pool) t.join();
     LMCO_CATCH
+}
+
+// DeferredList (core/stages.h) against the immediate contribution vector on a scripted event sequence.
+// type: 0 push (no visibility query), 1 "if (!occluded) push", 2 "if (!occluded) clear", 3 clear.
+// occl[i] is the answer of event i's visibility query.  Outputs: the lsScore tags left in each list.
+int lmco_deferred_probe(int nEvents, const int *type, const int *occl, float *outImm, int *nImm, float *outDef, int *nDef) {
+    Scene sc; memset(&sc, 0, sizeof(sc));
+    Ray ray; ray.org = mk3s(0.0f); ray.dir = mk3(0.0f, 0.0f, 1.0f);
+    // immediate
+    std::vector<float> imm;
+    for (int i = 0; i < nEvents; i++) {
+        if (type[i] == 0) imm.push_back((float)(i + 1));
+        else if (type[i] == 1) { if (!occl[i]) imm.push_back((float)(i + 1)); }
+        else if (type[i] == 2) { if (!occl[i]) imm.clear(); }
+        else imm.clear();
+    }
+    // deferred
+    const int CAP = 256;
+    if (nEvents > CAP) return -1;
+    std::vector<SubpathContrib> c(CAP); std::vector<int> flag(CAP); int n = 0;
+    ProbeSink sink; DeferredList<ProbeSink> dl; dl.bind(c.data(), flag.data(), &n, CAP, &sink);
+    for (int i = 0; i < nEvents; i++) {
+        sink.cur = i;
+        SubpathContrib x; memset(&x, 0, sizeof(x)); x.lsScore = (float)(i + 1);
+        if (type[i] == 0) dl.push(x);
+        else if (type[i] == 1) { if (!dl.occluded(sc, ray, 1.0f)) dl.push(x); }
+        else if (type[i] == 2) { if (!dl.occluded(sc, ray, 1.0f)) dl.clear(); }
+        else dl.clear();
+    }
+    for (size_t k = 0; k < sink.flags.size(); k++) *sink.flags[k] = cand_resolve(*sink.flags[k], occl[sink.event[k]] != 0);
+    n = deferred_compact(c.data(), flag.data(), n);
+    *nImm = (int)imm.size(); for (size_t k = 0; k < imm.size(); k++) outImm[k] = imm[k];
+    *nDef = n; for (int k = 0; k < n; k++) outDef[k] = c[k].lsScore;
+    return 0;
 }
 
 // 1: lmco_run_chains runs every proposal through the staged (wavefront) path functions

@@ -36,3 +36,20 @@ def test_staged_equals_monolithic(oracle, torus_xml, door_xml, scene, opts, chai
     # per-thread films are summed in scheduling order: equal up to fp32 summation order
     assert np.allclose(film0, film1, rtol=1e-4, atol=1e-6)
     assert (tr0 & 3 == 0).any() and (tr0 & 3 != 0).any()    # large and small steps both exercised
+
+
+def test_deferred_list_equals_immediate_vector_on_scripted_events(oracle):
+    """DeferredList (visibility answered later, contributions kept in push order, conditional clears) against
+    the reference's immediate std::vector semantics, on random event scripts including the clear() cases that
+    real paths almost never produce (src/path.cpp:700-704, 1345-1347)."""
+    import ctypes
+    rng = np.random.default_rng(7)
+    for trial in range(400):
+        n = int(rng.integers(1, 40))
+        types = rng.choice([0, 1, 1, 1, 2, 3], size=n, p=[0.2, 0.25, 0.25, 0.2, 0.07, 0.03]).astype(np.int32)
+        occl = rng.integers(0, 2, size=n).astype(np.int32)
+        imm = np.zeros(64, np.float32); dfr = np.zeros(64, np.float32)
+        ni = ctypes.c_int(); nd = ctypes.c_int()
+        rc = oracle.L.lmco_deferred_probe(n, oracle.p(types), oracle.p(occl), oracle.p(imm), ctypes.byref(ni), oracle.p(dfr), ctypes.byref(nd))
+        assert rc == 0
+        assert ni.value == nd.value and np.array_equal(imm[:ni.value], dfr[:nd.value]), (types, occl)
