@@ -740,8 +740,11 @@ template <class T> LMC_HD_NOINLINE const float *ad_bsdf_sampling(bool adjoint, c
 #endif
 #define LMC_VERTEX_SYNC2() LMC_VERTEX_SYNC()
 
-template <class T>
-LMC_HD_NOINLINE T eval_path_loglum(int maxCamDepth, int maxLightDepth, const float *sceneBuf, const float *vertParams, const T *pss) {
+// PSS: anything indexable that yields the i-th primary-sample value as a T: a float pointer for the forward
+// value, a seed object for the derivative sweeps (the seeded duals are built where they are consumed instead
+// of being staged in a local array: 100 local-memory stores fewer per sweep)
+template <class T, class PSS>
+LMC_HD_NOINLINE T eval_path_loglum(int maxCamDepth, int maxLightDepth, const float *sceneBuf, const float *vertParams, const PSS &pss) {
     const ADScene scn = ad_scene_deserialize(sceneBuf);
     const float *buffer = vertParams + 3;   // lensVertexPos
     int pi = 0;
@@ -923,7 +926,8 @@ LMC_HD_NOINLINE T eval_path_loglum(int maxCamDepth, int maxLightDepth, const flo
 
 // Forward value only.
 LMC_HD_NOINLINE float path_loglum(int camDepth, int lightDepth, const float *sceneBuf, const float *primary, const float *vertParams) {
-    return eval_path_loglum<float>(camDepth, lightDepth, sceneBuf, vertParams, primary + 1);
+    const float *pss = primary + 1;
+    return eval_path_loglum<float>(camDepth, lightDepth, sceneBuf, vertParams, pss);
 }
 
 // Gradient w.r.t. primary[1..D] (time excluded: Static mode), NCHUNK directions per sweep.
@@ -931,17 +935,23 @@ LMC_HD_NOINLINE float path_loglum(int camDepth, int lightDepth, const float *sce
 #define LMC_GRAD_CHUNK 4
 #endif
 #define LMC_GRAD_MAXDIM 24
+// seeds of one first-order sweep: value primary[1 + i], derivative e_(i - base) for the chunk's directions
+struct GradSeed {
+    const float *primary; int base;
+    LMC_HD Dual<LMC_GRAD_CHUNK> operator[](int i) const {
+        Dual<LMC_GRAD_CHUNK> r;
+        r.v = primary[1 + i];
+        for (int k = 0; k < LMC_GRAD_CHUNK; k++) r.d[k] = (i == base + k) ? 1.0f : 0.0f;
+        return r;
+    }
+};
 LMC_HD_NOINLINE float path_loglum_grad(int camDepth, int lightDepth, const float *sceneBuf, const float *primary,
                                        const float *vertParams, float *grad) {
     const int dim = 2 * ((camDepth + lightDepth - 1) > 2 ? (camDepth + lightDepth - 1) : 2);
     typedef Dual<LMC_GRAD_CHUNK> D;
     float value = 0.0f;
     for (int base = 0; base < dim; base += LMC_GRAD_CHUNK) {
-        D pss[LMC_GRAD_MAXDIM];
-        for (int i = 0; i < dim; i++) {
-            pss[i].v = primary[1 + i];
-            for (int k = 0; k < LMC_GRAD_CHUNK; k++) pss[i].d[k] = (i == base + k) ? 1.0f : 0.0f;
-        }
+        GradSeed pss; pss.primary = primary; pss.base = base;
         const D r = eval_path_loglum<D>(camDepth, lightDepth, sceneBuf, vertParams, pss);
         value = r.v;
         for (int k = 0; k < LMC_GRAD_CHUNK; k++) if (base + k < dim) grad[base + k] = r.d[k];
@@ -955,6 +965,20 @@ LMC_HD_NOINLINE float path_loglum_grad(int camDepth, int lightDepth, const float
 // (src/chad.cpp:333-545); hess is row-major D x D (hess[i * D + j] = d2 f / dx_i dx_j, symmetric).
 #define LMC_HESS_CHUNK 2
 #define LMC_HESS_MAXDIM 16
+// seeds of one second-order sweep: outer directions ba.., inner directions bb..
+struct HessSeed {
+    const float *primary; int ba, bb;
+    LMC_HD DualT<DualT<float, LMC_HESS_CHUNK>, LMC_HESS_CHUNK> operator[](int i) const {
+        DualT<DualT<float, LMC_HESS_CHUNK>, LMC_HESS_CHUNK> r;
+        r.v.v = primary[1 + i];
+        for (int k = 0; k < LMC_HESS_CHUNK; k++) r.v.d[k] = (i == bb + k) ? 1.0f : 0.0f;
+        for (int j = 0; j < LMC_HESS_CHUNK; j++) {
+            r.d[j].v = (i == ba + j) ? 1.0f : 0.0f;
+            for (int k = 0; k < LMC_HESS_CHUNK; k++) r.d[j].d[k] = 0.0f;
+        }
+        return r;
+    }
+};
 LMC_HD_NOINLINE float path_loglum_hess(int camDepth, int lightDepth, const float *sceneBuf, const float *primary,
                                        const float *vertParams, float *grad, float *hess) {
     const int dim = 2 * ((camDepth + lightDepth - 1) > 2 ? (camDepth + lightDepth - 1) : 2);
@@ -963,15 +987,7 @@ LMC_HD_NOINLINE float path_loglum_hess(int camDepth, int lightDepth, const float
     float value = 0.0f;
     for (int ba = 0; ba < dim; ba += LMC_HESS_CHUNK) {
         for (int bb = ba; bb < dim; bb += LMC_HESS_CHUNK) {
-            D2 pss[LMC_HESS_MAXDIM];
-            for (int i = 0; i < dim; i++) {
-                pss[i].v.v = primary[1 + i];
-                for (int k = 0; k < LMC_HESS_CHUNK; k++) pss[i].v.d[k] = (i == bb + k) ? 1.0f : 0.0f;
-                for (int j = 0; j < LMC_HESS_CHUNK; j++) {
-                    pss[i].d[j].v = (i == ba + j) ? 1.0f : 0.0f;
-                    for (int k = 0; k < LMC_HESS_CHUNK; k++) pss[i].d[j].d[k] = 0.0f;
-                }
-            }
+            HessSeed pss; pss.primary = primary; pss.ba = ba; pss.bb = bb;
             const D2 r = eval_path_loglum<D2>(camDepth, lightDepth, sceneBuf, vertParams, pss);
             value = r.v.v;
             for (int j = 0; j < LMC_HESS_CHUNK; j++) {
