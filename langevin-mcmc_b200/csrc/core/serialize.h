@@ -52,8 +52,9 @@ LMC_HD_NOINLINE void serialize_bsdf(const Scene &sc, int tid, V2 st, float *b) {
 // 56 floats (padded)
 template <bool COMPACT = false>
 LMC_HD_NOINLINE void serialize_light(const Scene &sc, int light, int lPrimID, float *b) {
-    for (int i = 0; i < LMC_SER_LIGHT; i++) b[i] = 0.0f;
     const Light &l = sc.lights[light];
+    // (COMPACT: an env-light record is written completely below -- entries 0..53 are all the evaluator reads)
+    if (!(COMPACT && l.type == LIGHT_ENV)) for (int i = 0; i < LMC_SER_LIGHT; i++) b[i] = 0.0f;
     b[0] = (float)l.type;
     if (l.type == LIGHT_POINT) { for (int k = 0; k < 3; k++) { b[1 + k] = l.pos[k]; b[4 + k] = l.emission[k]; } }
     else if (l.type == LIGHT_AREA) {
