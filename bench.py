@@ -36,9 +36,9 @@ CHAINS_PER_GPU = 1 << 20
 MUTATIONS_PER_STEP = 32
 # canonical state words S_LMC(L) = 14 L + 21; bytes per mutation = 8 S + 48
 ALGO_BYTES_PER_MUTATION = 8 * (14 * MAXDEPTH + 21) + 48   # 1112 B at L = 8
-# dram__bytes_read.sum + dram__bytes_write.sum of the 49 kernels of one iteration over 2^20 chains
-# (ncu, profiles/r01_launches_pervertex_2p20.csv / _summary.txt): 12.67 GB / 2^20 mutations
-DRAM_BYTES_PER_MUTATION_NCU = 12.67e9 / (1 << 20)
+# dram__bytes_read.sum + dram__bytes_write.sum of the 48 kernels of one iteration over 2^20 chains
+# (ncu, profiles/r01_launches_pervertex_2p20.csv / _summary.txt): 11.86 GB / 2^20 mutations
+DRAM_BYTES_PER_MUTATION_NCU = 11.86e9 / (1 << 20)
 
 
 def load_package():
@@ -273,7 +273,7 @@ def main():
                 "clocks": sampler.result(),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": DRAM_BYTES_PER_MUTATION_NCU * float(n_local) * M,
-                             "kernel": "one lmc_run_chains call = M chain-loop iterations of 49 launches each (k_wave_grad, k_trace, "
+                             "kernel": "one lmc_run_chains call = M chain-loop iterations of 48 launches each (k_wave_grad, k_trace, "
                                        "k_shade<P_CAM/G_CAM>, k_wave_finish+begin ...; shares in profiles/r01_launches_pervertex_2p20_summary.txt)",
                              "algorithmic_bytes_per_mutation": ALGO_BYTES_PER_MUTATION,
                              "kernel_ms_per_launch": k_ms, "peak_source": peak_src,
