@@ -8,6 +8,7 @@
 #pragma once
 #include "path.h"
 #include "pathgrad.h"
+#include "pathgrad_rev.h"
 
 namespace lmc {
 
@@ -175,6 +176,15 @@ LMC_HD_NOINLINE void path_gradient(const Scene &sc, const Path<MAXD> &path, floa
         for (int i = 0; i < 1100; i++) big[i] = 0.0f;
         float prim_[32];
         const int nv = serialize_path(sc, path, prim_, big);
+        if (path.lgtDepth == 0 && path.envLight >= 0 && path.nCam > 0) {
+            // The reference leaves the shape block of an environment hit untouched (src/path.cpp:2545-2548): its code
+            // then differentiates whatever the reused buffer held.  Emulate "stale but finite" with a fixed triangle
+            // (a zero block would turn the whole reverse sweep into NaN, which the reference only sees on a chain's
+            // very first evaluation).
+            float *q = big + 3 + (path.nCam - 1) * (LMC_SER_SHAPE + 2 + LMC_SER_BSDF + 1) + 2;
+            const float tri[18] = {-1e3f, -1e3f, 977.0f, 2e3f, 0.0f, 13.0f, 0.0f, 2e3f, -7.0f, 0, 0, 1, 0, 0, 1, 0, 0, 1};
+            for (int i = 0; i < 18; i++) q[i] = tri[i];
+        }
         const float lens[2] = {path.screenPos.x, path.screenPos.y};
         ref_grad_hook()(path.camDepth, path.lgtDepth, lens, prim_, sc.sceneSer, big, nv, grad, dim_);
         return;
@@ -187,7 +197,7 @@ LMC_HD_NOINLINE void path_gradient(const Scene &sc, const Path<MAXD> &path, floa
         return;
     }
     serialize_path<MAXD, true>(sc, path, primary, vertParams);
-    path_loglum_grad(path.camDepth, path.lgtDepth, sc.sceneSer, primary, vertParams, grad);
+    path_loglum_grad_mode(sc.opt.adjointCompat, path.camDepth, path.lgtDepth, sc.sceneSer, primary, vertParams, grad);
 }
 
 // dervFunc(..., vGrad, vHess) of the H2MC library (src/mutation_h2mc.h:74-79); hess row-major dim x dim

@@ -47,11 +47,11 @@ __global__ void k_bvh_probe(const __grid_constant__ Scene sc, int n, const float
 
 // one thread = one serialized path (reference ABI: PathFunc / PathFuncDerv, src/path.h:121-125)
 __global__ void k_eval_batch(int camDepth, int lightDepth, int n, const float *sceneSer, const float *primary, int primaryStride,
-                             const float *vertParams, int vertStride, float *logLum, float *grad, int dim) {
+                             const float *vertParams, int vertStride, float *logLum, float *grad, int dim, int mode) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float *p = primary + (size_t)i * primaryStride, *v = vertParams + (size_t)i * vertStride;
-    if (grad) logLum[i] = path_loglum_grad(camDepth, lightDepth, sceneSer, p, v, grad + (size_t)i * dim);
+    if (grad) logLum[i] = path_loglum_grad_mode(mode, camDepth, lightDepth, sceneSer, p, v, grad + (size_t)i * dim);
     else logLum[i] = path_loglum(camDepth, lightDepth, sceneSer, p, v);
 }
 
@@ -552,7 +552,7 @@ int lmc_eval_batch(lmc_ctx *c, int32_t cam_depth, int32_t light_depth, int32_t n
     CK(cudaMemcpyAsync(dP, primary, sizeof(float) * (size_t)n * (dim + 1), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(dV, vert_params, sizeof(float) * (size_t)n * vert_stride, cudaMemcpyHostToDevice, c->stream));
     if (hess) k_eval_batch_hess<<<(n + 63) / 64, 64, 0, c->stream>>>(cam_depth, light_depth, n, dS, dP, dim + 1, dV, vert_stride, dL, dG, dH, dim);
-    else k_eval_batch<<<(n + 63) / 64, 64, 0, c->stream>>>(cam_depth, light_depth, n, dS, dP, dim + 1, dV, vert_stride, dL, dG, dim);
+    else k_eval_batch<<<(n + 63) / 64, 64, 0, c->stream>>>(cam_depth, light_depth, n, dS, dP, dim + 1, dV, vert_stride, dL, dG, dim, c->sc.opt.adjointCompat);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(log_lum, dL, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));

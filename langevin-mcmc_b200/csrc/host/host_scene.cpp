@@ -533,7 +533,7 @@ Options default_options() {
     memset(&o, 0, sizeof(o));
     o.minDepth = -1; o.maxDepth = 8; o.bidirectional = 1; o.h2mc = 0; o.mala = 0;
     o.numChains = 128; o.seedOffset = 0; o.useLightCoordinateSampling = 0; o.largeStepMultiplexed = 0;
-    o.cacheEnabled = 0; o.maxDervDepth = 8; o.pssMinLength = 2; o.pssMaxLength = 12; o.adjointCompat = 0;
+    o.cacheEnabled = 0; o.maxDervDepth = 8; o.pssMinLength = 2; o.pssMaxLength = 12; o.adjointCompat = 1;
     o.perturbStdDev = 0.01f; o.roughnessThreshold = 0.05f; o.largeStepProbability = 0.05f;
     o.largeStepProbScale = 1.0f; o.malaGN = 100.0f; o.malaStepsize = 0.005f; o.malaStdDev = 0.005f;
     o.discreteStdDev = 0.01f; o.uniformMixingProbability = 0.1f; o.lsRatio = 0.1f;

@@ -352,7 +352,7 @@ int lmco_eval_batch(void *h, int camDepth, int lightDepth, int n, const float *p
     const int dim = primary_param_size(camDepth, lightDepth) - 1;
     for (int i = 0; i < n; i++) {
         const float *p = primary + (size_t)i * primaryStride, *v = vertParams + (size_t)i * vertStride;
-        if (grad) logLum[i] = path_loglum_grad(camDepth, lightDepth, sceneSer, p, v, grad + (size_t)i * dim);
+        if (grad) logLum[i] = path_loglum_grad_mode(st.head.opt.adjointCompat, camDepth, lightDepth, sceneSer, p, v, grad + (size_t)i * dim);
         else logLum[i] = path_loglum(camDepth, lightDepth, sceneSer, p, v);
     }
     return 0;

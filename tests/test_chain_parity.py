@@ -37,8 +37,10 @@ def test_oracle_chain_loop_properties(oracle, torus_xml):
 def test_oracle_R_vs_T_divergence_statistics(oracle, torus_xml, ref_mala):
     """Two-tier oracle: Oracle-R = the same chain loop with the REFERENCE's own
     generated reverse-mode gradient (oracle/_ref); Oracle-T = the twin the GPU matches bit for bit.
-    Their decision strings cannot be identical (the reference's reverse sweep deviates from its own
-    forward-mode gradient on glass paths, App. B#13): the agreement is reported and bounded."""
+    With the reverse sweep in the reference's merge order (option adjointcompat = 1, the default, App. B#13) the
+    two gradients agree to fp32 noise, so >= 95 % of the chains must produce the IDENTICAL 100-step decision
+    string (measured 99.0 %; with the true gradient it was 73.6 %); the rest are chains where an acceptance
+    probability sat within rounding of its uniform draw."""
     h = oracle.load(torus_xml)
     oracle.set_option(h, "maxdepth", 4)
     chains, steps = 1024, 100            # BASELINE configs[0]
@@ -54,9 +56,9 @@ def test_oracle_R_vs_T_divergence_statistics(oracle, torus_xml, ref_mala):
     accT, accR = sT[7] / sT[3], sR[7] / sR[3]
     print("Oracle-R vs Oracle-T: identical 100-step decision strings %.1f%% of chains; median first divergence %d; "
           "MALA acceptance T %.4f R %.4f; film sum T %.1f R %.1f" % (100 * same, int(np.median(first)), accT, accR, fT.sum(), fR.sum()))
-    assert same > 0.5
-    assert abs(accT - accR) < 0.02
-    assert abs(fT.sum() - fR.sum()) < 0.03 * fR.sum()
+    assert same >= 0.95
+    assert abs(accT - accR) < 0.002
+    assert abs(fT.sum() - fR.sum()) < 0.005 * fR.sum()
     # step-type sequences agree wherever the chains have not diverged: first steps are always equal
     assert np.array_equal(tT[:, 0], tR[:, 0])
 

@@ -9,13 +9,18 @@ Tolerances (north star: contribution / gradient within 1e-4 relative):
     relative on the contribution, for >= 99% of the paths; the remainder are the reference's
     6-decimal constants amplified by near-singular configurations and must
     stay below 5e-3.
-  * gradient vs the reference's forward-mode code (H2MC library): relative L2 error
-    <= 1e-4 median, <= 2e-3 at the 99th percentile (the reference is built with ispc fast-math).
-  * gradient vs the reference's reverse-mode code (MALA library): same bound on paths without a
-    RoughDielectric vertex and with camDepth >= 2.  With glass, and for light-tracing classes
-    (camDepth == 1, ConnectToCamera), the reference's reverse sweep is itself wrong by 1-100%
-    against its own forward-mode code (chad merges `if` outputs by assignment, SURVEY.md
-    App. B#13; re-measured by make_path_golden.py); that deviation is REPORTED, not hidden.
+  * gradient, option adjointcompat = 1 (default: one reverse sweep in the reference's merge order,
+    csrc/core/pathgrad_rev.h) vs the reference's reverse-mode code (MALA library) on EVERY golden
+    path -- including paths through RoughDielectric vertices and the light-tracing classes
+    (camDepth == 1), where the reference's sweep deviates from the true gradient by 1-100 %
+    (chad merges `if` outputs by assignment): relative L2 error <= 1e-4 median,
+    <= 5e-3 at the 99th percentile in each bucket.  (Both sides are fp32; the reference is built with
+    ispc fast-math and prints its constants with 6 decimals: the float64 interpretation of the same
+    program, tools/adgen/check_whole.py, sits at median 2e-6 / p99 1.3e-3 against it.)
+  * gradient, adjointcompat = 0 (reverse sweep, true adjoint) and = 2 (forward-mode duals,
+    csrc/core/pathgrad.h) vs the reference's forward-mode code (H2MC library): <= 1e-4 median,
+    <= 2e-3 p99; and against each other <= 1e-5 median (two independent derivations of the same
+    gradient).
 """
 import os
 
@@ -52,7 +57,7 @@ def evaluate_golden(eval_fn, g):
     return ll, grads
 
 
-def check_against_golden(ll, grads, g):
+def check_against_golden(ll, grads, g, mode=1):
     n = len(ll)
     # The mutation only evaluates the function when ssScore > 1e-10 (src/mutation_mala.h:100);
     # below that fp32 products underflow while the reference's C forward code runs in double.
@@ -76,14 +81,19 @@ def check_against_golden(ll, grads, g):
             buggy = (2 in bsdf_types(c, l, g["vert"][i])) or c == 1
             (e_rev_glass if buggy else e_rev_noglass).append(rel_l2(grads[i], rv))
     e_fm, e_rev_noglass, e_rev_glass = map(np.array, (e_fm, e_rev_noglass, e_rev_glass))
-    assert len(e_fm) > 100 and len(e_rev_noglass) > 100
-    assert np.median(e_fm) <= 1e-4 and np.percentile(e_fm, 99) <= 2e-3, (np.median(e_fm), np.percentile(e_fm, 99))
-    assert np.median(e_rev_noglass) <= 1e-4 and np.percentile(e_rev_noglass, 99) <= 2e-3, \
-        (np.median(e_rev_noglass), np.percentile(e_rev_noglass, 99))
-    return dict(fwd_med=float(np.median(d)), fwd_max=float(d.max()), fm_med=float(np.median(e_fm)),
-                fm_p99=float(np.percentile(e_fm, 99)), rev_noglass_med=float(np.median(e_rev_noglass)),
-                rev_glass_med=float(np.median(e_rev_glass)) if len(e_rev_glass) else None,
-                rev_glass_p90=float(np.percentile(e_rev_glass, 90)) if len(e_rev_glass) else None)
+    assert len(e_fm) > 100 and len(e_rev_noglass) > 100 and len(e_rev_glass) > 100
+    rep = dict(fwd_med=float(np.median(d)), fwd_max=float(d.max()), fm_med=float(np.median(e_fm)),
+               fm_p99=float(np.percentile(e_fm, 99)), rev_noglass_med=float(np.median(e_rev_noglass)),
+               rev_noglass_p99=float(np.percentile(e_rev_noglass, 99)),
+               rev_glass_med=float(np.median(e_rev_glass)), rev_glass_p90=float(np.percentile(e_rev_glass, 90)),
+               rev_glass_p99=float(np.percentile(e_rev_glass, 99)), n_glass=len(e_rev_glass))
+    if mode == 1:     # the reference's reverse sweep, every bucket
+        assert rep["rev_noglass_med"] <= 1e-4 and rep["rev_noglass_p99"] <= 5e-3, rep
+        assert rep["rev_glass_med"] <= 1e-4 and rep["rev_glass_p99"] <= 5e-3, rep
+    else:             # the true gradient
+        assert rep["fm_med"] <= 1e-4 and rep["fm_p99"] <= 2e-3, rep
+        assert rep["rev_noglass_med"] <= 1e-4 and rep["rev_noglass_p99"] <= 2e-3, rep
+    return rep
 
 
 def test_oracle_evaluator_matches_reference_golden(oracle, torus_xml, door_xml):
@@ -93,9 +103,17 @@ def test_oracle_evaluator_matches_reference_golden(oracle, torus_xml, door_xml):
     for s, h in handles.items():
         idx = np.where(g["scene"] == s)[0][0]
         assert np.allclose(oracle.scene_serialized(h), g["scene_ser"][idx], rtol=2e-6, atol=1e-6)
-    ll, grads = evaluate_golden(lambda s, c, l, p, v: oracle.eval_batch(handles[s], c, l, p, v), g)
-    rep = check_against_golden(ll, grads, g)
-    print("oracle vs reference golden:", rep)
+    by_mode = {}
+    for mode in (1, 0, 2):
+        for h in handles.values():
+            oracle.set_option(h, "adjointcompat", mode)
+        ll, grads = evaluate_golden(lambda s, c, l, p, v: oracle.eval_batch(handles[s], c, l, p, v), g)
+        rep = check_against_golden(ll, grads, g, mode)
+        by_mode[mode] = grads
+        print("oracle (adjointcompat=%d) vs reference golden:" % mode, rep)
+    # reverse sweep (true adjoint) == forward-mode duals: two independent derivations
+    e = [rel_l2(a, b) for a, b in zip(by_mode[0], by_mode[2]) if np.isfinite(a).all() and np.isfinite(b).all()]
+    assert np.median(e) <= 1e-5 and np.percentile(e, 99) <= 5e-3, (np.median(e), np.percentile(e, 99))
     # the tracer's own score must agree with the AD twin wherever the reference's twin is sane
     ok = np.isfinite(ll) & (g["ss"] > 1e-30)
     d = np.abs(ll[ok] - np.log(g["ss"][ok]))
