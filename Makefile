@@ -2,7 +2,8 @@
 # `make ref` = the reference's own generated path functions compiled into oracle/_ref/ (needs
 # /root/reference; outputs are git-ignored but travel to the GPU box).
 PKG      := langevin-mcmc_b200
-CORE_H   := $(wildcard $(PKG)/csrc/core/*.h) $(wildcard $(PKG)/csrc/host/*.h)
+CORE_INC := $(wildcard $(PKG)/csrc/core/*.inc)
+CORE_H   := $(wildcard $(PKG)/csrc/core/*.h) $(wildcard $(PKG)/csrc/host/*.h) $(CORE_INC)
 CXX      := $(shell which g++)
 CXXFLAGS := -O2 -std=c++17 -fPIC -mfma -ffp-contract=off -fno-fast-math -Wall -Wno-unused-function -pthread
 NVCC     := nvcc
@@ -15,10 +16,18 @@ oracle: oracle/liblmc_oracle.so
 oracle/liblmc_oracle.so: oracle/oracle_api.cpp $(PKG)/csrc/host/host_scene.cpp $(CORE_H)
 	$(CXX) $(CXXFLAGS) -shared -o $@ oracle/oracle_api.cpp $(PKG)/csrc/host/host_scene.cpp -lz -ldl
 
+# TIMING build of the CPU arm (bench.py cpu_baseline / --impl reference only; never used for parity): the
+# reference's own flags (src/Tupfile:17: g++ -march=native -Ofast) and the platform libm.  FAST_ARCH defaults to
+# x86-64-v3 so the prebuilt file runs on any AVX2 host; bench.py rebuilds it with -march=native on the box.
+FAST_ARCH ?= x86-64-v3
+oracle_fast: oracle/liblmc_oracle_fast.so
+oracle/liblmc_oracle_fast.so: oracle/oracle_api.cpp $(PKG)/csrc/host/host_scene.cpp $(CORE_H)
+	$(CXX) -Ofast -march=$(FAST_ARCH) -std=c++17 -fPIC -pthread -DLMC_TIMING_LIBM -w -shared -o $@ oracle/oracle_api.cpp $(PKG)/csrc/host/host_scene.cpp -lz -ldl
+
 CUDA_SRC := $(PKG)/csrc/cuda
 CUDA_OBJ := $(PKG)/build/lmc_abi.o $(PKG)/build/chain_inst_4.o $(PKG)/build/chain_inst_8.o $(PKG)/build/chain_inst_12.o
 lib: $(PKG)/liblmc_b200.so
-$(PKG)/build/%.o: $(CUDA_SRC)/%.cu $(CORE_H) $(CUDA_SRC)/chain_kernels.cuh include/lmc/lmc_abi.h
+$(PKG)/build/%.o: $(CUDA_SRC)/%.cu $(CORE_H) $(CORE_INC) $(CUDA_SRC)/chain_kernels.cuh $(CUDA_SRC)/trace_kernels.cuh include/lmc/lmc_abi.h
 	@mkdir -p $(PKG)/build
 	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $(PKG)/build/$*.ptxas.log || (cat $(PKG)/build/$*.ptxas.log; false)
 $(PKG)/build/host_scene.o: $(PKG)/csrc/host/host_scene.cpp $(CORE_H)
@@ -33,4 +42,4 @@ ref:
 clean:
 	rm -rf oracle/liblmc_oracle.so $(PKG)/liblmc_b200.so $(PKG)/build
 
-.PHONY: all oracle lib ref clean
+.PHONY: all oracle oracle_fast lib ref clean

@@ -1,26 +1,33 @@
 #!/usr/bin/env python3
-"""bench.py -- MCMC mutations/sec of the LMC chain loop on the bundled torus scene.
+"""bench.py -- MCMC mutations/sec of the LMC chain loop on the bundled scenes.
 
-Workload (BASELINE.json configs[1]): torus scene, LMC (mala) mutation, path length (maxdepth) 8,
-2^20 Markov chains per GPU, global cache off (every eligible MALA step evaluates its PSS
-gradient), options of scenes/torus/lmc.xml.  One "step" = every chain of the job advanced by
-MUTATIONS_PER_STEP iterations of the loop at src/mlt.cpp:91-170 (one `lmc_run_chains` call).
+Headline workload (BASELINE.json configs[1]): torus scene, LMC (mala) mutation, path length (maxdepth) 8,
+2^20 Markov chains per GPU, global cache off (every eligible MALA step evaluates its PSS gradient -- the
+reverse sweep in the reference's merge order, option adjointcompat = 1), options of scenes/torus/lmc.xml.
+One "step" = every chain of the job advanced by MUTATIONS_PER_STEP iterations of the loop at
+src/mlt.cpp:91-170 (one `lmc_run_chains` call).
 
     python bench.py --gpus N --steps K --warmup W            our arm (CUDA, one rank per GPU)
-    python bench.py --impl reference ...                      CPU arm: the reference's chain loop as
-                                                              restated by the oracle, all host cores
+    python bench.py --impl reference ...                      CPU arm: the reference's chain loop as restated by
+                                                              the oracle (TIMING build: -Ofast -march=native + libm,
+                                                              gradients from the reference's own generated code
+                                                              when oracle/_ref exists), all host cores
 
-Timed region (device arm): K steps bracketed by barrier + cuda synchronize, CUDA events on the
-launching stream, max over ranks; it includes the final NCCL all-reduce of the fp32 film
-(src/mlt.cpp:57->200 is the span the metric is defined on; MLTInit, scene load, BVH build are
-setup).  Chain records + wavefront queues (4.5 KB + 1.4 KB per chain, x 2^20 = 6 GB) are far larger
-than L2, so no explicit flush.
+Timed region (device arm): K steps bracketed by barrier + cuda synchronize, CUDA events on the launching
+stream, max over ranks; it includes the final NCCL all-reduce of the fp32 film (src/mlt.cpp:57->200 is the
+span the metric is defined on; MLTInit, scene load, BVH build are setup).  Chain records + wavefront queues
+(several GB at 2^20 chains) are far larger than L2, so no explicit flush.
+
+The same JSON line carries, under "extra" -> "configs", short device-timed runs of the other BASELINE
+configurations (veach-door LMC maxdepth 12; torus H2MC maxdepth 8; at N = 8 the door run IS configs[4]:
+2^23 chains over 8 GPUs), each with its own roofline fraction.
 """
 import argparse
 import ctypes
 import importlib.util
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -29,16 +36,31 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG_DIR = os.path.join(ROOT, "langevin-mcmc_b200")
-SCENE_XML = os.path.join(ROOT, "scenes", "torus", "lmc.xml")
 METRIC = "MCMC mutations/sec (torus, path len 8)"
-MAXDEPTH = 8
 CHAINS_PER_GPU = 1 << 20
 MUTATIONS_PER_STEP = 32
-# canonical state words S_LMC(L) = 14 L + 21; bytes per mutation = 8 S + 48
-ALGO_BYTES_PER_MUTATION = 8 * (14 * MAXDEPTH + 21) + 48   # 1112 B at L = 8
-# dram__bytes_read.sum + dram__bytes_write.sum of the 48 kernels of one iteration over 2^20 chains
-# (ncu, profiles/r01_launches_pervertex_2p20.csv / _summary.txt): 11.86 GB / 2^20 mutations
-DRAM_BYTES_PER_MUTATION_NCU = 11.86e9 / (1 << 20)
+
+
+def algo_bytes(kind, L):
+    """SURVEY.md s8(d): canonical state words S_LMC(L) = 14 L + 21, S_H2MC(L) = 8 L^2 + 6 L + 19;
+    bytes per mutation = 8 S + 48 (state read + written once, two film splats)."""
+    s = (14 * L + 21) if kind == "lmc" else (8 * L * L + 6 * L + 19)
+    return 8 * s + 48
+
+
+# name -> scene xml, option overrides, path length L, mutation kind
+WORKLOADS = {
+    "torus_lmc_L8": dict(xml=os.path.join("torus", "lmc.xml"), opts={"maxdepth": 8}, L=8, kind="lmc",
+                         text="torus, LMC (mala), maxdepth 8, 2^20 chains per GPU, global cache off (BASELINE configs[1])"),
+    "door_lmc_L12": dict(xml=os.path.join("veachdoor", "lmc.xml"), opts={"maxdepth": 12}, L=12, kind="lmc",
+                         text="veach-door, LMC, maxdepth 12, 2^20 chains per GPU (BASELINE configs[2]; x8 GPUs = configs[4])"),
+    "torus_h2mc_L8": dict(xml=os.path.join("torus", "h2mc.xml"), opts={"maxdepth": 8}, L=8, kind="h2mc",
+                          text="torus, H2MC (Hessian preconditioner), maxdepth 8, 2^20 chains per GPU (BASELINE configs[3])"),
+}
+HEADLINE = "torus_lmc_L8"
+# dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one iteration over 2^20 chains
+# (ncu, profiles/r02_launches_2p20_summary.txt), per mutation; None until measured for this build
+DRAM_BYTES_PER_MUTATION_NCU = None
 
 
 def load_package():
@@ -94,30 +116,59 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_chain_rate(threads, budget_s, maxdepth=MAXDEPTH):
-    """Times the CPU oracle's chain loop (restatement of src/mlt.cpp:60-196, same options, cache
-    off) on `threads` host threads for roughly budget_s seconds.  Returns (mut/s, sample text)."""
+# ------------------------------------------------------------------------------------------------
+# CPU arm (the only place bench.py executes anything under oracle/)
+# ------------------------------------------------------------------------------------------------
+def _timing_oracle():
+    """oracle/liblmc_oracle_fast.so: the CPU restatement built like the reference (`g++ -Ofast -march=native`,
+    src/Tupfile:17) with the platform libm -- the TIMING build.  Rebuilt for this host's ISA when a compiler is
+    here (about 40 s); otherwise the prebuilt x86-64-v3 file is used.  Returns (ctypes-backed Oracle, description)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from conftest import Oracle
-    o = Oracle()
-    h = o.load(SCENE_XML)
-    o.set_option(h, "maxdepth", maxdepth)
+    path = os.path.join(ROOT, "oracle", "liblmc_oracle_fast.so")
+    native = os.path.join(ROOT, "oracle", "liblmc_oracle_fast_native.so")
+    desc = "-Ofast -march=x86-64-v3 (prebuilt)"
+    if not os.path.exists(native) and os.environ.get("LMC_BENCH_NO_REBUILD") is None:
+        try:
+            subprocess.run(["g++", "-Ofast", "-march=native", "-std=c++17", "-fPIC", "-pthread", "-DLMC_TIMING_LIBM", "-w",
+                            "-shared", "-o", native, os.path.join(ROOT, "oracle", "oracle_api.cpp"),
+                            os.path.join(PKG_DIR, "csrc", "host", "host_scene.cpp"), "-lz", "-ldl"],
+                           check=True, timeout=300, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except Exception:
+            pass
+    if os.path.exists(native):
+        path, desc = native, "-Ofast -march=native (built on this host)"
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", ROOT, "oracle_fast"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    o = Oracle.__new__(Oracle)
+    o.L = ctypes.CDLL(path)
+    o.L.lmco_scene_load.restype = ctypes.c_void_p
+    o.L.lmco_last_error.restype = ctypes.c_char_p
+    return o, desc
+
+
+def cpu_chain_rate(o, threads, budget_s, workload=HEADLINE):
+    """Times the CPU oracle's chain loop (restatement of src/mlt.cpp:60-196, same options, cache off) on
+    `threads` host threads for roughly budget_s seconds.  Returns (mut/s, sample text)."""
+    wl = WORKLOADS[workload]
+    h = o.load(os.path.join(ROOT, "scenes", wl["xml"]))
+    for k, v in wl["opts"].items():
+        o.set_option(h, k, v)
     # when the reference's generated gradient code was built (oracle/_ref), the CPU arm evaluates
     # gradients with it (reverse mode, as the reference does) instead of the twin's evaluator
-    ref_grad = o.use_reference_gradient(True) > 0
-    chains, steps = 256 * threads, 32
+    ref_grad = wl["kind"] == "lmc" and o.use_reference_gradient(True) > 0
+    chains, steps = 256 * threads, 16
     norm, init_ls = o.mlt_init(h, 300000, chains, 32)
     t0 = time.time()
     o.run_chains(h, chains, steps, norm, init_ls, threads=threads, want_trace=False, samples_per_chain=steps)
-    dt = time.time() - t0
-    rate = chains * steps / dt
-    # size the measured run from the probe
-    steps2 = int(max(32, min(4096, budget_s * rate / chains)))
+    rate = chains * steps / (time.time() - t0)
+    steps2 = int(max(16, min(4096, budget_s * rate / chains)))      # size the measured run from the probe
     t0 = time.time()
     o.run_chains(h, chains, steps2, norm, init_ls, threads=threads, want_trace=False, samples_per_chain=steps2)
     dt = time.time() - t0
-    return chains * steps2 / dt, "%d chains x %d mutations, torus maxdepth %d, %d threads, gradient = %s" % (
-        chains, steps2, maxdepth, threads, "reference generated code (oracle/_ref)" if ref_grad else "oracle evaluator")
+    return chains * steps2 / dt, "%d chains x %d mutations, %s, %d threads, gradient = %s" % (
+        chains, steps2, workload, threads, "reference generated code (oracle/_ref, ispc -O3 fast-math)" if ref_grad
+        else "oracle evaluator")
 
 
 def run_reference_arm(args):
@@ -125,23 +176,130 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    o, build = _timing_oracle()
     vals, sample = [], ""
     for _ in range(args.warmup):
-        cpu_chain_rate(threads, 1.0)
+        cpu_chain_rate(o, threads, 1.0)
     for _ in range(args.steps):
-        v, sample = cpu_chain_rate(threads, max(2.0, 40.0 / max(1, args.steps)))
+        v, sample = cpu_chain_rate(o, threads, max(2.0, 40.0 / max(1, args.steps)))
         vals.append(v)
     value = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "mutations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "bundled torus scene (scenes/torus), synthetic chain seeds",
-            "config": {"workload": "torus LMC maxdepth 8, cache off (BASELINE configs[1] options)", "chains": 256 * threads,
-                       "note": "reference's own binary is unbuildable here (Embree/OIIO/Eigen/tup absent); this is the "
-                               "oracle port of its chain loop on all host cores"},
-            "cpu_baseline": {"value": value, "unit": "mutations/s", "cores": threads, "kind": "port", "sample": sample},
+            "vs_baseline": None, "dtype": "f32",
+            "data": "bundled torus scene (scenes/torus), chains seeded by MLTInit (300000 init paths), PCG seeds = chain ids",
+            "config": {"workload": WORKLOADS[HEADLINE]["text"], "chains": 256 * threads,
+                       "note": "the reference's own binary is unbuildable here (Embree/OIIO/Eigen/tup absent); this is the "
+                               "oracle port of its chain loop, timing build " + build + ", on all host cores; the "
+                               "reference's published torus LMC run is 4.31 M mutations/s on 32 cores (135 k/s/core, cache on)"},
+            "cpu_baseline": {"value": value, "unit": "mutations/s", "cores": threads, "kind": "port", "sample": sample,
+                             "build": build},
             "e2e": {"value": value, "unit": "mutations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# device arm
+# ------------------------------------------------------------------------------------------------
+def device_run(lmc, torch, dist, workload, n_local, M, K, W, rank, world, local, want_e2e):
+    """W warm-up + K timed steps of `workload`; returns a dict of measurements (rank-local except ms = max)."""
+    wl = WORKLOADS[workload]
+    scene = lmc.ParseScene(os.path.join(ROOT, "scenes", wl["xml"]))
+    for k, v in wl["opts"].items():
+        scene.options[k] = v
+    total = n_local * world
+    stream = torch.cuda.current_stream()
+    # ---- setup (untimed): MLTInit, every rank generates the init paths of its own logical threads ----
+    t_setup = time.time()
+    ctx = lmc.ChainContext(scene, local, stream=stream.cuda_stream)
+    init_t = torch.zeros(total + 1, dtype=torch.float32, device="cuda")
+    if rank == 0:
+        norm, init_ls = ctx.mlt_init(max(300000, 4 * total), total, 65536)
+        init_t[0] = norm
+        init_t[1:] = torch.from_numpy(init_ls).cuda()
+    if world > 1:
+        dist.broadcast(init_t, 0)
+    norm = float(init_t[0].item())
+    init_ls = init_t[1:].cpu().numpy()
+    setup_s = time.time() - t_setup
+
+    film_t = torch.zeros(scene.height, scene.width, 3, dtype=torch.float32, device="cuda")
+    ctx.film_bind(film_t.data_ptr())
+    ctx.begin(n_local, norm, init_ls, chain_base=rank * n_local, total_chains=total, samples_per_chain=M * (K + W))
+    for _ in range(W):
+        ctx.run(M)
+    torch.cuda.synchronize()
+    launches0 = ctx.stats()["kernel_launches"]
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(K):
+        ctx.run(M)
+    if world > 1:
+        dist.all_reduce(film_t)           # the single NCCL all-reduce of the fp32 film
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    ms = ev0.elapsed_time(ev1)
+    st = ctx.stats()
+    launches = st["kernel_launches"] - launches0 - 1   # minus the stats kernel itself
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    res = dict(ms=ms, value=float(total) * M * K / (ms * 1e-3), launches=int(launches), kernel_ms=st["last_kernel_ms"],
+               clocks=sampler.result(), setup_s=setup_s, stats=st, scene=scene)
+
+    if want_e2e:
+        # ---- e2e through the public API with HOST buffers: lmc_chains_begin uploads this job's init scores from
+        # pinned memory (H2D), then K steps of lmc_run_chains, each followed by a read of the step's result -- the
+        # progressive film, like the reference's reportIntervalSpp dump (src/mlt.cpp:171-193) -- into pinned host
+        # memory (D2H).  Chains continue across the K steps (same large-step schedule as the device-timed region).
+        pinned_init = torch.from_numpy(init_ls).pin_memory()
+        host_film = torch.empty(scene.height, scene.width, 3, dtype=torch.float32).pin_memory()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        ctx.begin(n_local, norm, pinned_init.numpy(), chain_base=rank * n_local, total_chains=total, samples_per_chain=M * K)
+        for _ in range(K):
+            ctx.run(M)
+            if world > 1:
+                dist.all_reduce(film_t)
+            host_film.copy_(film_t, non_blocking=False)
+        torch.cuda.synchronize()
+        e2e_s = time.time() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        res["e2e"] = {"value": float(total) * M * K / e2e_s, "unit": "mutations/s",
+                      "h2d_bytes_per_step": int(4 * total / K), "d2h_bytes_per_step": int(scene.height * scene.width * 3 * 4),
+                      "steps": K, "note": "begin (H2D init scores, once) + K x (run + film D2H); chains continue across steps"}
+    ctx.close()
+    del film_t
+    torch.cuda.empty_cache()
+    return res
+
+
+def roofline(res, workload, n_local, M, K, peak, peak_src, world):
+    wl = WORKLOADS[workload]
+    b = algo_bytes(wl["kind"], wl["L"])
+    k_ms = res["kernel_ms"] if res["kernel_ms"] and res["kernel_ms"] > 0 else res["ms"] / K
+    achieved = (float(n_local) * M * b) / (k_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": (DRAM_BYTES_PER_MUTATION_NCU * float(n_local) * M) if (DRAM_BYTES_PER_MUTATION_NCU and workload == HEADLINE) else None,
+            "kernel": "one lmc_run_chains call = M chain-loop iterations (k_wave_grad, k_trace, k_shade<...>, "
+                      "k_wave_finish+begin ...; per-kernel shares in profiles/)",
+            "algorithmic_bytes_per_mutation": b, "kernel_ms_per_launch": k_ms, "peak_source": peak_src,
+            "per_gpu_mutations_per_s": res["value"] / world}
 
 
 def main():
@@ -153,6 +311,7 @@ def main():
     ap.add_argument("--chains-per-gpu", type=int, default=CHAINS_PER_GPU)
     ap.add_argument("--mutations-per-step", type=int, default=MUTATIONS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -168,124 +327,48 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lmc = load_package()
-    scene = lmc.ParseScene(SCENE_XML)
-    scene.options["maxdepth"] = MAXDEPTH
-    n_local = args.chains_per_gpu
-    total = n_local * world
-    M, K, W = args.mutations_per_step, args.steps, args.warmup
+    n_local, M, K, W = args.chains_per_gpu, args.mutations_per_step, args.steps, args.warmup
+    peak, peak_src = measured_peak()
 
-    # ---- setup (untimed): MLTInit (init paths generated on rank 0's GPU, lmc_mlt_init_device), broadcast ----
-    t_setup = time.time()
-    stream = torch.cuda.current_stream()
-    ctx = lmc.ChainContext(scene, local, stream=stream.cuda_stream)
-    init_t = torch.zeros(total + 1, dtype=torch.float32, device="cuda")
-    if rank == 0:
-        norm, init_ls = ctx.mlt_init(max(300000, 4 * total), total, 65536)
-        init_t[0] = norm
-        init_t[1:] = torch.from_numpy(init_ls).cuda()
-    if world > 1:
-        dist.broadcast(init_t, 0)
-    norm = float(init_t[0].item())
-    init_ls = init_t[1:].cpu().numpy()
-    setup_s = time.time() - t_setup
-
-    film_t = torch.zeros(scene.height, scene.width, 3, dtype=torch.float32, device="cuda")
-    ctx.film_bind(film_t.data_ptr())
-    total_mut_per_chain = M * (K + W)
-    ctx.begin(n_local, norm, init_ls, chain_base=rank * n_local, total_chains=total, samples_per_chain=total_mut_per_chain)
-    for _ in range(W):
-        ctx.run(M)
-    torch.cuda.synchronize()
-    launches0 = ctx.stats()["kernel_launches"]
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    ev0.record(stream)
-    for _ in range(K):
-        ctx.run(M)
-    if world > 1:
-        dist.all_reduce(film_t)           # the single NCCL all-reduce of the fp32 film
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler.stop_flag = True
-    ms = ev0.elapsed_time(ev1)
-    st = ctx.stats()
-    kernel_ms.append(st["last_kernel_ms"])
-    launches = st["kernel_launches"] - launches0 - 1   # minus the stats kernel itself
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    mutations = float(total) * M * K
-    value = mutations / (ms * 1e-3)
-
-    # ---- e2e: the public API with host buffers: begin (H2D init scores) -> run -> film D2H ----
-    e2e_steps = max(1, min(K, 2))
-    pinned_init = torch.from_numpy(init_ls).pin_memory()
-    host_film = torch.empty(scene.height, scene.width, 3, dtype=torch.float32).pin_memory()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.time()
-    for _ in range(e2e_steps):
-        ta = time.time()
-        ctx.begin(n_local, norm, pinned_init.numpy(), chain_base=rank * n_local, total_chains=total, samples_per_chain=M)
-        tb = time.time()
-        ctx.run(M)
-        if world > 1:
-            dist.all_reduce(film_t)
-        tc = time.time()
-        host_film.copy_(film_t, non_blocking=False)
-        if os.environ.get("LMC_BENCH_VERBOSE"):
-            print("e2e step: begin call %.1f ms, run call %.1f ms, film copy (incl. wait) %.1f ms" % (
-                (tb - ta) * 1e3, (tc - tb) * 1e3, (time.time() - tc) * 1e3), file=sys.stderr)
-    torch.cuda.synchronize()
-    e2e_s = time.time() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = float(total) * M * e2e_steps / e2e_s
-    film_bytes = scene.height * scene.width * 3 * 4
+    res = device_run(lmc, torch, dist, HEADLINE, n_local, M, K, W, rank, world, local, want_e2e=True)
+    extra = {}
+    if not args.no_extra_configs:
+        for name in ("door_lmc_L12", "torus_h2mc_L8"):
+            m2 = max(4, M // 2)
+            r2 = device_run(lmc, torch, dist, name, n_local, m2, 2, 1, rank, world, local, want_e2e=False)
+            extra[name] = {"workload": WORKLOADS[name]["text"], "value": r2["value"], "unit": "mutations/s", "n_gpus": world,
+                           "steps": 2, "warmup": 1, "mutations_per_step": m2, "ms_per_step": r2["ms"] / 2,
+                           "gpu_launches": r2["launches"], "roofline": roofline(r2, name, n_local, m2, 2, peak, peak_src, world),
+                           "accepted": r2["stats"]["accepted"], "proposed": r2["stats"]["proposed"]}
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        per_gpu_rate = value / world
-        # dominant kernel = k_chain_run: algorithmic bytes per launch / its mean launch time
-        k_ms = kernel_ms[-1] if kernel_ms and kernel_ms[-1] > 0 else ms / K
-        achieved = (float(n_local) * M * ALGO_BYTES_PER_MUTATION) / (k_ms * 1e-3) / 1e9
-        line = {"metric": METRIC, "value": value, "unit": "mutations/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        st = res["stats"]
+        line = {"metric": METRIC, "value": res["value"], "unit": "mutations/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": res["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "bundled torus scene (scenes/torus), chains seeded by MLTInit, PCG seeds = chain ids",
-                "config": {"workload": "torus, LMC (mala), maxdepth 8, 2^20 chains per GPU, global cache off",
-                           "chains_per_gpu": n_local, "mutations_per_step": M, "l2": "inputs larger than L2 (6 GB of chain records + wavefront queues)",
-                           "setup_s": round(setup_s, 2), "film_allreduce": world > 1},
-                "e2e": {"value": e2e_value, "unit": "mutations/s", "h2d_bytes_per_step": int(4 * total),
-                        "d2h_bytes_per_step": int(film_bytes), "steps": e2e_steps},
-                "gpu_launches": int(launches),
-                "clocks": sampler.result(),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": DRAM_BYTES_PER_MUTATION_NCU * float(n_local) * M,
-                             "kernel": "one lmc_run_chains call = M chain-loop iterations of 48 launches each (k_wave_grad, k_trace, "
-                                       "k_shade<P_CAM/G_CAM>, k_wave_finish+begin ...; shares in profiles/r01_launches_pervertex_2p20_summary.txt)",
-                             "algorithmic_bytes_per_mutation": ALGO_BYTES_PER_MUTATION,
-                             "kernel_ms_per_launch": k_ms, "peak_source": peak_src,
-                             "per_gpu_mutations_per_s": per_gpu_rate},
+                "config": {"workload": WORKLOADS[HEADLINE]["text"], "chains_per_gpu": n_local, "mutations_per_step": M,
+                           "gradient": "reverse sweep in the reference's merge order (adjointcompat = 1)",
+                           "l2": "inputs larger than L2 (GBs of chain records + wavefront queues)",
+                           "setup_s": round(res["setup_s"], 2), "film_allreduce": world > 1},
+                "e2e": res["e2e"], "gpu_launches": res["launches"], "clocks": res["clocks"],
+                "roofline": roofline(res, HEADLINE, n_local, M, K, peak, peak_src, world),
                 "stats": {"accepted": st["accepted"], "proposed": st["proposed"], "gradient_evals": st["gradient_evals"],
-                          "gradient_nonfinite": st["gradient_nonfinite"]}}
+                          "gradient_nonfinite": st["gradient_nonfinite"]},
+                "extra": {"configs": extra}}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, sample = cpu_chain_rate(threads, 12.0)
-            line["cpu_baseline"] = {"value": v, "unit": "mutations/s", "cores": threads, "kind": "port", "sample": sample}
+            o, build = _timing_oracle()
+            v, sample = cpu_chain_rate(o, threads, 12.0)
+            line["cpu_baseline"] = {"value": v, "unit": "mutations/s", "cores": threads, "kind": "port", "sample": sample,
+                                    "build": build}
+            try:       # the parity build (-O2, no fast-math, double-precision deterministic math) for comparison
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                from conftest import Oracle
+                vp, _ = cpu_chain_rate(Oracle(), threads, 4.0)
+                line["cpu_baseline"]["parity_build_value"] = vp
+            except Exception:
+                pass
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

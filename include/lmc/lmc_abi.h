@@ -18,6 +18,14 @@
  *   lmc_eval_batch                       PathFunc / PathFuncDerv         src/path.h:121-125 (dlsym'd
  *                                        evaluate_path_bidir_mala_<c>_<l>_static[_derv], src/path.cpp:3389-3417)
  *   lmc_bvh_probe                        Intersect / Occluded            src/scene.cpp:106-149 (rtcIntersect1 / rtcOccluded1)
+ *   lmc_merge_buffer / lmc_write_image   MergeBuffer, BufferToFilm,      src/image.h:79-105, src/image.cpp:29-60
+ *                                        WriteImage                      (end of MLT(), src/mlt.cpp:203-212, and the
+ *                                                                        progressive dump, src/mlt.cpp:171-193)
+ *   lmc_create_multi / lmc_comm_* /      the shared SampleBuffer all     src/mlt.cpp:55 (indirectBuffer), src/image.h:66-77;
+ *   lmc_allreduce_film                   chain threads splat into        one ctx per GPU + one NCCL all-reduce
+ *
+ * C++ mirror of the reference's plugin-surface headers (same type and field names) over this ABI:
+ * include/lmc/{dptoptions,parsescene,bsdf,mutation,mlt}.h.
  */
 #ifndef LMC_ABI_H
 #define LMC_ABI_H
@@ -44,6 +52,7 @@ typedef struct lmc_scene_info {
     int32_t width, height;       /* film */
     int32_t num_triangles, num_bvh_nodes, num_lights, num_shapes, num_textures;
     int32_t spp, direct_spp, num_init_samples; /* <dpt> spp / directspp / numinitsamples */
+    int32_t report_interval_spp;               /* <dpt> reportintervalspp (0 = no progressive dumps) */
 } lmc_scene_info;
 
 /* counters accumulated by lmc_run_chains (sum over the ctx's chains since lmc_chains_begin) */
@@ -54,6 +63,7 @@ typedef struct lmc_stats {
     uint64_t gradient_nonfinite; /* gradients zeroed by the IsFinite guard, src/mutation_mala.h:108-110 */
     uint64_t kernel_launches;    /* CUDA kernels launched by this ctx so far */
     double last_kernel_ms;       /* device time of the chain kernels of the last lmc_run_chains (CUDA events) */
+    uint64_t outlier_resets;     /* chain resets of the "stuck chain" rule, src/mlt.cpp:147-169 */
 } lmc_stats;
 
 /* chain-run descriptor: the loop-invariant inputs of the lambda at src/mlt.cpp:60-90 */
@@ -126,6 +136,26 @@ int lmc_film_read(lmc_ctx *ctx, float *host_rgb);          /* D2H copy, synchron
 int lmc_film_device_ptr(lmc_ctx *ctx, void **device_ptr);  /* for an NCCL all-reduce by the caller */
 /* Use caller-owned device memory (W*H*3 floats) as the film, e.g. a torch tensor */
 int lmc_film_bind(lmc_ctx *ctx, void *device_ptr);
+
+/* ---- multi-GPU: one ctx per device, chains sharded by global id, ONE collective --------------------------------- */
+/* One process, n devices: creates a ctx on each and an NCCL communicator over them (ncclCommInitAll).  out[n]. */
+int lmc_create_multi(const lmc_scene *scene, const int32_t *devices, int32_t n, lmc_ctx **out);
+/* One process per GPU: rank 0 calls lmc_comm_unique_id (128 bytes, an ncclUniqueId), hands it to the other ranks
+ * by any side channel (MPI, torch.distributed, a file); every rank then calls lmc_comm_init_rank on its ctx. */
+int lmc_comm_unique_id(void *id128);
+int lmc_comm_init_rank(lmc_ctx *ctx, int32_t nranks, int32_t rank, const void *id128);
+/* Sum of the films of a job, in place, asynchronous on each ctx's stream (ncclAllReduce, fp32, sum).  ctxs[n]: all
+ * ctx of THIS process that belong to the communicator (n = 1 with lmc_comm_init_rank, n = the device count with
+ * lmc_create_multi).  Statistics are not reduced: add lmc_get_stats over the ctx / ranks. */
+int lmc_allreduce_film(lmc_ctx **ctxs, int32_t n);
+
+/* ---- film output (host) ----------------------------------------------------------------------------------------- */
+/* film[i] = w1 * buffer1[i] + w2 * buffer2[i] for n floats: MergeBuffer + BufferToFilm (src/image.h:79-105), called
+ * by MLT() with (direct, 1/directSpp, indirect, 1/spp) (src/mlt.cpp:203-207).  Either buffer may be NULL (= zeros). */
+int lmc_merge_buffer(const float *buffer1, float w1, const float *buffer2, float w2, int64_t n, float *film);
+/* WriteImage (src/image.cpp:29-60): rgb = H x W x 3 floats, row 0 on top.  ".exr" -> OpenEXR scan-line file with
+ * three uncompressed 32-bit float channels; ".pfm" -> portable float map. */
+int lmc_write_image(const char *path, int32_t width, int32_t height, const float *rgb);
 
 /* ---- fine-grained boundary (parity harness) ------------------------------------------------- */
 /* n serialized paths of class (cam_depth, light_depth) in the reference's buffer layout

@@ -22,13 +22,15 @@ class MutationType(enum.IntEnum):  # src/mutation.h:11
 
 class _SceneInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("width", "height", "num_triangles", "num_bvh_nodes", "num_lights",
-                                              "num_shapes", "num_textures", "spp", "direct_spp", "num_init_samples")]
+                                              "num_shapes", "num_textures", "spp", "direct_spp", "num_init_samples",
+                                              "report_interval_spp")]
 
 
 class _Stats(ctypes.Structure):
     _fields_ = [("proposed", ctypes.c_uint64 * 4), ("accepted", ctypes.c_uint64 * 4),
                 ("gradient_evals", ctypes.c_uint64), ("gradient_nonfinite", ctypes.c_uint64),
-                ("kernel_launches", ctypes.c_uint64), ("last_kernel_ms", ctypes.c_double)]
+                ("kernel_launches", ctypes.c_uint64), ("last_kernel_ms", ctypes.c_double),
+                ("outlier_resets", ctypes.c_uint64)]
 
 
 class _RunDesc(ctypes.Structure):
@@ -72,6 +74,9 @@ def load_library():
         "lmc_eval_batch": (i32, [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
         "lmc_vert_param_size": (i32, [i32, i32]),
         "lmc_bvh_probe": (i32, [vp, i32, vp, f32, f32, i32, vp, vp, vp]),
+        "lmc_create_multi": (i32, [vp, vp, i32, vp]), "lmc_comm_unique_id": (i32, [vp]),
+        "lmc_comm_init_rank": (i32, [vp, i32, i32, vp]), "lmc_allreduce_film": (i32, [vp, i32]),
+        "lmc_merge_buffer": (i32, [vp, f32, vp, f32, i64, vp]), "lmc_write_image": (i32, [cp, i32, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -156,8 +161,26 @@ def MLTInit(scene, numInitSamples=None, numChains=None, logicalThreads=32):
 
 
 def MergeBuffer(buffer1, b1Weight, buffer2, b2Weight):
-    """src/image.h:79-98 followed by BufferToFilm (:100-105): film = b1Weight * buffer1 + b2Weight * buffer2."""
-    return np.float32(b1Weight) * np.asarray(buffer1, np.float32) + np.float32(b2Weight) * np.asarray(buffer2, np.float32)
+    """src/image.h:79-98 followed by BufferToFilm (:100-105): film = b1Weight * buffer1 + b2Weight * buffer2
+    (lmc_merge_buffer)."""
+    b1 = np.ascontiguousarray(buffer1, np.float32)
+    b2 = np.ascontiguousarray(buffer2, np.float32)
+    out = np.empty_like(b1)
+    _check(load_library().lmc_merge_buffer(_ptr(b1), float(b1Weight), _ptr(b2), float(b2Weight), b1.size, _ptr(out)))
+    return out
+
+
+def WriteImage(filename, film):
+    """src/image.cpp:29-60: H x W x 3 float film -> OpenEXR (".exr", three uncompressed float channels) or ".pfm"."""
+    film = np.ascontiguousarray(film, np.float32)
+    _check(load_library().lmc_write_image(filename.encode(), film.shape[1], film.shape[0], _ptr(film)))
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, every rank passes it to ChainContext.comm_init)."""
+    buf = np.zeros(128, np.uint8)
+    _check(load_library().lmc_comm_unique_id(_ptr(buf)))
+    return buf
 
 
 def decode_trace(trace):
@@ -194,8 +217,20 @@ class ChainContext:
         _check(load_library().lmc_direct_lighting(self._c, int(direct_spp), _ptr(out)))
         return out
 
-    def begin(self, num_chains, normalization, init_ls_score=None, chain_base=0, total_chains=None,
-              samples_per_chain=0):
+    def comm_init(self, nranks, rank, unique_id):
+        """Join the film communicator of a one-process-per-GPU job (lmc_comm_init_rank)."""
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        _check(load_library().lmc_comm_init_rank(self._c, int(nranks), int(rank), _ptr(uid)))
+
+    def allreduce_film(self):
+        """Sum of the films of the job, in place, asynchronous on this ctx's stream (lmc_allreduce_film)."""
+        arr = (ctypes.c_void_p * 1)(self._c)
+        _check(load_library().lmc_allreduce_film(arr, 1))
+
+    def begin(self, num_chains, normalization, init_ls_score=None, chain_base=0, total_chains=None, *,
+              samples_per_chain):
+        """samples_per_chain = numSamplesThisChain of the whole run (src/mlt.cpp:64-65): the large-step schedule
+        (LS_RATIO, src/mlt.cpp:96) depends on it, so it has no default."""
         d = _RunDesc()
         d.num_chains = int(num_chains)
         d.chain_base = int(chain_base)
@@ -223,7 +258,7 @@ class ChainContext:
         _check(load_library().lmc_get_stats(self._c, ctypes.byref(s)))
         return {"proposed": list(s.proposed), "accepted": list(s.accepted), "gradient_evals": s.gradient_evals,
                 "gradient_nonfinite": s.gradient_nonfinite, "kernel_launches": s.kernel_launches,
-                "last_kernel_ms": s.last_kernel_ms}
+                "last_kernel_ms": s.last_kernel_ms, "outlier_resets": s.outlier_resets}
 
     def film(self):
         out = np.zeros((self.scene.height, self.scene.width, 3), np.float32)
@@ -278,20 +313,31 @@ class ChainContext:
             pass
 
 
-def MLT(scene, numChains=None, mutationsPerChain=None, device=0, logicalThreads=32, numInitSamples=None):
-    """The chain phase of MLT() (src/mlt.cpp:20-215): MLTInit on the host, the chain loop on the
-    GPU.  Returns (indirect film / spp-equivalent as H x W x 3, stats).  The direct-lighting
-    pre-pass and EXR output of the reference are out of scope."""
+def MLT(scene, numChains=None, mutationsPerChain=None, device=0, logicalThreads=32, numInitSamples=None, directSpp=None,
+        outputName=None):
+    """MLT() (src/mlt.cpp:20-215) on one GPU: DirectLighting pre-pass, MLTInit on the host, the chain loop on the
+    GPU, MergeBuffer(direct / directSpp, indirect / spp) -> film, optional WriteImage.  Returns (film H x W x 3,
+    stats).  Known deviations from the reference's MLT(): every chain runs mutationsPerChain iterations (the
+    reference adds one to chainId < numSamplesPerChain % numChains, src/mlt.cpp:40,64-65); the global cache is not
+    built, so LMC keeps evaluating gradients where the reference switches to cached moments (src/mutation_mala.h:131-161);
+    a gradient that is not evaluated because ssScore <= 1e-10 is zero instead of the stale vector the reference
+    reuses.  The C++ form with multi-GPU sharding and progressive dumps is include/lmc/mlt.h."""
     if numChains is None:
         numChains = int(scene.options["numchains"])
     if mutationsPerChain is None:
         mutationsPerChain = scene.info["spp"] * scene.width * scene.height // numChains
+    if directSpp is None:
+        directSpp = scene.info["direct_spp"]
     norm, init_ls = MLTInit(scene, numInitSamples, numChains, logicalThreads)
     ctx = ChainContext(scene, device)
+    direct = ctx.direct_lighting(directSpp) if directSpp > 0 else np.zeros((scene.height, scene.width, 3), np.float32)
     ctx.begin(numChains, norm, init_ls, samples_per_chain=mutationsPerChain)
     ctx.run(mutationsPerChain)
-    film = ctx.film()
+    indirect = ctx.film()
     stats = ctx.stats()
     ctx.close()
     spp = numChains * mutationsPerChain / float(scene.width * scene.height)
-    return film / np.float32(spp), stats
+    film = MergeBuffer(direct, 1.0 / directSpp if directSpp > 0 else 0.0, indirect, 1.0 / spp if spp > 0 else 0.0)
+    if outputName:
+        WriteImage(outputName, film)
+    return film, stats

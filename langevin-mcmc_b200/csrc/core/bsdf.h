@@ -67,10 +67,6 @@ LMC_HD BsdfParams bsdf_params(const Scene &sc, int geom, V2 st) {
     return p;
 }
 
-// BSDF::Roughness (lambertian.h:37-39, phong.cpp:155-157, roughdielectric.h:61-63)
-LMC_HD float bsdf_roughness(const BsdfParams &p) {
-    return (p.type == BSDF_ROUGHDIELECTRIC) ? p.alpha : 1.0f;
-}
 
 // ---- sampling helpers ---------------------------------------------------------------------
 // src/sampling.h:104-109 (ADEpsilon<Float>() == 0)
@@ -395,18 +391,58 @@ LMC_HD bool roughdielectric_sample(bool adjoint, const BsdfParams &p, V3 wi, V3 
     return true;
 }
 
-// ---- dispatch (replaces the virtual calls of src/bsdf.h:10-68) ------------------------------
+// ---- the BSDF table (replaces the virtual calls of struct BSDF, src/bsdf.h:10-68) -----------------------------
+// A device kernel cannot call a virtual per mutation, so the reference's plugin surface becomes an enum-keyed table:
+// one row per BSDFType (include/lmc/bsdf.h mirrors the enum) naming the row's entry points, all with the SAME
+// signatures:
+//   <name>_evaluate (bool adjoint, const BsdfParams &, wi, normal, wo,                 contrib, cosWo, pdf, revPdf)
+//   <name>_sample   (bool adjoint, const BsdfParams &, wi, normal, rnd, uDiscrete, wo,  contrib, cosWo, pdf, revPdf)
+//   <name>_roughness(const BsdfParams &)
+// The dispatchers below are generated from the table.  Adding a BSDF = a new enum value in core/scene.h, its three
+// entry points, one row here, its parameters in BsdfParams / serialize_bsdf (the 10-float record of App. A.4), and its
+// differentiable twin as a row of BSDF_TABLE in tools/adgen/pathfn.py (the adjoint is then generated, not written).
+#define LMC_BSDF_TABLE(ROW) \
+    ROW(BSDF_LAMBERTIAN, lambertian) \
+    ROW(BSDF_PHONG, phong) \
+    ROW(BSDF_ROUGHDIELECTRIC, roughdielectric)
+
+LMC_HD void lambertian_evaluate(bool, const BsdfParams &p, V3 wi, V3 n, V3 wo, V3 &c, float &cw, float &pdf, float &rp) { lambertian_eval(p, wi, n, wo, c, cw, pdf, rp); }
+LMC_HD bool lambertian_sample(bool, const BsdfParams &p, V3 wi, V3 n, V2 rnd, float, V3 &wo, V3 &c, float &cw, float &pdf, float &rp) { return lambertian_sample(p, wi, n, rnd, wo, c, cw, pdf, rp); }
+LMC_HD float lambertian_roughness(const BsdfParams &) { return 1.0f; }                 // src/lambertian.h:37-39
+LMC_HD void phong_evaluate(bool, const BsdfParams &p, V3 wi, V3 n, V3 wo, V3 &c, float &cw, float &pdf, float &rp) { phong_eval(p, wi, n, wo, c, cw, pdf, rp); }
+LMC_HD bool phong_sample(bool, const BsdfParams &p, V3 wi, V3 n, V2 rnd, float, V3 &wo, V3 &c, float &cw, float &pdf, float &rp) { return phong_sample(p, wi, n, rnd, wo, c, cw, pdf, rp); }
+LMC_HD float phong_roughness(const BsdfParams &) { return 1.0f; }                      // src/phong.cpp:155-157
+LMC_HD void roughdielectric_evaluate(bool adjoint, const BsdfParams &p, V3 wi, V3 n, V3 wo, V3 &c, float &cw, float &pdf, float &rp) { roughdielectric_eval(adjoint, p, wi, n, wo, c, cw, pdf, rp); }
+LMC_HD float roughdielectric_roughness(const BsdfParams &p) { return p.alpha; }        // src/roughdielectric.h:61-63
+
+// BSDF::Evaluate / EvaluateAdjoint
 LMC_HD_NOINLINE void bsdf_eval(bool adjoint, const BsdfParams &p, V3 wi, V3 normal, V3 wo,
                       V3 &contrib, float &cosWo, float &pdf, float &revPdf) {
-    if (p.type == BSDF_LAMBERTIAN) lambertian_eval(p, wi, normal, wo, contrib, cosWo, pdf, revPdf);
-    else if (p.type == BSDF_PHONG) phong_eval(p, wi, normal, wo, contrib, cosWo, pdf, revPdf);
-    else roughdielectric_eval(adjoint, p, wi, normal, wo, contrib, cosWo, pdf, revPdf);
+    switch (p.type) {
+#define LMC_ROW(ID, name) case ID: name##_evaluate(adjoint, p, wi, normal, wo, contrib, cosWo, pdf, revPdf); return;
+        LMC_BSDF_TABLE(LMC_ROW)
+#undef LMC_ROW
+    }
+    contrib = mk3s(0.0f); cosWo = 0.0f; pdf = 0.0f; revPdf = 0.0f;
 }
+// BSDF::Sample / SampleAdjoint
 LMC_HD_NOINLINE bool bsdf_sample(bool adjoint, const BsdfParams &p, V3 wi, V3 normal, V2 rnd, float uDiscrete,
                         V3 &wo, V3 &contrib, float &cosWo, float &pdf, float &revPdf) {
-    if (p.type == BSDF_LAMBERTIAN) return lambertian_sample(p, wi, normal, rnd, wo, contrib, cosWo, pdf, revPdf);
-    if (p.type == BSDF_PHONG) return phong_sample(p, wi, normal, rnd, wo, contrib, cosWo, pdf, revPdf);
-    return roughdielectric_sample(adjoint, p, wi, normal, rnd, uDiscrete, wo, contrib, cosWo, pdf, revPdf);
+    switch (p.type) {
+#define LMC_ROW(ID, name) case ID: return name##_sample(adjoint, p, wi, normal, rnd, uDiscrete, wo, contrib, cosWo, pdf, revPdf);
+        LMC_BSDF_TABLE(LMC_ROW)
+#undef LMC_ROW
+    }
+    return false;
+}
+// BSDF::Roughness
+LMC_HD float bsdf_roughness(const BsdfParams &p) {
+    switch (p.type) {
+#define LMC_ROW(ID, name) case ID: return name##_roughness(p);
+        LMC_BSDF_TABLE(LMC_ROW)
+#undef LMC_ROW
+    }
+    return 1.0f;
 }
 
 }  // namespace lmc

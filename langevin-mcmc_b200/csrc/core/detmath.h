@@ -202,6 +202,19 @@ LMC_HD_NOINLINE double dm_atan2_d(double y, double x) {
 // ---------------------------------------------------------------------------------------
 // float front-ends
 // ---------------------------------------------------------------------------------------
+#if defined(LMC_TIMING_LIBM) && !defined(__CUDACC__)
+// TIMING build of the CPU oracle only (`make oracle_fast`, used by bench.py's CPU arm): the platform libm in
+// single precision, as the reference is built (`g++ -Ofast -march=native`, src/Tupfile:17).  Results are NOT
+// bit-reproducible; no parity test uses this build.
+LMC_HD float dm_sin(float x) { return sinf(x); }
+LMC_HD float dm_cos(float x) { return cosf(x); }
+LMC_HD void dm_sincos(float x, float &s, float &c) { s = sinf(x); c = cosf(x); }
+LMC_HD float dm_exp(float x) { return expf(x); }
+LMC_HD float dm_log(float x) { return logf(x); }
+LMC_HD float dm_pow(float x, float y) { return powf(x, y); }
+LMC_HD float dm_atan2(float y, float x) { return atan2f(y, x); }
+LMC_HD float dm_acos(float x) { return acosf(x < -1.0f ? -1.0f : (x > 1.0f ? 1.0f : x)); }
+#else
 LMC_HD float dm_sin(float x) { double s, c; dm_sincos_d((double)x, s, c); return (float)s; }
 LMC_HD float dm_cos(float x) { double s, c; dm_sincos_d((double)x, s, c); return (float)c; }
 LMC_HD void dm_sincos(float x, float &s, float &c) {
@@ -233,6 +246,7 @@ LMC_HD float dm_acos(float x) {
     if (xd < -1.0) xd = -1.0;
     return (float)dm_atan2_d(sqrt((1.0 - xd) * (1.0 + xd)), xd);
 }
+#endif
 
 // ---------------------------------------------------------------------------------------
 // Mineiro fastlog / fastpow (bit tricks; fastmath.h:364-381, 233-242, 1186-1190).

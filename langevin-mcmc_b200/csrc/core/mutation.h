@@ -25,9 +25,7 @@ enum MutationType { MUT_LARGE = 0, MUT_SMALL = 1, MUT_H2MC_SMALL = 2, MUT_MALA_S
 #define LMC_PCD_MAX 100.0f
 #define LMC_MTM_MIN (-5.0f)
 #define LMC_MTM_MAX 5.0f
-#define LMC_OUTLIER_WEAK_REJECT_CNT 10000
-#define LMC_OUTLIER_STRONG_REJECT_CNT 1000
-#define LMC_OUTLIER_RATIO_THRESHOLD 30.0f
+// outlier thresholds (src/mutation.h:5-8): Options::outlier* (defaults 10000 / 1000 / 30)
 
 template <int DIM>
 struct Gaussian {                // src/gaussian.h:9-19 (diagonal members only; dense = H2MC)
@@ -118,6 +116,7 @@ struct ChainVars {               // Chain (src/mutation.h:28-43) + per-chain loo
     float lastScoreSum, lastScore;    // LargeStep members (src/mutation_large.h:16-17)
     int adjacentReject;
     int lastMutationType;
+    int outlierResets;                // statistics only: how often the reset of src/mlt.cpp:147-169 fired
 };
 
 template <int MAXD>
@@ -125,7 +124,7 @@ LMC_HD void chain_vars_init(ChainVars<MAXD> &c) {
     for (int i = 0; i < Limits<MAXD>::DIM; i++) {
         c.v1[i] = 0; c.v2[i] = 0; c.curr_new_v1[i] = 0; c.curr_new_v2[i] = 0; c.prop_new_v1[i] = 0; c.prop_new_v2[i] = 0;
     }
-    c.buffered = 0; c.t = 0; c.lastScoreSum = 1.0f; c.lastScore = 1.0f; c.adjacentReject = 0; c.lastMutationType = MUT_LARGE;
+    c.buffered = 0; c.t = 0; c.lastScoreSum = 1.0f; c.lastScore = 1.0f; c.adjacentReject = 0; c.lastMutationType = MUT_LARGE; c.outlierResets = 0;
 }
 
 // Film accumulation (src/image.h:66-77).  FILM is a functor add(pixelIndex, channel, value)
@@ -683,13 +682,13 @@ LMC_HD StepInfo phase_finish(const Scene &sc, const RunParams &rp, int chainId, 
         }
     } else {
         ch.adjacentReject += 1;
-        const bool strongReject = cur.sp.lsScore > LMC_OUTLIER_RATIO_THRESHOLD * rp.normalization;
-        if (ch.adjacentReject > LMC_OUTLIER_WEAK_REJECT_CNT ||
-            (strongReject && ch.adjacentReject > LMC_OUTLIER_STRONG_REJECT_CNT)) {
+        const bool strongReject = cur.sp.lsScore > sc.opt.outlierRatioThreshold * rp.normalization;
+        if (ch.adjacentReject > sc.opt.outlierWeakRejectCnt ||
+            (strongReject && ch.adjacentReject > sc.opt.outlierStrongRejectCnt)) {
             int cid = chainId, cnt = 0;
             for (;;) {
                 cur.sp.lsScore = rp.initLsScore[cid];
-                if (cur.sp.lsScore < LMC_OUTLIER_RATIO_THRESHOLD * rp.normalization) break;
+                if (cur.sp.lsScore < sc.opt.outlierRatioThreshold * rp.normalization) break;
                 cid = (int)(((long long)cid + sampleIdx + (long long)(cnt++)) % (long long)rp.numChains);
                 if (cnt > rp.numChains) break;   // guard: the reference would spin forever
             }
@@ -697,6 +696,7 @@ LMC_HD StepInfo phase_finish(const Scene &sc, const RunParams &rp, int chainId, 
             prop.valid = 0; prop.gaussianInitialized = 0; prop.nSplat = 0;
             path_clear(prop.path);
             ch.buffered = 0;
+            ch.outlierResets += 1;
         }
     }
     return info;

@@ -106,7 +106,11 @@ struct Options {                 // src/dptoptions.h:7-34 + compile-time constan
     int cacheEnabled;            // always 0 here (GlobalCache out of scope)
     int maxDervDepth;            // 8
     int pssMinLength, pssMaxLength;   // 2, 12
-    int adjointCompat;           // 1: reproduce the reference's reverse-mode merge semantics
+    int adjointCompat;           // gradient of the mutations: 1 reverse sweep in the reference's merge order (default),
+                                 // 0 reverse sweep / true adjoint, 2 forward-mode duals (core/pathgrad_rev.h)
+    int outlierWeakRejectCnt;    // OUTLIER_WEAK_REJECT_CNT 10000    (src/mutation.h:6)
+    int outlierStrongRejectCnt;  // OUTLIER_STRONG_REJECT_CNT 1000   (src/mutation.h:7)
+    float outlierRatioThreshold; // OUTLIER_RATIO_THRESHOLD 30       (src/mutation.h:8)
     float perturbStdDev;         // 0.01
     float roughnessThreshold;    // 0.05
     float largeStepProbability;  // 0.05

@@ -223,8 +223,11 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_begin(const __grid_con
 }
 
 // gradient of the current state (which = 0) or of the proposal (which = 1) for a sorted list
+// occupancy of the gradient kernel in units of 128 threads per SM.  The reverse-sweep evaluator is bound by the
+// latency of its local-memory traffic (checkpoints, spills): 4 (two 256-thread blocks, 128 registers) measured
+// 1.69 ms per proposal-gradient launch against 2.28 ms at 2 (255 registers) on 2^20 chains (profiles/r02_*).
 #ifndef LMC_GRAD_MINB
-#define LMC_GRAD_MINB 2
+#define LMC_GRAD_MINB 4
 #endif
 #ifndef LMC_PROP_MINB
 #define LMC_PROP_MINB 4
@@ -825,14 +828,14 @@ __global__ void __launch_bounds__(128) k_mlt_init_paths(const __grid_constant__ 
 template <int MAXD>
 __global__ void k_chain_stats(const ChainRec<MAXD> *states, int n, unsigned long long *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long v[10];
-    for (int k = 0; k < 10; k++) v[k] = 0ULL;
+    unsigned long long v[11];
+    for (int k = 0; k < 11; k++) v[k] = 0ULL;
     if (i < n) {
         const ChainState<MAXD> &cs = states[i].cs;
         for (int k = 0; k < 4; k++) { v[k] = cs.nPropose[k]; v[4 + k] = cs.nAccept[k]; }
-        v[8] = cs.gradStats[0]; v[9] = cs.gradStats[1];
+        v[8] = cs.gradStats[0]; v[9] = cs.gradStats[1]; v[10] = (unsigned long long)cs.ch.outlierResets;
     }
-    for (int k = 0; k < 10; k++) {
+    for (int k = 0; k < 11; k++) {
         unsigned long long x = v[k];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
         if ((threadIdx.x & 31) == 0 && x) atomicAdd(out + k, x);

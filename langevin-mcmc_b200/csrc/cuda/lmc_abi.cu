@@ -18,6 +18,8 @@
 #include "chain_kernels.cuh"
 #include "../host/host_scene.h"
 #include "../host/mlt_init.h"
+#include "../host/image_io.h"
+#include "film_comm.h"
 
 using namespace lmc;
 using namespace lmc_cuda;
@@ -28,6 +30,18 @@ namespace {
 thread_local std::string g_err;
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(LMC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+// temporary device buffer released on every exit path (the CK macro returns early on a CUDA error)
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { return cudaMalloc((void **)&p, sizeof(T) * (count ? count : 1)); }
+    operator T *() const { return p; }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
 
 __global__ void k_bvh_probe(const __grid_constant__ Scene sc, int n, const float *rays, float tmin, float tmax, int anyHit,
                             int *triId, int *geomPrim, float *tuv) {
@@ -110,6 +124,7 @@ struct lmc_ctx {
     uint64_t launches = 0;
     double lastMs = 0.0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ncclComm_t comm = nullptr;      // film all-reduce (lmc_create_multi / lmc_comm_init_rank); NULL for a lone ctx
 };
 
 namespace {
@@ -216,7 +231,7 @@ int chain_stats(lmc_ctx *c) {
     const int n = c->desc.num_chains;
     const int d = c->maxdTemplate;
     const void *st = c->states;
-    CK(cudaMemsetAsync(c->statsDev, 0, 10 * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->statsDev, 0, 11 * sizeof(unsigned long long), c->stream));
     c->launches++;
     CK(d == 4 ? launch_chain_stats_4(c->stream, st, n, c->statsDev)
               : (d == 8 ? launch_chain_stats_8(c->stream, st, n, c->statsDev) : launch_chain_stats_12(c->stream, st, n, c->statsDev)));
@@ -252,6 +267,7 @@ int lmc_scene_get_info(const lmc_scene *scene, lmc_scene_info *out) {
     out->width = s.head.cam.width; out->height = s.head.cam.height; out->num_triangles = s.head.numTris;
     out->num_bvh_nodes = s.head.numNodes; out->num_lights = s.head.numLights; out->num_shapes = s.head.numGeoms;
     out->num_textures = s.head.numTextures; out->spp = s.spp; out->direct_spp = s.directSpp; out->num_init_samples = s.numInitSamples;
+    out->report_interval_spp = s.reportIntervalSpp;
     return LMC_OK;
 }
 int lmc_scene_set_option(lmc_scene *scene, const char *name, double value) {
@@ -293,9 +309,9 @@ int lmc_mlt_init_device(lmc_ctx *c, int64_t num_init_samples, int32_t num_chains
     CK(cudaSetDevice(c->device));
     const int d = c->maxdTemplate;
     const int T = logical_threads;
-    int *dCounts = nullptr; long long *dOffsets = nullptr; float *dScores = nullptr;
-    CK(cudaMalloc((void **)&dCounts, sizeof(int) * (size_t)T));
-    CK(cudaMalloc((void **)&dOffsets, sizeof(long long) * (size_t)T));
+    DevBuf<int> dCounts; DevBuf<long long> dOffsets; DevBuf<float> dScores;
+    CK(dCounts.alloc((size_t)T));
+    CK(dOffsets.alloc((size_t)T));
     auto launch = [&](int emit) {
         return d == 4 ? launch_mlt_init_paths_4(c->stream, c->sc, num_init_samples, T, emit, dCounts, dOffsets, dScores)
                       : (d == 8 ? launch_mlt_init_paths_8(c->stream, c->sc, num_init_samples, T, emit, dCounts, dOffsets, dScores)
@@ -313,14 +329,13 @@ int lmc_mlt_init_device(lmc_ctx *c, int64_t num_init_samples, int32_t num_chains
     if (e == cudaSuccess) {
         for (int t = 0; t < T; t++) { offsets[t] = total; total += counts[t]; }
         scores.resize((size_t)total);
-        e = cudaMalloc((void **)&dScores, sizeof(float) * (size_t)std::max<long long>(total, 1));
+        e = dScores.alloc((size_t)total);
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(dOffsets, offsets.data(), sizeof(long long) * (size_t)T, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) { e = launch(1); c->launches++; }
     if (e == cudaSuccess && total > 0) e = cudaMemcpyAsync(scores.data(), dScores, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) rc = fail(LMC_ERR_CUDA, std::string("lmc_mlt_init_device: ") + cudaGetErrorString(e));
-    cudaFree(dCounts); cudaFree(dOffsets); if (dScores) cudaFree(dScores);
     if (rc) return rc;
     try {
         lmc_host::InitResult r;
@@ -337,8 +352,8 @@ int lmc_direct_lighting(lmc_ctx *c, int32_t direct_spp, float *host_rgb) {
     const int W = c->sc.cam.width, H = c->sc.cam.height;
     const size_t bytes = (size_t)W * H * 3 * sizeof(float);
     if (direct_lighting_skipped(c->sc) || direct_spp == 0) { memset(host_rgb, 0, bytes); return LMC_OK; }
-    float *dBuf = nullptr;
-    CK(cudaMalloc((void **)&dBuf, bytes));
+    DevBuf<float> dBuf;
+    CK(dBuf.alloc(bytes / sizeof(float)));
     cudaError_t e = cudaMemsetAsync(dBuf, 0, bytes, c->stream);
     const int nX = (W + LMC_DIRECT_TILE - 1) / LMC_DIRECT_TILE, nY = (H + LMC_DIRECT_TILE - 1) / LMC_DIRECT_TILE;
     if (e == cudaSuccess) {
@@ -348,7 +363,6 @@ int lmc_direct_lighting(lmc_ctx *c, int32_t direct_spp, float *host_rgb) {
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_rgb, dBuf, bytes, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(dBuf);
     if (e != cudaSuccess) return fail(LMC_ERR_CUDA, std::string("lmc_direct_lighting: ") + cudaGetErrorString(e));
     return LMC_OK;
 }
@@ -365,6 +379,8 @@ int lmc_create(const lmc_scene *scene, int32_t device, lmc_ctx **out) {
     if (s.head.opt.h2mc && s.head.opt.maxDepth > 8) return fail(LMC_ERR_UNSUPPORTED, "h2mc needs maxdepth <= 8 (dense Gaussians are stored for dim <= 16)");
     if (s.head.opt.maxDervDepth > 8) return fail(LMC_ERR_UNSUPPORTED, "maxdervdepth must be <= 8 (derivative functions exist for camDepth + lightDepth - 1 <= 8)");
     if (s.head.opt.largeStepMultiplexed) return fail(LMC_ERR_UNSUPPORTED, "largestepmultiplexed is not supported");
+    if (s.head.opt.useLightCoordinateSampling) return fail(LMC_ERR_UNSUPPORTED, "uselightcoordinatesampling is not supported (the sampler has no light-coordinate branch)");
+    if (s.head.opt.adjointCompat < 0 || s.head.opt.adjointCompat > 2) return fail(LMC_ERR_ARG, "adjointcompat must be 0, 1 or 2");
     lmc_ctx *c = new lmc_ctx();
     c->device = device;
     c->sc = s.head;
@@ -380,7 +396,7 @@ int lmc_create(const lmc_scene *scene, int32_t device, lmc_ctx **out) {
 #undef UP
     const size_t filmBytes = (size_t)d.cam.width * d.cam.height * 3 * sizeof(float);
     if (cudaMalloc((void **)&c->film, filmBytes) != cudaSuccess || cudaMemset(c->film, 0, filmBytes) != cudaSuccess ||
-        cudaMalloc((void **)&c->statsDev, 10 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc((void **)&c->statsDev, 11 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
         lmc_destroy(c);
         return fail(LMC_ERR_CUDA, "device allocation failed");
@@ -424,6 +440,7 @@ void lmc_destroy(lmc_ctx *c) {
     if (c->wc.evJoin) cudaEventDestroy(c->wc.evJoin);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->comm && nccl_api().lib) nccl_api().CommDestroy(c->comm);
     delete c;
 }
 
@@ -454,10 +471,10 @@ int lmc_run_chains(lmc_ctx *c, int64_t num_mutations, uint8_t *trace, float *a_t
     if (!c->begun) return fail(LMC_ERR_STATE, "lmc_chains_begin has not been called");
     if (num_mutations <= 0) return fail(LMC_ERR_ARG, "num_mutations must be positive");
     CK(cudaSetDevice(c->device));
-    unsigned char *dTrace = nullptr; float *dA = nullptr;
+    DevBuf<unsigned char> dTrace; DevBuf<float> dA;
     const size_t cnt = (size_t)c->desc.num_chains * (size_t)num_mutations;
-    if (trace) CK(cudaMalloc((void **)&dTrace, cnt));
-    if (a_trace) CK(cudaMalloc((void **)&dA, cnt * sizeof(float)));
+    if (trace) CK(dTrace.alloc(cnt));
+    if (a_trace) CK(dA.alloc(cnt));
     int rc = run_chains(c, num_mutations, dTrace, dA);
     if (rc == LMC_OK && (trace || a_trace)) {
         cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -465,8 +482,6 @@ int lmc_run_chains(lmc_ctx *c, int64_t num_mutations, uint8_t *trace, float *a_t
         if (e == cudaSuccess && a_trace) e = cudaMemcpy(a_trace, dA, cnt * sizeof(float), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = fail(LMC_ERR_CUDA, cudaGetErrorString(e));
     }
-    if (dTrace) cudaFree(dTrace);
-    if (dA) cudaFree(dA);
     return rc;
 }
 
@@ -484,11 +499,11 @@ int lmc_get_stats(lmc_ctx *c, lmc_stats *out) {
     if (c->begun) {
         const int rc = chain_stats(c);
         if (rc) return rc;
-        unsigned long long h[10];
+        unsigned long long h[11];
         CK(cudaMemcpyAsync(h, c->statsDev, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         for (int k = 0; k < 4; k++) { out->proposed[k] = h[k]; out->accepted[k] = h[4 + k]; }
-        out->gradient_evals = h[8]; out->gradient_nonfinite = h[9];
+        out->gradient_evals = h[8]; out->gradient_nonfinite = h[9]; out->outlier_resets = h[10];
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->lastMs = ms;
         else cudaGetLastError();
@@ -524,6 +539,83 @@ int lmc_film_bind(lmc_ctx *c, void *device_ptr) {
     return LMC_OK;
 }
 
+// ---- multi-GPU -----------------------------------------------------------------------------------------------
+#define NCK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(LMC_ERR_CUDA, std::string(#call) + ": " + nccl_api().GetErrorString(r_)); } while (0)
+
+int lmc_create_multi(const lmc_scene *scene, const int32_t *devices, int32_t n, lmc_ctx **out) {
+    if (!scene || !devices || !out || n < 1) return fail(LMC_ERR_ARG, "bad argument");
+    for (int i = 0; i < n; i++) out[i] = nullptr;
+    for (int i = 0; i < n; i++) {
+        const int rc = lmc_create(scene, devices[i], &out[i]);
+        if (rc) { for (int k = 0; k < i; k++) { lmc_destroy(out[k]); out[k] = nullptr; } return rc; }
+    }
+    if (n == 1) return LMC_OK;
+    NcclApi &api = nccl_api();
+    if (!api.load()) { for (int i = 0; i < n; i++) { lmc_destroy(out[i]); out[i] = nullptr; } return fail(LMC_ERR_UNSUPPORTED, api.error); }
+    std::vector<ncclComm_t> comms(n);
+    std::vector<int> devs(devices, devices + n);
+    const ncclResult_t r = api.CommInitAll(comms.data(), n, devs.data());
+    if (r != ncclSuccess) {
+        for (int i = 0; i < n; i++) { lmc_destroy(out[i]); out[i] = nullptr; }
+        return fail(LMC_ERR_CUDA, std::string("ncclCommInitAll: ") + api.GetErrorString(r));
+    }
+    for (int i = 0; i < n; i++) out[i]->comm = comms[i];
+    return LMC_OK;
+}
+
+int lmc_comm_unique_id(void *id128) {
+    if (!id128) return fail(LMC_ERR_ARG, "null argument");
+    NcclApi &api = nccl_api();
+    if (!api.load()) return fail(LMC_ERR_UNSUPPORTED, api.error);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCK(api.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return LMC_OK;
+}
+
+int lmc_comm_init_rank(lmc_ctx *c, int32_t nranks, int32_t rank, const void *id128) {
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(LMC_ERR_ARG, "bad argument");
+    if (c->comm) return fail(LMC_ERR_STATE, "this ctx already belongs to a communicator");
+    NcclApi &api = nccl_api();
+    if (!api.load()) return fail(LMC_ERR_UNSUPPORTED, api.error);
+    CK(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NCK(api.CommInitRank(&c->comm, nranks, id, rank));
+    return LMC_OK;
+}
+
+int lmc_allreduce_film(lmc_ctx **ctxs, int32_t n) {
+    if (!ctxs || n < 1) return fail(LMC_ERR_ARG, "bad argument");
+    for (int i = 0; i < n; i++) if (!ctxs[i]) return fail(LMC_ERR_ARG, "null ctx");
+    if (n == 1 && !ctxs[0]->comm) return LMC_OK;                      // a lone GPU: the film is already the sum
+    for (int i = 0; i < n; i++) if (!ctxs[i]->comm) return fail(LMC_ERR_STATE, "ctx without a communicator (lmc_create_multi / lmc_comm_init_rank)");
+    NcclApi &api = nccl_api();
+    const size_t count = (size_t)ctxs[0]->sc.cam.width * ctxs[0]->sc.cam.height * 3;
+    NCK(api.GroupStart());
+    for (int i = 0; i < n; i++) {
+        lmc_ctx *c = ctxs[i];
+        const ncclResult_t r = api.AllReduce(c->film, c->film, count, ncclFloat32, ncclSum, c->comm, c->stream);
+        if (r != ncclSuccess) { api.GroupEnd(); return fail(LMC_ERR_CUDA, std::string("ncclAllReduce: ") + api.GetErrorString(r)); }
+    }
+    NCK(api.GroupEnd());
+    return LMC_OK;
+}
+
+// ---- film output (host) ----------------------------------------------------------------------------------------
+int lmc_merge_buffer(const float *buffer1, float w1, const float *buffer2, float w2, int64_t n, float *film) {
+    if (!film || n < 0) return fail(LMC_ERR_ARG, "bad argument");
+    lmc_host::merge_buffer(buffer1, w1, buffer2, w2, (long long)n, film);
+    return LMC_OK;
+}
+
+int lmc_write_image(const char *path, int32_t width, int32_t height, const float *rgb) {
+    if (!path || !rgb || width < 1 || height < 1) return fail(LMC_ERR_ARG, "bad argument");
+    if (!lmc_host::write_image(path, width, height, rgb)) return fail(LMC_ERR_IO, std::string("cannot write ") + path);
+    return LMC_OK;
+}
+
 int32_t lmc_vert_param_size(int32_t cam_depth, int32_t light_depth) {
     const int maxDepth = cam_depth + light_depth;
     return maxDepth * 46 + maxDepth * 10 + 56 + maxDepth * 2 + maxDepth * 1 + 3 + 1 + 1;
@@ -541,13 +633,13 @@ int lmc_eval_batch(lmc_ctx *c, int32_t cam_depth, int32_t light_depth, int32_t n
     CK(cudaSetDevice(c->device));
     const int dim = 2 * (len > 2 ? len : 2);
     if (hess && !grad) return fail(LMC_ERR_ARG, "hess requires grad");
-    float *dS = nullptr, *dP = nullptr, *dV = nullptr, *dL = nullptr, *dG = nullptr, *dH = nullptr;
-    if (hess) CK(cudaMalloc((void **)&dH, sizeof(float) * (size_t)n * dim * dim));
-    CK(cudaMalloc((void **)&dS, 38 * sizeof(float)));
-    CK(cudaMalloc((void **)&dP, sizeof(float) * (size_t)n * (dim + 1)));
-    CK(cudaMalloc((void **)&dV, sizeof(float) * (size_t)n * vert_stride));
-    CK(cudaMalloc((void **)&dL, sizeof(float) * (size_t)n));
-    if (grad) CK(cudaMalloc((void **)&dG, sizeof(float) * (size_t)n * dim));
+    DevBuf<float> dS, dP, dV, dL, dG, dH;
+    if (hess) CK(dH.alloc((size_t)n * dim * dim));
+    CK(dS.alloc(38));
+    CK(dP.alloc((size_t)n * (dim + 1)));
+    CK(dV.alloc((size_t)n * vert_stride));
+    CK(dL.alloc((size_t)n));
+    if (grad) CK(dG.alloc((size_t)n * dim));
     CK(cudaMemcpyAsync(dS, c->sc.sceneSer, 38 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(dP, primary, sizeof(float) * (size_t)n * (dim + 1), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(dV, vert_params, sizeof(float) * (size_t)n * vert_stride, cudaMemcpyHostToDevice, c->stream));
@@ -559,7 +651,6 @@ int lmc_eval_batch(lmc_ctx *c, int32_t cam_depth, int32_t light_depth, int32_t n
     if (grad) CK(cudaMemcpyAsync(grad, dG, sizeof(float) * (size_t)n * dim, cudaMemcpyDeviceToHost, c->stream));
     if (hess) CK(cudaMemcpyAsync(hess, dH, sizeof(float) * (size_t)n * dim * dim, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(dS); cudaFree(dP); cudaFree(dV); cudaFree(dL); if (dG) cudaFree(dG); if (dH) cudaFree(dH);
     return LMC_OK;
 }
 
@@ -568,11 +659,11 @@ int lmc_bvh_probe(lmc_ctx *c, int32_t n, const float *rays, float tmin, float tm
     if (!c || !rays || !tri_id || n < 0) return fail(LMC_ERR_ARG, "bad argument");
     if (n == 0) return LMC_OK;
     CK(cudaSetDevice(c->device));
-    float *dR = nullptr, *dT = nullptr; int *dI = nullptr, *dG = nullptr;
-    CK(cudaMalloc((void **)&dR, sizeof(float) * 6 * (size_t)n));
-    CK(cudaMalloc((void **)&dI, sizeof(int) * (size_t)n));
-    CK(cudaMalloc((void **)&dG, sizeof(int) * 2 * (size_t)n));
-    CK(cudaMalloc((void **)&dT, sizeof(float) * 3 * (size_t)n));
+    DevBuf<float> dR, dT; DevBuf<int> dI, dG;
+    CK(dR.alloc(6 * (size_t)n));
+    CK(dI.alloc((size_t)n));
+    CK(dG.alloc(2 * (size_t)n));
+    CK(dT.alloc(3 * (size_t)n));
     CK(cudaMemcpyAsync(dR, rays, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     k_bvh_probe<<<(n + 127) / 128, 128, 0, c->stream>>>(c->sc, n, dR, tmin, tmax, any_hit, dI, dG, dT);
     c->launches++;
@@ -581,7 +672,6 @@ int lmc_bvh_probe(lmc_ctx *c, int32_t n, const float *rays, float tmin, float tm
     if (geom_prim && !any_hit) CK(cudaMemcpyAsync(geom_prim, dG, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     if (tuv && !any_hit) CK(cudaMemcpyAsync(tuv, dT, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(dR); cudaFree(dI); cudaFree(dG); cudaFree(dT);
     return LMC_OK;
 }
 

@@ -16,6 +16,7 @@
 #include "host_scene.h"
 #include "mini_xml.h"
 #include "../core/bsdf.h"
+#include "../core/bvh.h"
 
 #include <zlib.h>
 #include <algorithm>
@@ -459,14 +460,24 @@ struct Builder {
         return ~((first << 3) | (hi - lo - 1));
     }
     // returns child reference; bounds written to `box`
+    // Depth budget.  The traversal keeps at most one deferred child per inner node on the way down, in a fixed
+    // stack of LMC_BVH_STACK entries (core/bvh.h, cuda/trace_kernels.cuh), so no leaf may sit below LMC_BVH_STACK - 1
+    // inner nodes.  A median split halves the primitive count, i.e. a subtree of n primitives built from median
+    // splits alone is at most ceil(log2 n) deep; SAH splits (which may be arbitrarily unbalanced on skewed
+    // geometry) are therefore only taken while depth + ceil(log2 n) leaves one level of slack.  maxDepth records
+    // what was built and is checked again after the build and when a .pack is loaded (bvh_depth()).
+    int maxDepth = 0;
+    static int ceil_log2(int n) { int b = 0; while ((1 << b) < n) b++; return b; }
     int build(int lo, int hi, BBoxF &box, int depth) {
         box = BBoxF();
         BBoxF cb;
         for (int i = lo; i < hi; i++) { box.merge(prims[i].box); cb.grow(prims[i].c); }
         const int n = hi - lo;
-        if (n == 1 || (depth >= 40 && n <= 8)) return make_leaf(lo, hi);
+        if (depth > maxDepth) maxDepth = depth;
+        const bool sahAllowed = depth + ceil_log2(n) <= LMC_BVH_STACK - 2;
+        if (n == 1 || (!sahAllowed && n <= 8 && depth + 1 <= LMC_BVH_STACK - 1)) return make_leaf(lo, hi);
         int mid = -1;
-        if (depth < 40) {
+        if (sahAllowed) {
             // binned SAH on the widest centroid axis, falling back over all axes
             float bestCost = INFINITY; int bestAxis = -1, bestSplit = -1;
             const int NB = 16;
@@ -534,6 +545,7 @@ Options default_options() {
     o.minDepth = -1; o.maxDepth = 8; o.bidirectional = 1; o.h2mc = 0; o.mala = 0;
     o.numChains = 128; o.seedOffset = 0; o.useLightCoordinateSampling = 0; o.largeStepMultiplexed = 0;
     o.cacheEnabled = 0; o.maxDervDepth = 8; o.pssMinLength = 2; o.pssMaxLength = 12; o.adjointCompat = 1;
+    o.outlierWeakRejectCnt = 10000; o.outlierStrongRejectCnt = 1000; o.outlierRatioThreshold = 30.0f;
     o.perturbStdDev = 0.01f; o.roughnessThreshold = 0.05f; o.largeStepProbability = 0.05f;
     o.largeStepProbScale = 1.0f; o.malaGN = 100.0f; o.malaStepsize = 0.005f; o.malaStdDev = 0.005f;
     o.discreteStdDev = 0.01f; o.uniformMixingProbability = 0.1f; o.lsRatio = 0.1f;
@@ -556,7 +568,8 @@ const OptField kOptFields[] = {
     LMC_OI("h2mc", h2mc), LMC_OI("mala", mala), LMC_OI("numchains", numChains), LMC_OI("seedoffset", seedOffset),
     LMC_OI("uselightcoordinatesampling", useLightCoordinateSampling), LMC_OI("largestepmultiplexed", largeStepMultiplexed),
     LMC_OI("maxdervdepth", maxDervDepth), LMC_OI("pssminlength", pssMinLength), LMC_OI("pssmaxlength", pssMaxLength),
-    LMC_OI("adjointcompat", adjointCompat),
+    LMC_OI("adjointcompat", adjointCompat), LMC_OI("outlierweakrejectcnt", outlierWeakRejectCnt),
+    LMC_OI("outlierstrongrejectcnt", outlierStrongRejectCnt), LMC_OF("outlierratiothreshold", outlierRatioThreshold),
     LMC_OF("perturbstddev", perturbStdDev), LMC_OF("roughnessthreshold", roughnessThreshold),
     LMC_OF("largestepprob", largeStepProbability), LMC_OF("largestepscale", largeStepProbScale),
     LMC_OF("mala-gn", malaGN), LMC_OF("mala-stepsize", malaStepsize), LMC_OF("malastddev", malaStdDev),
@@ -845,8 +858,12 @@ void load_scene_xml(const std::string &xmlPath, SceneStore &out) {
                 else if (name == "uniformmixprob") opt.uniformMixingProbability = std::stof(v);
                 else if (name == "numchains") opt.numChains = std::stoi(v);
                 else if (name == "seedoffset") opt.seedOffset = std::stoi(v);
-                else if (name == "reportintervalspp") { /* progressive dumps: out of scope */ }
-                else if (name == "uselightcoordinatesampling") opt.useLightCoordinateSampling = (v == "true");
+                else if (name == "reportintervalspp") out.reportIntervalSpp = std::stoi(v);
+                else if (name == "uselightcoordinatesampling") {
+                    // the path sampler here has no light-coordinate branch (src/path.cpp:762-798 / 2974-3013): accepting
+                    // the flag would differentiate a different function than the one sampled
+                    if (v == "true") throw std::runtime_error("uselightcoordinatesampling is not supported");
+                }
                 else if (name == "largestepmultiplexed") opt.largeStepMultiplexed = (v == "true");
                 else if (name == "h2mc") opt.h2mc = (v == "true");
                 else if (name == "mala") opt.mala = (v == "true");
@@ -885,6 +902,8 @@ void load_scene_xml(const std::string &xmlPath, SceneStore &out) {
     if (src.empty()) throw std::runtime_error("scene has no triangles");
     BBoxF rootBox;
     const int root = B.build(0, (int)B.prims.size(), rootBox, 0);
+    if (B.maxDepth > LMC_BVH_STACK - 1)
+        throw std::runtime_error("BVH deeper than the traversal stack (" + std::to_string(B.maxDepth) + " levels)");
     if (root < 0) {
         // single leaf: wrap it in a node so traversal always starts at an inner node
         BvhNode nd; memset(&nd, 0, sizeof(nd));
@@ -1095,6 +1114,23 @@ void save_scene_pack(const std::string &path, const SceneStore &s) {
     const int meta[3] = {s.spp, s.directSpp, s.numInitSamples}; f.write((const char *)meta, 12);
 }
 
+// number of inner nodes on the longest root-to-leaf path (children < 0 are leaves); -1 for a malformed array
+int bvh_depth(const std::vector<BvhNode> &nodes) {
+    if (nodes.empty()) return 0;
+    std::vector<std::pair<int, int>> st;
+    st.push_back({0, 1});
+    int deepest = 0; size_t visited = 0;
+    while (!st.empty()) {
+        const std::pair<int, int> t = st.back(); st.pop_back();
+        if (t.first < 0 || t.first >= (int)nodes.size() || ++visited > 2 * nodes.size()) return -1;
+        if (t.second > deepest) deepest = t.second;
+        const BvhNode &nd = nodes[t.first];
+        if (nd.left >= 0) st.push_back({nd.left, t.second + 1});
+        if (nd.right >= 0 && nd.right != nd.left) st.push_back({nd.right, t.second + 1});
+    }
+    return deepest;
+}
+
 void load_scene_pack(const std::string &path, SceneStore &out) {
     std::ifstream f(path, std::ios::binary);
     if (!f) throw std::runtime_error("cannot open scene pack " + path);
@@ -1110,6 +1146,9 @@ void load_scene_pack(const std::string &path, SceneStore &out) {
     rd_vec(f, out.envRowWeights);
     int meta[3]; f.read((char *)meta, 12);
     if (!f) throw std::runtime_error("truncated scene pack " + path);
+    const int depth = bvh_depth(out.nodes);
+    if (depth < 0 || depth > LMC_BVH_STACK)
+        throw std::runtime_error("scene pack: BVH malformed or deeper than the traversal stack: " + path);
     out.spp = meta[0]; out.directSpp = meta[1]; out.numInitSamples = meta[2];
     out.integrator = "mcmc";
 }

@@ -29,6 +29,7 @@ struct SceneStore {
     lmc::Scene head;          // scalar members valid; pointer members filled by view()
     std::string outputName;
     int spp, directSpp, numInitSamples;
+    int reportIntervalSpp = 0;   // <dpt> reportintervalspp: progressive image dump every so many spp (src/mlt.cpp:171-193)
     std::string integrator;
 
     // Returns a Scene whose pointers reference this store's host arrays.

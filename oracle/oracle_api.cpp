@@ -70,7 +70,7 @@ void run_chains_t(const Scene &sc, int numChains, int chainBase, int totalChains
     const int W = sc.cam.width, H = sc.cam.height;
     if (threads < 1) threads = 1;
     std::vector<std::vector<float>> films(threads);
-    std::vector<std::vector<unsigned long long>> tstats(threads, std::vector<unsigned long long>(10, 0ULL));
+    std::vector<std::vector<unsigned long long>> tstats(threads, std::vector<unsigned long long>(11, 0ULL));
     std::atomic<int> next(0);
     auto work = [&](int w) {
         ref_grad_hook() = (g_useRef && g_refLoaded) ? ref_gradient : nullptr;
@@ -90,7 +90,7 @@ void run_chains_t(const Scene &sc, int numChains, int chainBase, int totalChains
             chain_run(sc, rp, gid, *cs, numSteps, tab, 1, hf, trace ? trace + (size_t)i * numSteps : nullptr,
                       aTrace ? aTrace + (size_t)i * numSteps : nullptr, 1, side, staged);
             for (int k = 0; k < 4; k++) { tstats[w][k] += cs->nPropose[k]; tstats[w][4 + k] += cs->nAccept[k]; }
-            tstats[w][8] += cs->gradStats[0]; tstats[w][9] += cs->gradStats[1];
+            tstats[w][8] += cs->gradStats[0]; tstats[w][9] += cs->gradStats[1]; tstats[w][10] += (unsigned long long)cs->ch.outlierResets;
         }
         delete cs;
         delete side;
@@ -100,7 +100,7 @@ void run_chains_t(const Scene &sc, int numChains, int chainBase, int totalChains
     for (int w = 0; w < threads; w++) pool.emplace_back(work, w);
     for (auto &t : pool) t.join();
     if (film) for (int w = 0; w < threads; w++) for (size_t k = 0; k < (size_t)W * H * 3; k++) film[k] += films[w][k];
-    if (stats) for (int k = 0; k < 10; k++) { stats[k] = 0; for (int w = 0; w < threads; w++) stats[k] += tstats[w][k]; }
+    if (stats) for (int k = 0; k < 11; k++) { stats[k] = 0; for (int w = 0; w < threads; w++) stats[k] += tstats[w][k]; }
 }
 
 template <int MAXD>
@@ -182,7 +182,7 @@ int lmco_mlt_init(void *h, long long numInitSamples, int numChains, int logicalT
     LMCO_CATCH
 }
 
-// stats[10]: nPropose[4], nAccept[4], gradEvals, gradNonFinite
+// stats[11]: nPropose[4], nAccept[4], gradEvals, gradNonFinite, outlierResets
 int lmco_run_chains(void *h, int numChains, int chainBase, int totalChains, long long numSteps,
                     long long numSamplesThisChain, float normalization, const float *initLs, float *film,
                     unsigned char *trace, float *aTrace, int threads, unsigned long long *stats) {
@@ -365,7 +365,7 @@ int lmco_eval_batch_hess(void *h, int camDepth, int lightDepth, int n, const flo
     const int dim = primary_param_size(camDepth, lightDepth) - 1;
     if (dim > LMC_HESS_MAXDIM) return -1;
     for (int i = 0; i < n; i++)
-        logLum[i] = path_loglum_hess(camDepth, lightDepth, sceneSer, primary + (size_t)i * primaryStride,
+        logLum[i] = (st.head.opt.adjointCompat == 3 ? path_loglum_hess_rev : path_loglum_hess)(camDepth, lightDepth, sceneSer, primary + (size_t)i * primaryStride,
                                      vertParams + (size_t)i * vertStride, grad + (size_t)i * dim, hess + (size_t)i * dim * dim);
     return 0;
 }

@@ -6,7 +6,10 @@ REFERENCE's OWN generated code compiled into oracle/_ref/ (oracle/build_ref.sh):
   ref_fwd   evaluate_path_bidir_mala_<c>_<l>_static        log Luminance(contrib)
   ref_rev   evaluate_path_bidir_mala_<c>_<l>_static_derv   reverse-mode gradient (what LMC uses)
   ref_fwdm  evaluate_path_bidir_<c>_<l>_static_derv        forward-mode gradient (H2MC library)
-  ref_hess  the same call's Hessian, hess[i * D + j] = d(grad_j)/dx_i, classes with c + l - 1 <= 5
+  ref_hess  the same call's Hessian, hess[i * D + j] = d(grad_j)/dx_i, every class (c + l - 1 <= 8, D <= 16)
+
+Scenes: 0 = torus (environment light), 1 = veach-door (area light), 2 = torus with the point emitter the reference
+keeps commented out in its scene file (scenes/torus/point.xml; the only PointLight configuration).
 
 The inputs are produced by the oracle's path recorder (lmco_sample_paths: GeneratePathBidir ->
 ToSubpath -> optional PerturbPathBidir -> Serialize).  For (c, 0) paths that end on the
@@ -35,8 +38,8 @@ def main():
     mala, hess = ref_lib("libpathref_mala.so"), ref_lib("libpathref_hess.so")
     assert mala is not None and hess is not None, "run `make ref` first"
     recs = []
-    for scene in ("torus", "veachdoor"):
-        h = o.load(os.path.join(ROOT, "scenes", scene, "lmc.xml"))
+    for sid, (scene, xml) in enumerate((("torus", "lmc.xml"), ("veachdoor", "lmc.xml"), ("torus", "point.xml"))):
+        h = o.load(os.path.join(ROOT, "scenes", scene, xml))
         ser = o.scene_serialized(h)
         out = o.sample_paths(h, seed=2024, num_large_steps=3000, perturb=True, max_len=8, max_records=40000)
         cl = out[:, :2].astype(int)
@@ -59,8 +62,8 @@ def main():
             getattr(mala, "evaluate_path_bidir_mala_%d_%d_static" % (c, l))(o.p(lens), o.p(prim), o.p(ser), o.p(vert), o.p(fwd))
             getattr(mala, "evaluate_path_bidir_mala_%d_%d_static_derv" % (c, l))(o.p(lens), o.p(prim), o.p(ser), o.p(vert), o.p(rev), None)
             fwdm = np.full(16, np.nan, np.float32)
-            rhess = np.full(100, np.nan, np.float32)     # reference Hessian (row = direction), dim <= 10
-            fh = getattr(hess, "evaluate_path_bidir_%d_%d_static_derv" % (c, l), None) if c + l - 1 <= 5 else None
+            rhess = np.full(256, np.nan, np.float32)     # reference Hessian (row = direction), dim <= 16
+            fh = getattr(hess, "evaluate_path_bidir_%d_%d_static_derv" % (c, l), None) if c + l - 1 <= 8 else None
             if fh is not None:
                 g = np.zeros(dim, np.float32)
                 hh = np.zeros(dim * dim, np.float32)
@@ -69,9 +72,9 @@ def main():
                 rhess[:dim * dim] = hh
             rv = np.full(16, np.nan, np.float32)
             rv[:dim] = rev
-            recs.append(dict(scene=0 if scene == "torus" else 1, c=c, l=l, lens=lens, primary=prim[:17], vert=vert[:VS],
+            recs.append(dict(scene=sid, c=c, l=l, lens=lens, primary=prim[:17], vert=vert[:VS],
                              scene_ser=ser, ls=out[i, 4], ss=out[i, 5], ref_fwd=fwd[0], ref_rev=rv, ref_fwdm=fwdm, ref_hess=rhess))
-        print(scene, "classes", sorted(per.items()))
+        print(scene, xml, "classes", sorted(per.items()))
     keys = recs[0].keys()
     arrays = {k: np.stack([np.asarray(r[k]) for r in recs]) for k in keys}
     np.savez_compressed(os.path.join(HERE, "path_golden.npz"), **arrays)

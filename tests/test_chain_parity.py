@@ -102,6 +102,21 @@ def test_cuda_door_scene_and_isotropic_kernel(lmc, oracle, door_xml):
             assert ((trace & 3) != 3).all()
 
 
+def compare_slices_with_oracle(oracle, xml, opts, trace, a, norm, init_ls, steps, slices):
+    """trace / a: [chain][step] of the FULL job on the GPU; every (base, count) slice must equal the CPU oracle's run
+    of exactly those global chain ids (seed = chain id, same init scores, same total chain count)."""
+    h = oracle.load(xml)
+    for k, v in opts.items():
+        oracle.set_option(h, k, v)
+    total = trace.shape[0]
+    for base, count in slices:
+        _, ot, oa, _ = oracle.run_chains(h, count, steps, norm, init_ls, chain_base=base, total_chains=total,
+                                         samples_per_chain=steps)
+        g, ga = trace[base:base + count], a[base:base + count]
+        assert np.array_equal(g, ot), "chains %d..%d: %d diverge" % (base, base + count, int((g != ot).any(axis=1).sum()))
+        assert np.array_equal(ga.view(np.uint32), oa.view(np.uint32))
+
+
 @pytest.mark.gpu
 def test_cuda_launch_split_and_sharding_invariance(lmc, torus_xml):
     """100 mutations in one launch == 4 launches of 25 (state round-trips through HBM bit-exactly),
@@ -125,7 +140,7 @@ def test_cuda_launch_split_and_sharding_invariance(lmc, torus_xml):
 
 
 @pytest.mark.gpu
-def test_cuda_full_size_properties(lmc, torus_xml):
+def test_cuda_full_size_properties(lmc, oracle, torus_xml):
     """BASELINE configs[1] size (2^20 chains, maxdepth 8): size-independent invariants."""
     sc = lmc.ParseScene(torus_xml)
     sc.options["maxdepth"] = 8
@@ -134,13 +149,16 @@ def test_cuda_full_size_properties(lmc, torus_xml):
     init_ls = np.resize(init_small, chains)
     ctx = lmc.ChainContext(sc, 0)
     ctx.begin(chains, norm, init_ls, samples_per_chain=steps)
-    ctx.run(steps)
+    trace, a = ctx.run(steps, trace=True, a_trace=True)
     st = ctx.stats()
     assert sum(st["proposed"]) == chains * steps
     assert st["proposed"][0] >= chains                 # every chain opens with a large step
     assert all(a <= p for a, p in zip(st["accepted"], st["proposed"]))
     film = ctx.film()
     assert np.isfinite(film).all() and film.min() >= 0.0
+    # slices of the 2^20-chain job against the CPU oracle, bit for bit (decisions and acceptance probabilities)
+    compare_slices_with_oracle(oracle, torus_xml, {"maxdepth": 8}, trace, a, norm, init_ls, steps,
+                               [(0, 512), (777777, 256), (chains - 256, 256)])
     # energy check: sum of splats / mutations estimates the image mean (normalization = b)
     mean = float(film.sum()) / (chains * steps) / 3.0
     assert 0.2 * norm < mean < 5.0 * norm
@@ -181,7 +199,7 @@ def test_cuda_per_vertex_wavefront_equals_monolithic_propose(lmc, torus_xml, doo
     ("door", {"maxdepth": 12}, 4),                          # BASELINE configs[2]: veach-door, LMC, path length 12, 2^20 chains
     ("torus_h2mc", {"maxdepth": 8}, 3),                     # BASELINE configs[3]: torus, H2MC mutation, path length 8, 2^20 chains
 ])
-def test_cuda_full_size_other_configs(lmc, torus_xml, door_xml, scene, opts, steps):
+def test_cuda_full_size_other_configs(lmc, oracle, torus_xml, door_xml, scene, opts, steps):
     """The other single-GPU BASELINE configurations at their full chain count: size-independent invariants
     (every mutation accounted for, first step large, finite non-negative film with the right energy) and the
     first 512 chains of the big job equal to the chains of a 512-chain job (seed = global chain id)."""
@@ -194,11 +212,14 @@ def test_cuda_full_size_other_configs(lmc, torus_xml, door_xml, scene, opts, ste
     norm, init_small = ctx.mlt_init(300000, 4096, 4096)
     init_ls = np.resize(init_small, chains)
     ctx.begin(chains, norm, init_ls, samples_per_chain=steps)
-    ctx.run(steps)
+    trace, a = ctx.run(steps, trace=True, a_trace=True)
     st = ctx.stats()
     assert sum(st["proposed"]) == chains * steps
     assert st["proposed"][0] >= chains
     assert all(a <= p for a, p in zip(st["accepted"], st["proposed"]))
+    # slices of the full-size job against the CPU oracle, bit for bit
+    compare_slices_with_oracle(oracle, xml, opts, trace, a, norm, init_ls, steps,
+                               [(0, 256), (500000, 128)] if scene == "door" else [(0, 96), (900001, 64)])
     if scene == "torus_h2mc":
         assert st["proposed"][2] > 0 and st["proposed"][3] == 0      # H2MC small steps, no MALA
     else:
@@ -243,3 +264,72 @@ def test_cuda_proposal_path_is_chosen_by_chain_count(lmc, torus_xml, monkeypatch
         ctx.close()
     assert np.array_equal(runs["auto"][0], runs["1"][0])
     assert runs["auto"][1] < 15 < runs["1"][1]
+
+
+def _outlier_opts():
+    # thresholds of src/mutation.h:5-8 lowered so that the reset of src/mlt.cpp:147-169 fires within a short run:
+    # any chain rejected 6 times in a row is reset (weak rule), a chain whose current lsScore exceeds 0.5 x
+    # normalization already after 2 (strong rule), and the walk over the init states skips those above 0.5 x too
+    return {"maxdepth": 6, "outlierweakrejectcnt": 6, "outlierstrongrejectcnt": 2, "outlierratiothreshold": 0.5}
+
+
+def test_oracle_outlier_reset_fires_and_follows_the_reference_rule(oracle, torus_xml):
+    """Outlier ("stuck chain") reset, src/mlt.cpp:147-169 with the constants of src/mutation.h:5-8 as options.
+    With the default thresholds (10000 / 1000 / 30) no 100-step test ever reaches the branch; lowered thresholds
+    make it fire.  Checked against the rule itself: after a reset the chain is invalid, so the next step is a large
+    step whatever the uniform draw says, and the reset count of the run is reproduced by a replay of the decision
+    strings."""
+    h = oracle.load(torus_xml)
+    opts = _outlier_opts()
+    for k, v in opts.items():
+        oracle.set_option(h, k, v)
+    chains, steps = 512, 160
+    norm, ls = oracle.mlt_init(h, 100000, chains, 32)
+    film, trace, a, stats = oracle.run_chains(h, chains, steps, norm, ls, samples_per_chain=steps)
+    resets = int(stats[10])
+    assert resets > 50, "the lowered thresholds must trigger resets (%d)" % resets
+    # replay: adjacentReject counts consecutive rejections (never cleared by a reset, as in the reference);
+    # the weak rule alone gives a lower bound on the resets, and every reset forces a large step next
+    acc = (trace >> 2) & 1
+    typ = trace & 3
+    lower = 0
+    for c in range(chains):
+        adj = 0
+        for s in range(steps):
+            if acc[c, s]:
+                adj = 0
+            else:
+                adj += 1
+                if adj > opts["outlierweakrejectcnt"]:
+                    lower += 1
+                    if s + 1 < steps:
+                        assert typ[c, s + 1] == 0, "chain %d step %d: a reset chain must restart with a large step" % (c, s + 1)
+    assert lower <= resets
+    assert np.isfinite(film).all()
+    # default thresholds: the same run never resets
+    h2 = oracle.load(torus_xml)
+    oracle.set_option(h2, "maxdepth", 6)
+    _, _, _, stats2 = oracle.run_chains(h2, chains, steps, norm, ls, samples_per_chain=steps)
+    assert int(stats2[10]) == 0
+
+
+@pytest.mark.gpu
+def test_cuda_outlier_reset_bit_identical_to_oracle(lmc, oracle, torus_xml):
+    """The reset branch on the device (k_wave_finish) against the CPU oracle: same decisions, same acceptance
+    probabilities, same number of resets, same film."""
+    opts = _outlier_opts()
+    sc = lmc.ParseScene(torus_xml)
+    sc.options.update(opts)
+    chains, steps = 512, 160
+    norm, init_ls = lmc.MLTInit(sc, 100000, chains, 32)
+    ctx = lmc.ChainContext(sc, 0)
+    ctx.begin(chains, norm, init_ls, samples_per_chain=steps)
+    trace, a = ctx.run(steps, trace=True, a_trace=True)
+    st = ctx.stats()
+    film = ctx.film()
+    ofilm, otrace, oa, ostats = oracle_run(oracle, torus_xml, opts, chains, steps, norm, init_ls, samples_per_chain=steps)
+    assert st["outlier_resets"] == int(ostats[10]) and st["outlier_resets"] > 50
+    assert np.array_equal(trace, otrace)
+    assert np.array_equal(a.view(np.uint32), oa.view(np.uint32))
+    assert np.allclose(film, ofilm, rtol=1e-4, atol=1e-5)
+    ctx.close()

@@ -26,16 +26,22 @@ def test_jacobi_eigensolver_matches_lapack(oracle):
             assert (lead > 0).all()                                          # sign convention
 
 
-def test_hessian_matches_reference_generated_code(oracle, torus_xml, door_xml):
-    """Second-order forward mode vs the reference's forward-over-reverse Hessian
-    (evaluate_path_bidir_<c>_<l>_static_derv, vectors in tests/golden/path_golden.npz)."""
+@pytest.mark.parametrize("mode", [1, 3])
+def test_hessian_matches_reference_generated_code(oracle, torus_xml, door_xml, mode):
+    """Our Hessians vs the reference's (evaluate_path_bidir_<c>_<l>_static_derv, vectors in
+    tests/golden/path_golden.npz, every path length up to 8):
+      mode 1  second-order forward mode (csrc/core/pathgrad.h path_loglum_hess) -- what the H2MC mutation runs
+      mode 3  forward-over-reverse: the generated reverse sweep on dual numbers (pathgrad_rev.h, host only) -- an
+              independent derivation used as a cross-check."""
     g = np.load(os.path.join(GOLDEN, "path_golden.npz"))
-    handles = {0: oracle.load(torus_xml), 1: oracle.load(door_xml)}
-    errs, errs_glass = [], []
+    handles = {0: oracle.load(torus_xml), 1: oracle.load(door_xml), 2: oracle.load(os.path.join(SCENES, "torus", "point.xml"))}
+    for h in handles.values():
+        oracle.set_option(h, "adjointcompat", mode)
+    errs, errs_glass, lens = [], [], []
     for i in range(len(g["c"])):
         c, l, s = int(g["c"][i]), int(g["l"][i]), int(g["scene"][i])
         dim = 2 * max(c + l - 1, 2)
-        if c + l - 1 > 5 or g["ss"][i] <= 1e-10 or not np.isfinite(g["ref_hess"][i, :dim * dim]).all():
+        if c + l - 1 > 8 or g["ss"][i] <= 1e-10 or not np.isfinite(g["ref_hess"][i, :dim * dim]).all():
             continue
         prim = np.ascontiguousarray(g["primary"][i:i + 1, :dim + 1])
         vert = np.ascontiguousarray(g["vert"][i:i + 1])
@@ -48,12 +54,13 @@ def test_hessian_matches_reference_generated_code(oracle, torus_xml, door_xml):
             continue
         H = g["ref_hess"][i, :dim * dim].reshape(dim, dim)
         O = oh.reshape(dim, dim)
-        assert np.array_equal(O, O.T)                  # ours is symmetric by construction
+        assert np.array_equal(O, O.T)                  # ours is symmetric by construction (mode 3: symmetrised)
         e = np.abs(O - H).max() / (np.abs(H).max() + 1e-3)
         (errs_glass if 2 in bsdf_types(c, l, g["vert"][i]) else errs).append(e)
-        assert np.abs(og - g["ref_fwdm"][i, :dim]).max() <= 1e-2 * (np.abs(og).max() + 1e-3)   # sanity only; bounds in test_ref_parity
+        lens.append(c + l - 1)
+        assert np.abs(og - g["ref_fwdm"][i, :dim]).max() <= 5e-2 * (np.abs(og).max() + 1e-3)   # sanity only; bounds in test_ref_parity
     errs, errs_glass = np.array(errs), np.array(errs_glass)
-    assert len(errs) > 60
+    assert len(errs) > 150 and max(lens) == 8 and sum(1 for x in lens if x >= 6) > 60   # path lengths 6-8 are pinned too (H2MC at maxdepth 8)
     assert np.median(errs) <= 1e-4 and np.percentile(errs, 90) <= 2e-3, (np.median(errs), np.percentile(errs, 90))
     # glass: the reference's reverse half carries its merge bug; report, bound loosely
     print("hessian rel err: no glass med %.2e p90 %.2e | glass med %.2e p90 %.2e" %

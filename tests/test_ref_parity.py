@@ -18,8 +18,8 @@ Tolerances (north star: contribution / gradient within 1e-4 relative):
     ispc fast-math and prints its constants with 6 decimals: the float64 interpretation of the same
     program, tools/adgen/check_whole.py, sits at median 2e-6 / p99 1.3e-3 against it.)
   * gradient, adjointcompat = 0 (reverse sweep, true adjoint) and = 2 (forward-mode duals,
-    csrc/core/pathgrad.h) vs the reference's forward-mode code (H2MC library): <= 1e-4 median,
-    <= 2e-3 p99; and against each other <= 1e-5 median (two independent derivations of the same
+    csrc/core/pathgrad.h) vs the reference's forward-mode code (H2MC library, every path length up to 8):
+    <= 1e-4 median, <= 5e-3 p99; and against each other <= 1e-5 median (two independent derivations of the same
     gradient).
 """
 import os
@@ -28,6 +28,11 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, ROOT, bsdf_types
+
+
+def point_xml():
+    """torus with the point emitter the reference keeps commented out in its scene file (scene id 2 of the fixture)."""
+    return os.path.join(ROOT, "scenes", "torus", "point.xml")
 
 
 def load_golden():
@@ -91,14 +96,14 @@ def check_against_golden(ll, grads, g, mode=1):
         assert rep["rev_noglass_med"] <= 1e-4 and rep["rev_noglass_p99"] <= 5e-3, rep
         assert rep["rev_glass_med"] <= 1e-4 and rep["rev_glass_p99"] <= 5e-3, rep
     else:             # the true gradient
-        assert rep["fm_med"] <= 1e-4 and rep["fm_p99"] <= 2e-3, rep
-        assert rep["rev_noglass_med"] <= 1e-4 and rep["rev_noglass_p99"] <= 2e-3, rep
+        assert rep["fm_med"] <= 1e-4 and rep["fm_p99"] <= 5e-3, rep
+        assert rep["rev_noglass_med"] <= 1e-4 and rep["rev_noglass_p99"] <= 5e-3, rep
     return rep
 
 
 def test_oracle_evaluator_matches_reference_golden(oracle, torus_xml, door_xml):
     g = load_golden()
-    handles = {0: oracle.load(torus_xml), 1: oracle.load(door_xml)}
+    handles = {0: oracle.load(torus_xml), 1: oracle.load(door_xml), 2: oracle.load(point_xml())}
     # the scene block the golden inputs were evaluated with must be what the loader produces
     for s, h in handles.items():
         idx = np.where(g["scene"] == s)[0][0]
@@ -139,9 +144,9 @@ def test_live_reference_library_agrees_with_golden(oracle, ref_mala):
 @pytest.mark.gpu
 def test_cuda_eval_batch_matches_reference_golden_and_oracle(lmc, oracle, torus_xml, door_xml):
     g = load_golden()
-    scenes = {0: lmc.ParseScene(torus_xml), 1: lmc.ParseScene(door_xml)}
+    scenes = {0: lmc.ParseScene(torus_xml), 1: lmc.ParseScene(door_xml), 2: lmc.ParseScene(point_xml())}
     ctxs = {s: lmc.ChainContext(sc, 0) for s, sc in scenes.items()}
-    handles = {0: oracle.load(torus_xml), 1: oracle.load(door_xml)}
+    handles = {0: oracle.load(torus_xml), 1: oracle.load(door_xml), 2: oracle.load(point_xml())}
 
     def gpu_eval(s, c, l, p, v):
         lens = np.zeros((len(p), 2), np.float32)
@@ -159,3 +164,28 @@ def test_cuda_eval_batch_matches_reference_golden_and_oracle(lmc, oracle, torus_
     assert bit_equal(ll, ll_o)
     nbad = sum(0 if bit_equal(a, b) else 1 for a, b in zip(grads, grads_o))
     assert nbad == 0, "%d of %d gradients differ bitwise between CUDA and the CPU twin" % (nbad, len(grads))
+
+
+def test_point_light_paths_match_reference_code(oracle):
+    """PointLight (src/pointlight.cpp:37-116) is in neither bundled scene's active configuration; scene 2 of the
+    fixture enables the point emitter of scenes/torus/lmc.xml.  Forward value and reverse-mode gradient of its
+    direct-lighting (c, 1) and light-subpath (c, >= 2) classes against the reference's compiled code, incl. the
+    twin's `lightType == PointLight` MIS term (SURVEY.md App. B#4)."""
+    g = load_golden()
+    h = oracle.load(point_xml())
+    idx = np.where(g["scene"] == 2)[0]
+    assert len(idx) > 50 and (g["l"][idx] >= 2).any() and (g["l"][idx] == 1).any()
+    errs, fwd = [], []
+    for i in idx:
+        c, l = int(g["c"][i]), int(g["l"][i])
+        dim = 2 * max(c + l - 1, 2)
+        # light type of the record really is PointLight (0): direct-light record or emitting light
+        ll, gr = oracle.eval_batch(h, c, l, np.ascontiguousarray(g["primary"][i:i + 1, :dim + 1]), np.ascontiguousarray(g["vert"][i:i + 1]))
+        if not (np.isfinite(g["ref_fwd"][i]) and g["ss"][i] > 1e-10 and np.isfinite(g["ref_rev"][i, :dim]).all()):
+            continue
+        fwd.append(abs(ll[0] - g["ref_fwd"][i]))
+        errs.append(rel_l2(gr[0], g["ref_rev"][i, :dim]))
+    errs, fwd = np.array(errs), np.array(fwd)
+    assert len(errs) > 40
+    assert np.median(fwd) <= 1e-5 and fwd.max() <= 5e-3, (np.median(fwd), fwd.max())
+    assert np.median(errs) <= 1e-4 and np.percentile(errs, 95) <= 5e-3, (np.median(errs), np.percentile(errs, 95))

@@ -34,6 +34,7 @@ class Emitter:
         self.ind = 1
         self.decl_t, self.decl_f = [], []
         self.declared = set()
+        self.partner = {}      # sin node <-> cos node of the same argument recorded at the same nesting level
 
     def w(self, s):
         self.lines.append("    " * self.ind + s)
@@ -89,9 +90,28 @@ class Emitter:
         return "%s %s %s" % (va, sym, vb)
 
     def forward(self, items):
+        # sin(x) and cos(x) of the same x at the same nesting level: ONE evaluation of the sincos kernel, and the
+        # reverse sweep reads the partner's value as the derivative instead of evaluating it again
+        by_arg = {}
+        for it in items:
+            if it[0] == "def" and it[1].op in ("sin", "cos"):
+                by_arg.setdefault(it[1].args[0], {})[it[1].op] = it[1]
+        skip = set()
+        for arg, d in by_arg.items():
+            if len(d) == 2:
+                self.partner[d["sin"]] = d["cos"]
+                self.partner[d["cos"]] = d["sin"]
         for it in items:
             if it[0] == "def":
                 n = it[1]
+                if n in skip:
+                    continue
+                if n in self.partner:
+                    m = self.partner[n]
+                    s_, c_ = (n, m) if n.op == "sin" else (m, n)
+                    self.w("ad_sincos(%s, %s, %s);" % (self.name(n.args[0]), self.name(s_), self.name(c_)))
+                    skip.add(m)
+                    continue
                 self.w("%s = %s;" % (self.name(n), self.expr(n)))
             else:
                 _, sp, branches = it
@@ -129,13 +149,13 @@ class Emitter:
         if op == "neg": return minus(ae)
         if op == "sq": return plus("%s * (2.0f * %s)" % (ae, a[0]))
         if op == "inv": return minus("%s * (%s * %s)" % (ae, r, r))
-        if op == "sin": return plus("%s * ad_cos(%s)" % (ae, a[0]))
-        if op == "cos": return minus("%s * ad_sin(%s)" % (ae, a[0]))
+        if op == "sin": return plus("%s * %s" % (ae, self.name(self.partner[e]) if e in self.partner else "ad_cos(%s)" % a[0]))
+        if op == "cos": return minus("%s * %s" % (ae, self.name(self.partner[e]) if e in self.partner else "ad_sin(%s)" % a[0]))
         if op == "sqrt": return plus("%s * (0.5f / %s)" % (ae, r))
         if op == "exp": return plus("%s * %s" % (ae, r))
         if op == "log": return plus("%s / %s" % (ae, a[0]))
         if op == "acos": return minus("%s / ad_sqrt(1.0f - %s * %s)" % (ae, a[0], a[0]))
-        if op == "pow": return plus("%s * (%s * ad_pow(%s, %s - 1.0f))" % (ae, a[1], a[0], a[1]))
+        if op == "pow": return plus("%s * (%s * %s / %s)" % (ae, a[1], r, a[0]))      # y x^(y-1) = y x^y / x
         if op == "atan2":
             den = "(%s * %s + %s * %s)" % (a[0], a[0], a[1], a[1])
             return plus("%s * (%s / %s)" % (ae, a[1], den)) if k == 0 else minus("%s * (%s / %s)" % (ae, a[0], den))
@@ -174,33 +194,37 @@ class Emitter:
 def emit_stage(name):
     prog = st.program(name)
     nin, nout = st.STAGES[name]
-    sig = "const float *scene, const float *vert, const float *lvert, float lightType, const T *in"
+    terminal = nout == 1
+    sig = "const float *scene, const float *vert, const float *lvert, float lightType, const T *in, const T *lp"
     text = []
-    # forward only
-    em = Emitter(prog)
-    em.forward(prog.fwd)
-    for i, o in enumerate(prog.outputs):
-        em.w("out[%d] = %s;" % (i, em.as_t(o)))
-    text.append("template <class T>\nLMC_HD_NOINLINE void st_%s_fwd(%s, T *out) {" % (name, sig))
-    text += _decls(em)
-    text += em.lines
-    text.append("}")
+    if not terminal:
+        em = Emitter(prog)
+        em.forward(prog.fwd)
+        for i, o in enumerate(prog.outputs):
+            em.w("out[%d] = %s;" % (i, em.as_t(o)))
+        text.append("template <class T>\nLMC_HD_NOINLINE void st_%s_fwd(%s, T *out) {" % (name, sig))
+        text += _decls(em)
+        text += em.lines
+        text.append("}")
     # forward + reverse
     em = Emitter(prog)
     em.accs = set()
     em.forward(prog.fwd)
-    for i, o in enumerate(prog.outputs):
-        em.w("out[%d] = %s;" % (i, em.as_t(o)))
+    if terminal:
+        em.w("out[0] = %s;" % em.as_t(prog.outputs[0]))
     fwd_lines = em.lines
     em.lines = []
     for i, o in enumerate(prog.outputs):
         if cl._has_acc(o):
             em.w("%s = %s + oadj[%d];" % (em.acc(o), em.acc(o), i))
     em.reverse(prog.rev)
-    for i in range(nin):
-        n = prog.inputs["in[%d]" % i]
-        em.w("iadj[%d] = %s;" % (i, em.acc(n) if n in prog.nz else "ad_const<T>(0.0f)"))
-    text.append("template <class T, bool COMPAT>\nLMC_HD_NOINLINE void st_%s_rev(%s, const T *oadj, T *out, T *iadj) {" % (name, sig))
+    for key, n in prog.inputs.items():
+        if not n.diff:
+            continue
+        arr, idx = key[:2], int(key[3:-1])
+        dst = "iadj" if arr == "in" else "ladj"
+        em.w("%s[%d] = %s;" % (dst, idx, em.acc(n) if n in prog.nz else "ad_const<T>(0.0f)"))
+    text.append("template <class T, bool COMPAT>\nLMC_HD_NOINLINE void st_%s_rev(%s, const T *oadj, T *out, T *iadj, T *ladj) {" % (name, sig))
     text += _decls(em)
     text += fwd_lines
     accs = sorted(em.accs, key=lambda s: int(s[1:]))

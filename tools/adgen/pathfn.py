@@ -552,18 +552,31 @@ def sample_roughdielectric(adjoint, b, wi, normal, r0, r1, uDiscrete):
     return wo, contrib, cosWo, pdf, revPdf
 
 
+# The BSDF table of the differentiable twin, in the order of the reference's if-chain (src/bsdf.cpp:24-55, 87-150):
+# (type id, evaluate(adjoint, b, wi, normal, wo) -> contrib, cosWo, pdf, revPdf,
+#           sample(adjoint, b, wi, normal, r0, r1, uDiscrete) -> wo, contrib, cosWo, pdf, revPdf).
+# A new BSDF is a new row here (its adjoint is generated) plus a row of LMC_BSDF_TABLE in csrc/core/bsdf.h.
+BSDF_TABLE = [
+    (BSDF_PHONG, lambda adj, b, wi, n, wo: evaluate_phong(b, wi, n, wo),
+     lambda adj, b, wi, n, r0, r1, u: sample_phong(b, wi, n, r0, r1, u)),
+    (BSDF_ROUGHDIELECTRIC, lambda adj, b, wi, n, wo: evaluate_roughdielectric(adj, b, wi, n, wo),
+     lambda adj, b, wi, n, r0, r1, u: sample_roughdielectric(adj, b, wi, n, r0, r1, u)),
+    (BSDF_LAMBERTIAN, lambda adj, b, wi, n, wo: evaluate_lambertian(b, wi, n, wo),
+     lambda adj, b, wi, n, r0, r1, u: sample_lambertian(b, wi, n, r0, r1)),
+]
+
+
 def evaluate_bsdf(adjoint, buffer, wi, normal, wo):     # src/bsdf.cpp:13-66
     t = buffer[0]
     b = buffer + 1
-    ret = begin_if(Eq(t, BSDF_PHONG), 6)
-    c, cw, p, rp = evaluate_phong(b, wi, normal, wo)
-    set_cond_output(c + [cw, p, rp])
-    begin_else_if(Eq(t, BSDF_ROUGHDIELECTRIC))
-    c, cw, p, rp = evaluate_roughdielectric(adjoint, b, wi, normal, wo)
-    set_cond_output(c + [cw, p, rp])
-    begin_else_if(Eq(t, BSDF_LAMBERTIAN))
-    c, cw, p, rp = evaluate_lambertian(b, wi, normal, wo)
-    set_cond_output(c + [cw, p, rp])
+    ret = None
+    for k, (tid, ev, _) in enumerate(BSDF_TABLE):
+        if k == 0:
+            ret = begin_if(Eq(t, tid), 6)
+        else:
+            begin_else_if(Eq(t, tid))
+        c, cw, p, rp = ev(adjoint, b, wi, normal, wo)
+        set_cond_output(c + [cw, p, rp])
     begin_else()
     set_cond_output([C(0.0)] * 6)
     end_if()
@@ -573,15 +586,14 @@ def evaluate_bsdf(adjoint, buffer, wi, normal, wo):     # src/bsdf.cpp:13-66
 def sample_bsdf(adjoint, buffer, wi, normal, r0, r1, uDiscrete):     # src/bsdf.cpp:68-171
     t = buffer[0]
     b = buffer + 1
-    ret = begin_if(Eq(t, BSDF_PHONG), 9)
-    wo, c, cw, p, rp = sample_phong(b, wi, normal, r0, r1, uDiscrete)
-    set_cond_output(wo + c + [cw, p, rp])
-    begin_else_if(Eq(t, BSDF_ROUGHDIELECTRIC))
-    wo, c, cw, p, rp = sample_roughdielectric(adjoint, b, wi, normal, r0, r1, uDiscrete)
-    set_cond_output(wo + c + [cw, p, rp])
-    begin_else_if(Eq(t, BSDF_LAMBERTIAN))
-    wo, c, cw, p, rp = sample_lambertian(b, wi, normal, r0, r1)
-    set_cond_output(wo + c + [cw, p, rp])
+    ret = None
+    for k, (tid, _, sm) in enumerate(BSDF_TABLE):
+        if k == 0:
+            ret = begin_if(Eq(t, tid), 9)
+        else:
+            begin_else_if(Eq(t, tid))
+        wo, c, cw, p, rp = sm(adjoint, b, wi, normal, r0, r1, uDiscrete)
+        set_cond_output(wo + c + [cw, p, rp])
     begin_else()
     set_cond_output([C(0.0)] * 9)
     end_if()

@@ -63,7 +63,12 @@ def record_stage(name):
     nin, nout = STAGES[name]
     cl.begin_function()
     params = pf.Params()
-    x = [cl.inp("in[%d]" % i, True) for i in range(nin)]
+    if name == "connect_camera":
+        x = [cl.inp("lp[%d]" % i, True) for i in range(NL)]
+    elif name == "cam_connect":
+        x = [cl.inp("in[%d]" % i, True) for i in range(NS)] + [cl.inp("lp[%d]" % i, True) for i in range(NL)]
+    else:
+        x = [cl.inp("in[%d]" % i, True) for i in range(nin)]
     vert = pf.Buf(params, "vert")
     lvert = pf.Buf(params, "lvert")
     scn = pf.Scene(pf.Buf(params, "scene"))
@@ -169,9 +174,12 @@ def program(name):
 def _run(name, scene, vert, voff, lvert_off, lightType, xin, out_adj=None, compat=True):
     prog = program(name)
     vals = {}
+    lpbase = NS if name == "cam_connect" else 0
     for key in prog.inputs:
         if key.startswith("in["):
             vals[key] = xin[int(key[3:-1])]
+        elif key.startswith("lp["):
+            vals[key] = xin[lpbase + int(key[3:-1])]
         elif key.startswith("vert["):
             vals[key] = float(vert[voff + int(key[5:-1])])
         elif key.startswith("lvert["):
@@ -183,7 +191,12 @@ def _run(name, scene, vert, voff, lvert_off, lightType, xin, out_adj=None, compa
     outs, adj = prog.evaluate(vals, out_adj, compat)
     if adj is not None:
         nin = STAGES[name][0]
-        adj = [adj.get("in[%d]" % i, 0.0) for i in range(nin)]
+        if name == "connect_camera":
+            adj = [adj.get("lp[%d]" % i, 0.0) for i in range(NL)]
+        elif name == "cam_connect":
+            adj = [adj.get("in[%d]" % i, 0.0) for i in range(NS)] + [adj.get("lp[%d]" % i, 0.0) for i in range(NL)]
+        else:
+            adj = [adj.get("in[%d]" % i, 0.0) for i in range(nin)]
     return outs, adj
 
 

@@ -20,7 +20,7 @@ syms = []
 for line in out.splitlines():
     p = line.split()
     if len(p) >= 8 and p[3] == 'FUNC' and p[6] == sec_idx:
-        syms.append((int(p[1], 16), int(p[2]), p[7]))
+        syms.append((int(p[1], 16), int(p[2], 0), p[7]))
 syms.sort()
 def demangle(n):
     n = n.split('$')[-1] if '$' in n else n
