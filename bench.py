@@ -226,6 +226,16 @@ def device_run(lmc, torch, dist, workload, n_local, M, K, W, rank, world, local,
 
     film_t = torch.zeros(scene.height, scene.width, 3, dtype=torch.float32, device="cuda")
     ctx.film_bind(film_t.data_ptr())
+    if world > 1:
+        # the film communicator lives behind the C ABI (lmc_comm_unique_id / lmc_comm_init_rank / lmc_allreduce_film):
+        # rank 0 creates the NCCL id, torch.distributed is only the side channel that hands it to the other ranks
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.from_numpy(lmc.comm_unique_id()))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(world, rank, uid.cpu().numpy())
+        ctx.allreduce_film()              # untimed: the first collective of a communicator sets up its channels (film is still zero)
+        torch.cuda.synchronize()
     ctx.begin(n_local, norm, init_ls, chain_base=rank * n_local, total_chains=total, samples_per_chain=M * (K + W))
     for _ in range(W):
         ctx.run(M)
@@ -241,7 +251,7 @@ def device_run(lmc, torch, dist, workload, n_local, M, K, W, rank, world, local,
     for _ in range(K):
         ctx.run(M)
     if world > 1:
-        dist.all_reduce(film_t)           # the single NCCL all-reduce of the fp32 film
+        ctx.allreduce_film()              # the single NCCL all-reduce of the fp32 film (lmc_allreduce_film)
     ev1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -269,10 +279,10 @@ def device_run(lmc, torch, dist, workload, n_local, M, K, W, rank, world, local,
         torch.cuda.synchronize()
         t0 = time.time()
         ctx.begin(n_local, norm, pinned_init.numpy(), chain_base=rank * n_local, total_chains=total, samples_per_chain=M * K)
-        for _ in range(K):
+        for k in range(K):
             ctx.run(M)
-            if world > 1:
-                dist.all_reduce(film_t)
+            if world > 1 and k == K - 1:
+                ctx.allreduce_film()      # once, at the end: an all-reduce is in place, the chains keep splatting
             host_film.copy_(film_t, non_blocking=False)
         torch.cuda.synchronize()
         e2e_s = time.time() - t0
