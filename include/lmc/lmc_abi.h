@@ -64,6 +64,10 @@ typedef struct lmc_stats {
     uint64_t kernel_launches;    /* CUDA kernels launched by this ctx so far */
     double last_kernel_ms;       /* device time of the chain kernels of the last lmc_run_chains (CUDA events) */
     uint64_t outlier_resets;     /* chain resets of the "stuck chain" rule, src/mlt.cpp:147-169 */
+    uint64_t cache_queries;      /* global cache (option globalcache): global_cache_t::query calls, src/global_cache.h:96 */
+    uint64_t cache_hits;         /* ... that found a neighbour within PSS_QUERY_DIST */
+    uint32_t cache_count[5];     /* entries stored per PSS dimension D = 4, 6, 8, 10, 12 (3000 = ready) */
+    uint32_t reserved_u32;
 } lmc_stats;
 
 /* chain-run descriptor: the loop-invariant inputs of the lambda at src/mlt.cpp:60-90 */

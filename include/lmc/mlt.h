@@ -138,6 +138,7 @@ inline MLTResult MLT(const Scene *scene, const std::vector<int> &devices = std::
         for (int k = 0; k < 4; k++) { res.stats.proposed[k] += s.proposed[k]; res.stats.accepted[k] += s.accepted[k]; }
         res.stats.gradient_evals += s.gradient_evals; res.stats.gradient_nonfinite += s.gradient_nonfinite;
         res.stats.kernel_launches += s.kernel_launches; res.stats.outlier_resets += s.outlier_resets;
+        res.stats.cache_queries += s.cache_queries; res.stats.cache_hits += s.cache_hits;
     }
     // MergeBuffer(direct / directSpp, indirect / spp) -> BufferToFilm -> WriteImage, src/mlt.cpp:203-210
     const Float sppRun = Float(double(numSamplesPerChain) * double(numChains) / double(numPixels));

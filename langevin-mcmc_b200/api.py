@@ -30,7 +30,8 @@ class _Stats(ctypes.Structure):
     _fields_ = [("proposed", ctypes.c_uint64 * 4), ("accepted", ctypes.c_uint64 * 4),
                 ("gradient_evals", ctypes.c_uint64), ("gradient_nonfinite", ctypes.c_uint64),
                 ("kernel_launches", ctypes.c_uint64), ("last_kernel_ms", ctypes.c_double),
-                ("outlier_resets", ctypes.c_uint64)]
+                ("outlier_resets", ctypes.c_uint64), ("cache_queries", ctypes.c_uint64), ("cache_hits", ctypes.c_uint64),
+                ("cache_count", ctypes.c_uint32 * 5), ("reserved_u32", ctypes.c_uint32)]
 
 
 class _RunDesc(ctypes.Structure):
@@ -258,7 +259,8 @@ class ChainContext:
         _check(load_library().lmc_get_stats(self._c, ctypes.byref(s)))
         return {"proposed": list(s.proposed), "accepted": list(s.accepted), "gradient_evals": s.gradient_evals,
                 "gradient_nonfinite": s.gradient_nonfinite, "kernel_launches": s.kernel_launches,
-                "last_kernel_ms": s.last_kernel_ms, "outlier_resets": s.outlier_resets}
+                "last_kernel_ms": s.last_kernel_ms, "outlier_resets": s.outlier_resets,
+                "cache_queries": s.cache_queries, "cache_hits": s.cache_hits, "cache_count": list(s.cache_count)}
 
     def film(self):
         out = np.zeros((self.scene.height, self.scene.width, 3), np.float32)

@@ -78,4 +78,24 @@ LMC_HD void chain_run(const Scene &sc, const RunParams &rp, int globalChainId, C
     cs.rngEpoch = rng.epoch;
 }
 
+// Global cache: apply the push requests of ONE iteration in chain order (src/mlt.cpp:121-127 pushes under a mutex in
+// whatever order the threads arrive; here the order is defined: by chain id, all requests of an iteration after the
+// iteration).  Entries beyond PSS_MAX_SIZE are dropped (global_cache_t::push returns false once is_ready), a slot becomes
+// ready when it holds PSS_MAX_SIZE entries.  Host form; the device runs the same rule as k_cache_count / _scan / _write.
+template <int MAXD>
+inline void cache_commit_host(const Scene &sc, ChainState<MAXD> *const *states, int n) {
+    for (int i = 0; i < n; i++) {
+        ChainVars<MAXD> &ch = states[i]->ch;
+        const int dim = ch.pushDim;
+        if (dim <= 0) continue;
+        ch.pushDim = 0;
+        const int s = cache_slot(dim);
+        if (s < 0 || sc.gc.count[s] >= LMC_CACHE_MAX_SIZE) continue;
+        float *e = sc.gc.data + cache_slot_offset(s) + (size_t)sc.gc.count[s] * 3 * dim;
+        for (int k = 0; k < dim; k++) { e[k] = ch.pss[k]; e[dim + k] = ch.v1[k]; e[2 * dim + k] = ch.v2[k]; }
+        sc.gc.count[s] += 1;
+    }
+    for (int s = 0; s < LMC_CACHE_SLOTS; s++) if (sc.gc.count[s] >= LMC_CACHE_MAX_SIZE) sc.gc.ready[s] = 1;
+}
+
 }  // namespace lmc

@@ -117,6 +117,12 @@ struct ChainVars {               // Chain (src/mutation.h:28-43) + per-chain loo
     int adjacentReject;
     int lastMutationType;
     int outlierResets;                // statistics only: how often the reset of src/mlt.cpp:147-169 fired
+    // global cache (src/mutation.h:28-43 Chain::pss, last_pss, pathWeight, queried; used only with opt.cacheEnabled)
+    float pss[Limits<MAXD>::DIM], last_pss[Limits<MAXD>::DIM];
+    float pathWeight;
+    int queried;
+    int cacheQueries, cacheHits;      // statistics: global_cache_t::query calls / calls that found a neighbour
+    int pushDim;                      // > 0: this chain asks for a push of (pss, v1, v2) into the cache of that dimension
 };
 
 template <int MAXD>
@@ -125,6 +131,8 @@ LMC_HD void chain_vars_init(ChainVars<MAXD> &c) {
         c.v1[i] = 0; c.v2[i] = 0; c.curr_new_v1[i] = 0; c.curr_new_v2[i] = 0; c.prop_new_v1[i] = 0; c.prop_new_v2[i] = 0;
     }
     c.buffered = 0; c.t = 0; c.lastScoreSum = 1.0f; c.lastScore = 1.0f; c.adjacentReject = 0; c.lastMutationType = MUT_LARGE; c.outlierResets = 0;
+    for (int i = 0; i < Limits<MAXD>::DIM; i++) { c.pss[i] = 0; c.last_pss[i] = 0; }
+    c.pathWeight = 0.0f; c.queried = 0; c.pushDim = 0; c.cacheQueries = 0; c.cacheHits = 0;
 }
 
 // Film accumulation (src/image.h:66-77).  FILM is a functor add(pixelIndex, channel, value)
@@ -335,12 +343,51 @@ struct StepScratch {
 // How MALASmallStep obtains the Gaussian of a state (src/mutation_mala.h:94-163 with the global
 // cache never ready): 0 = IsotropicGaussian(malaStdDev); 1 = ComputeGaussian with a zero gradient
 // (ssScore <= 1e-10, the reference skips dervFunc); 2 = ComputeGaussian with the evaluated gradient.
+// With the global cache (opt.cacheEnabled) a fourth way: 3 = the dimension's cache is ready, no gradient is evaluated
+// any more, the moments come from a cache query / are reused (src/mutation_mala.h:131-161).
+LMC_HD bool cache_ready(const Scene &sc, int dim) {
+    if (!sc.opt.cacheEnabled) return false;
+    const int s = cache_slot(dim);
+    return s >= 0 && sc.gc.ready[s] != 0;
+}
 template <int MAXD>
 LMC_HD int mala_grad_mode(const Scene &sc, const MarkovState<MAXD> &st) {
     const int dim = path_dimension(st.path);
     const bool haveFunc = (st.sp.camDepth + st.sp.lightDepth - 1) <= sc.opt.maxDervDepth && grad_supported(sc, st.path);
-    if (dim >= sc.opt.pssMinLength && dim <= sc.opt.pssMaxLength && haveFunc) return (st.sp.ssScore > 1e-10f) ? 2 : 1;
-    return 0;
+    const bool inRange = dim >= sc.opt.pssMinLength && dim <= sc.opt.pssMaxLength;
+    const bool ready = inRange && cache_ready(sc, dim);
+    if (inRange && !ready && haveFunc) return (st.sp.ssScore > 1e-10f) ? 2 : 1;
+    return ready ? 3 : 0;
+}
+
+// global_cache_t::query (src/global_cache.h:96-124): the entries within radius^2 = D * PSS_QUERY_DIST^2 of pss -- at
+// most LMC_CACHE_KNN of them: the reference's patched nanoflann stops its KD-tree walk after 5 in-radius points
+// (nanoflann.hpp:256-262), i.e. which 5 it keeps depends on the tree; here they are the first 5 in INSERTION order --
+// averaged with weights 1 / (dist^2 + 1e-6), dist being the SQUARED distance nanoflann reports.
+LMC_HD bool cache_query(const Scene &sc, int dim, const float *pss, float *v1, float *v2) {
+    const int s = cache_slot(dim);
+    if (s < 0 || !sc.gc.ready[s]) return false;
+    const float *base = sc.gc.data + cache_slot_offset(s);
+    const int stride = 3 * dim;
+    const float radius = (float)dim * (LMC_CACHE_QUERY_DIST * LMC_CACHE_QUERY_DIST);
+    int idx[LMC_CACHE_KNN]; float dist[LMC_CACHE_KNN]; int found = 0;
+    for (int e = 0; e < LMC_CACHE_MAX_SIZE && found < LMC_CACHE_KNN; e++) {
+        const float *q = base + (size_t)e * stride;
+        float d = 0.0f;
+        for (int j = 0; j < dim; j++) { const float t = pss[j] - q[j]; d += t * t; }
+        if (d < radius) { idx[found] = e; dist[found] = d; found++; }
+    }
+    if (!found) return false;
+    double sum_w = 0.0;
+    for (int i = 0; i < dim; i++) { v1[i] = 0.0f; v2[i] = 0.0f; }
+    for (int k = 0; k < found; k++) {
+        const float *q = base + (size_t)idx[k] * stride;
+        const float w = 1.0f / (dist[k] * dist[k] + 1e-6f);
+        for (int i = 0; i < dim; i++) { v1[i] += q[dim + i] * w; v2[i] += q[2 * dim + i] * w; }
+        sum_w += (double)w;
+    }
+    for (int i = 0; i < dim; i++) { v1[i] = (float)((double)v1[i] / sum_w); v2[i] = (float)((double)v2[i] / sum_w); }
+    return true;
 }
 
 // dervFunc + IsFinite guard (src/mutation_mala.h:100-110)
@@ -360,10 +407,33 @@ LMC_HD void mala_eval_gradient(const Scene &sc, const MarkovState<MAXD> &st, flo
 // drift clamp, Adam-style moments, diagonal Gaussian (src/mutation_mala.h:111-129, src/mala.cpp:7-51).
 // `grad` is read only when mode == 2.
 template <int MAXD>
-LMC_HD_NOINLINE void mala_finish_gaussian(const Scene &sc, const MarkovState<MAXD> &st, const ChainVars<MAXD> &ch, int mode,
+LMC_HD_NOINLINE void mala_finish_gaussian(const Scene &sc, const MarkovState<MAXD> &st, ChainVars<MAXD> &ch, int mode,
                                           const float *grad, float *new_v1, float *new_v2, Gaussian<Limits<MAXD>::DIM> &out) {
     const int dim = path_dimension(st.path);
+    if (sc.opt.cacheEnabled) {      // GetPathPss(path, chain->pss); chain->pathWeight = lsScore (src/mutation_mala.h:89-92,184-187)
+        get_path_pss(st.path, ch.pss);
+        ch.pathWeight = st.sp.lsScore;
+    }
     if (mode == 0) { isotropic_gaussian(dim, sc.opt.malaStdDev, out); return; }
+    if (mode == 3) {                // src/mutation_mala.h:131-161 / 221-252
+        bool reuse = false;
+        if (ch.queried) {
+            float dist_sqr = 0.0f;
+            for (int i = 0; i < dim; i++) { const float diff = ch.pss[i] - ch.last_pss[i]; dist_sqr += diff * diff; }
+            if (dist_sqr < (float)dim * (LMC_CACHE_REUSE_DIST * LMC_CACHE_REUSE_DIST)) reuse = true;
+        }
+        if (!reuse) {
+            ch.cacheQueries += 1;
+            if (!cache_query(sc, dim, ch.pss, ch.v1, ch.v2)) { isotropic_gaussian(dim, sc.opt.malaStdDev, out); return; }
+            ch.cacheHits += 1;
+            ch.queried = 1;
+            for (int i = 0; i < dim; i++) ch.last_pss[i] = ch.pss[i];
+        }
+        float Mq[Limits<MAXD>::DIM];
+        for (int i = 0; i < dim; i++) Mq[i] = dm_clamp(1.0f / (1e-3f + dm_sqrt(ch.v2[i])), LMC_PCD_MIN, LMC_PCD_MAX);
+        compute_gaussian_lmc(dim, ch.v1, Mq, sc.opt.malaStepsize, sc.opt.malaStdDev, st.sp.ssScore, out);
+        return;
+    }
     float vGrad[Limits<MAXD>::DIM];
     for (int i = 0; i < dim; i++) vGrad[i] = (mode == 2) ? grad[i] : 0.0f;
     float norm = 0.0f;
@@ -408,6 +478,10 @@ LMC_HD void phase_begin(const Scene &sc, const RunParams &rp, long long sampleId
     if (!ch.buffered) {
         for (int i = 0; i < Limits<MAXD>::DIM; i++) {
             ch.v1[i] = 0; ch.v2[i] = 0; ch.curr_new_v1[i] = 0; ch.curr_new_v2[i] = 0; ch.prop_new_v1[i] = 0; ch.prop_new_v2[i] = 0;
+        }
+        if (sc.opt.cacheEnabled) {
+            for (int i = 0; i < Limits<MAXD>::DIM; i++) { ch.pss[i] = 0; ch.last_pss[i] = 0; }
+            ch.queried = 0;
         }
         ch.buffered = 1;
     }
@@ -670,6 +744,11 @@ LMC_HD StepInfo phase_finish(const Scene &sc, const RunParams &rp, int chainId, 
         ncur.valid = 1;
         ch.adjacentReject = 0;
         if (isLargeStep) {
+            if (sc.opt.cacheEnabled && ch.buffered && ch.pathWeight > 1e-10f) {      // src/mlt.cpp:121-127
+                const int pdim = path_dimension(states[curIdx ^ 1].path);             // the state the chain leaves
+                if (pdim >= sc.opt.pssMinLength && pdim <= sc.opt.pssMaxLength && cache_slot(pdim) >= 0 && !cache_ready(sc, pdim))
+                    ch.pushDim = pdim;        // committed in chain order after the iteration (cache_commit / k_cache_*)
+            }
             ch.lastScoreSum = ncur.scoreSum;
             ch.lastScore = ncur.sp.lsScore;
             ncur.gaussianInitialized = 0;

@@ -103,7 +103,8 @@ struct Options {                 // src/dptoptions.h:7-34 + compile-time constan
     int seedOffset;
     int useLightCoordinateSampling;
     int largeStepMultiplexed;
-    int cacheEnabled;            // always 0 here (GlobalCache out of scope)
+    int cacheEnabled;            // option `globalcache`: the cross-chain cache of src/global_cache.h (default 0: every
+                                 // eligible MALA step evaluates its gradient -- the benchmark / parity mode)
     int maxDervDepth;            // 8
     int pssMinLength, pssMaxLength;   // 2, 12
     int adjointCompat;           // gradient of the mutations: 1 reverse sweep in the reference's merge order (default),
@@ -124,6 +125,27 @@ struct Options {                 // src/dptoptions.h:7-34 + compile-time constan
     // H2MCParam (src/h2mc.h:9-23), evaluated once on the host from sigma = perturbStdDev, L = pi/2
     float h2mcL, h2mcPosScale, h2mcPosOffset, h2mcNegScale, h2mcNegOffset;
 };
+
+// Global cache of adaptation states (src/global_cache.h:16-163, instantiated at src/mlt.cpp:53): for every PSS
+// dimension D in [PSS_MIN_LENGTH, PSS_MAX_LENGTH] up to PSS_MAX_SIZE = 3000 entries (pss[D], v1[D], v2[D]) pushed by
+// chains that leave a MALA-adapted state with an accepted large step (src/mlt.cpp:121-127).  Once a dimension is
+// full, chains of that dimension stop evaluating gradients and look their moments up here
+// (src/mutation_mala.h:131-161).  D = 2 * max(c + l - 1, 2) is even and >= 4, so five slots cover D = 4 .. 12.
+#define LMC_CACHE_SLOTS 5
+#define LMC_CACHE_MAX_SIZE 3000          // PSS_MAX_SIZE
+#define LMC_CACHE_QUERY_DIST 0.01f       // PSS_QUERY_DIST
+#define LMC_CACHE_REUSE_DIST 0.10f       // PSS_REUSE_DIST
+#define LMC_CACHE_KNN 5
+struct GlobalCacheView {
+    float *data;     // slot s (D = 4 + 2 s) starts at cache_slot_offset(s); entry e = 3 D floats: pss, v1, v2
+    int *count;      // [LMC_CACHE_SLOTS] entries stored
+    int *ready;      // [LMC_CACHE_SLOTS] is_ready
+};
+LMC_HD int cache_slot(int dim) { return (dim >= 4 && dim <= 12 && (dim & 1) == 0) ? (dim - 4) / 2 : -1; }
+LMC_HD int cache_slot_offset(int s) {        // floats before slot s: 3000 * 3 * sum_{k<s} (4 + 2k)
+    return LMC_CACHE_MAX_SIZE * 3 * (4 * s + s * (s - 1));
+}
+#define LMC_CACHE_FLOATS (LMC_CACHE_MAX_SIZE * 3 * (4 + 6 + 8 + 10 + 12))
 
 struct Scene {
     // geometry
@@ -149,6 +171,7 @@ struct Scene {
     float bsphereRadius;         // already x1000 (src/scene.cpp:40)
     float sceneSer[38];          // Serialize(scene) for the reference ABI (src/scene.cpp:164-169)
     Options opt;
+    GlobalCacheView gc;          // valid only when opt.cacheEnabled (owned by the ctx / the oracle run)
 };
 
 #define LMC_ISECT_EPS 5e-4f   // c_IsectEpsilon, src/commondef.h:53

@@ -828,20 +828,109 @@ __global__ void __launch_bounds__(128) k_mlt_init_paths(const __grid_constant__ 
 template <int MAXD>
 __global__ void k_chain_stats(const ChainRec<MAXD> *states, int n, unsigned long long *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long v[11];
-    for (int k = 0; k < 11; k++) v[k] = 0ULL;
+    unsigned long long v[13];
+    for (int k = 0; k < 13; k++) v[k] = 0ULL;
     if (i < n) {
         const ChainState<MAXD> &cs = states[i].cs;
         for (int k = 0; k < 4; k++) { v[k] = cs.nPropose[k]; v[4 + k] = cs.nAccept[k]; }
         v[8] = cs.gradStats[0]; v[9] = cs.gradStats[1]; v[10] = (unsigned long long)cs.ch.outlierResets;
+        v[11] = (unsigned long long)cs.ch.cacheQueries; v[12] = (unsigned long long)cs.ch.cacheHits;
     }
-    for (int k = 0; k < 11; k++) {
+    for (int k = 0; k < 13; k++) {
         unsigned long long x = v[k];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
         if ((threadIdx.x & 31) == 0 && x) atomicAdd(out + k, x);
     }
 }
 
+
+// ---- global cache: commit of one iteration's push requests in chain order (core/chain.h cache_commit_host) --------
+// k_cache_count   per block and slot: number of chains asking for a push            -> blockCounts[slot][block]
+// k_cache_scan    one block: exclusive scan over the blocks, starting at the slot's fill level; new fill level and
+//                 ready flag (slot full); `active` = any request at all this iteration
+// k_cache_write   stable rank of a request inside its block (warp ballots) + block offset = its entry index;
+//                 requests that land beyond PSS_MAX_SIZE are dropped; the request flag is cleared
+// All three return at once when every slot is ready (the steady state of a cache run).
+#define LMC_CACHE_BLOCK 256
+__device__ __forceinline__ bool cache_all_ready(const GlobalCacheView &gc) {
+    bool all = true;
+    for (int s = 0; s < LMC_CACHE_SLOTS; s++) all = all && gc.ready[s] != 0;
+    return all;
+}
+template <int MAXD>
+__global__ void __launch_bounds__(LMC_CACHE_BLOCK) k_cache_count(const __grid_constant__ Scene sc, const ChainRec<MAXD> *states, int n, int *blockCounts) {
+    if (cache_all_ready(sc.gc)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = (i < n) ? cache_slot(states[i].cs.ch.pushDim) : -1;
+    for (int s = 0; s < LMC_CACHE_SLOTS; s++) {
+        const int c = __syncthreads_count(slot == s);
+        if (threadIdx.x == 0) blockCounts[s * gridDim.x + blockIdx.x] = c;
+    }
+}
+static __global__ void __launch_bounds__(1024) k_cache_scan(GlobalCacheView gc, int *blockCounts, int numBlocks, int *active) {
+    __shared__ int warpSum[32];
+    __shared__ int carry;
+    if (cache_all_ready(gc)) { if (threadIdx.x == 0) *active = 0; return; }
+    int any = 0;
+    for (int s = 0; s < LMC_CACHE_SLOTS; s++) {
+        if (threadIdx.x == 0) carry = gc.count[s];
+        __syncthreads();
+        for (int b0 = 0; b0 < numBlocks; b0 += 1024) {
+            const int b = b0 + threadIdx.x;
+            const int v = (b < numBlocks) ? blockCounts[s * numBlocks + b] : 0;
+            int x = v;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+            if ((threadIdx.x & 31) == 31) warpSum[threadIdx.x >> 5] = x;
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                int w = warpSum[threadIdx.x];
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += y; }
+                warpSum[threadIdx.x] = w;
+            }
+            __syncthreads();
+            const int before = carry + ((threadIdx.x >> 5) ? warpSum[(threadIdx.x >> 5) - 1] : 0) + x - v;
+            if (b < numBlocks) blockCounts[s * numBlocks + b] = before;      // exclusive prefix = first entry index of the block
+            __syncthreads();
+            if (threadIdx.x == 1023) carry = before + v;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            any |= (carry > gc.count[s]);
+            gc.count[s] = carry < LMC_CACHE_MAX_SIZE ? carry : LMC_CACHE_MAX_SIZE;
+            if (carry >= LMC_CACHE_MAX_SIZE) gc.ready[s] = 1;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *active = any;
+}
+template <int MAXD>
+__global__ void __launch_bounds__(LMC_CACHE_BLOCK) k_cache_write(const __grid_constant__ Scene sc, ChainRec<MAXD> *states, int n, const int *blockCounts,
+                                                                const int *active) {
+    if (!*active) return;
+    __shared__ int warpCnt[LMC_CACHE_SLOTS][LMC_CACHE_BLOCK / 32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int dim = (i < n) ? states[i].cs.ch.pushDim : 0;
+    const int slot = cache_slot(dim);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int rankInWarp = 0;
+    for (int s = 0; s < LMC_CACHE_SLOTS; s++) {
+        const unsigned m = __ballot_sync(0xffffffffu, slot == s);
+        if (slot == s) rankInWarp = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) warpCnt[s][warp] = __popc(m);
+    }
+    __syncthreads();
+    if (slot >= 0) {
+        int rank = rankInWarp;
+        for (int w = 0; w < warp; w++) rank += warpCnt[slot][w];
+        const int pos = blockCounts[slot * gridDim.x + blockIdx.x] + rank;
+        ChainVars<MAXD> &ch = states[i].cs.ch;
+        if (pos < LMC_CACHE_MAX_SIZE) {
+            float *e = sc.gc.data + cache_slot_offset(slot) + (size_t)pos * 3 * dim;
+            for (int k = 0; k < dim; k++) { e[k] = ch.pss[k]; e[dim + k] = ch.v1[k]; e[2 * dim + k] = ch.v2[k]; }
+        }
+        ch.pushDim = 0;
+    }
+}
 
 // launchers (defined by LMC_INSTANTIATE_CHAIN in chain_inst_*.cu)
 #ifndef LMC_WAVEFRONT_MIN_CHAINS
@@ -864,6 +953,7 @@ struct WaveCfg {
     // issue utilisation each) run side by side: the large-step one goes to this auxiliary stream.
     cudaStream_t aux;
     cudaEvent_t evFork, evJoin;
+    int *cacheBlockCounts;       // [LMC_CACHE_SLOTS][ceil(n / LMC_CACHE_BLOCK)] + 1 (active flag); global cache runs only
 };
 #define LMC_DECLARE_CHAIN(MAXD) \
     size_t chain_state_bytes_##MAXD(); \
@@ -1014,7 +1104,18 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         // the large-step list of this iteration is consumed: refill it for the next one in the fused finish + begin
         e = cudaMemsetAsync(wl.largeCount, 0, sizeof(int), st);
         if (e != cudaSuccess) return e;
-        if (k + 1 < numSteps) k_wave_finish<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides, wl);
+        if (sc.opt.cacheEnabled) {
+            // chains interact through the cache: the iteration's push requests are committed (in chain order) between
+            // its finish and the next iteration's begin, so the two are not fused
+            const int CB = (n + LMC_CACHE_BLOCK - 1) / LMC_CACHE_BLOCK;
+            int *active = wc.cacheBlockCounts + LMC_CACHE_SLOTS * CB;
+            k_wave_finish<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides, wl);
+            k_cache_count<MAXD><<<CB, LMC_CACHE_BLOCK, 0, st>>>(sc, states, n, wc.cacheBlockCounts);
+            k_cache_scan<<<1, 1024, 0, st>>>(sc.gc, wc.cacheBlockCounts, CB, active);
+            k_cache_write<MAXD><<<CB, LMC_CACHE_BLOCK, 0, st>>>(sc, states, n, wc.cacheBlockCounts, active);
+            if (k + 1 < numSteps) k_wave_begin<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl);
+            *launches += 4;
+        } else if (k + 1 < numSteps) k_wave_finish<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides, wl);
         else k_wave_finish<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides, wl);
         *launches += 4;
         pt.mark("finish (+ begin)");

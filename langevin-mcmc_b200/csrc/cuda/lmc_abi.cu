@@ -124,6 +124,8 @@ struct lmc_ctx {
     uint64_t launches = 0;
     double lastMs = 0.0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float *cacheData = nullptr; int *cacheInts = nullptr;       // global cache (option globalcache): entries; count[5] + ready[5]
+    int *cacheBlockCounts = nullptr; int cacheBlockCap = 0;
     ncclComm_t comm = nullptr;      // film all-reduce (lmc_create_multi / lmc_comm_init_rank); NULL for a lone ctx
 };
 
@@ -202,6 +204,18 @@ int chains_begin(lmc_ctx *c) {
         CK(cudaMemsetAsync(c->sides, 0, sizeof(H2mcSide) * (size_t)n, c->stream));
         if (!c->wc.padSide) { CK(cudaMalloc((void **)&c->wc.padSide, sizeof(H2mcSide))); CK(cudaMemsetAsync(c->wc.padSide, 0, sizeof(H2mcSide), c->stream)); }
     }
+    if (c->sc.opt.cacheEnabled) {
+        // a fresh cache for every job (GlobalCache globalCache; src/mlt.cpp:53)
+        CK(cudaMemsetAsync(c->cacheData, 0, sizeof(float) * (size_t)LMC_CACHE_FLOATS, c->stream));
+        CK(cudaMemsetAsync(c->cacheInts, 0, sizeof(int) * 2 * LMC_CACHE_SLOTS, c->stream));
+        const int need = LMC_CACHE_SLOTS * ((n + LMC_CACHE_BLOCK - 1) / LMC_CACHE_BLOCK) + 1;
+        if (c->cacheBlockCap < need) {
+            if (c->cacheBlockCounts) { cudaFree(c->cacheBlockCounts); c->cacheBlockCounts = nullptr; }
+            CK(cudaMalloc((void **)&c->cacheBlockCounts, sizeof(int) * (size_t)need));
+            c->cacheBlockCap = need;
+        }
+        c->wc.cacheBlockCounts = c->cacheBlockCounts;
+    }
     c->fullWavesTuned = 0; c->iterationsSinceBegin = 0;
     c->wc.fullWavesTuned = &c->fullWavesTuned; c->wc.iterationsSinceBegin = &c->iterationsSinceBegin;
     c->launches++;
@@ -231,7 +245,7 @@ int chain_stats(lmc_ctx *c) {
     const int n = c->desc.num_chains;
     const int d = c->maxdTemplate;
     const void *st = c->states;
-    CK(cudaMemsetAsync(c->statsDev, 0, 11 * sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(c->statsDev, 0, 13 * sizeof(unsigned long long), c->stream));
     c->launches++;
     CK(d == 4 ? launch_chain_stats_4(c->stream, st, n, c->statsDev)
               : (d == 8 ? launch_chain_stats_8(c->stream, st, n, c->statsDev) : launch_chain_stats_12(c->stream, st, n, c->statsDev)));
@@ -380,6 +394,7 @@ int lmc_create(const lmc_scene *scene, int32_t device, lmc_ctx **out) {
     if (s.head.opt.maxDervDepth > 8) return fail(LMC_ERR_UNSUPPORTED, "maxdervdepth must be <= 8 (derivative functions exist for camDepth + lightDepth - 1 <= 8)");
     if (s.head.opt.largeStepMultiplexed) return fail(LMC_ERR_UNSUPPORTED, "largestepmultiplexed is not supported");
     if (s.head.opt.useLightCoordinateSampling) return fail(LMC_ERR_UNSUPPORTED, "uselightcoordinatesampling is not supported (the sampler has no light-coordinate branch)");
+    if (s.head.opt.cacheEnabled && s.head.opt.h2mc) return fail(LMC_ERR_UNSUPPORTED, "globalcache applies to the MALA mutation only");
     if (s.head.opt.adjointCompat < 0 || s.head.opt.adjointCompat > 2) return fail(LMC_ERR_ARG, "adjointcompat must be 0, 1 or 2");
     lmc_ctx *c = new lmc_ctx();
     c->device = device;
@@ -394,9 +409,18 @@ int lmc_create(const lmc_scene *scene, int32_t device, lmc_ctx **out) {
     UP(d.env.image, s.envImage, float); UP(d.env.cdfRows, s.envCdfRows, float); UP(d.env.cdfCols, s.envCdfCols, float);
     UP(d.env.rowWeights, s.envRowWeights, float);
 #undef UP
+    d.gc.data = nullptr; d.gc.count = nullptr; d.gc.ready = nullptr;
+    if (d.opt.cacheEnabled) {
+        if (cudaMalloc((void **)&c->cacheData, sizeof(float) * (size_t)LMC_CACHE_FLOATS) != cudaSuccess ||
+            cudaMalloc((void **)&c->cacheInts, sizeof(int) * 2 * LMC_CACHE_SLOTS) != cudaSuccess) {
+            lmc_destroy(c);
+            return fail(LMC_ERR_CUDA, "device allocation failed (global cache)");
+        }
+        d.gc.data = c->cacheData; d.gc.count = c->cacheInts; d.gc.ready = c->cacheInts + LMC_CACHE_SLOTS;
+    }
     const size_t filmBytes = (size_t)d.cam.width * d.cam.height * 3 * sizeof(float);
     if (cudaMalloc((void **)&c->film, filmBytes) != cudaSuccess || cudaMemset(c->film, 0, filmBytes) != cudaSuccess ||
-        cudaMalloc((void **)&c->statsDev, 11 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc((void **)&c->statsDev, 13 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
         lmc_destroy(c);
         return fail(LMC_ERR_CUDA, "device allocation failed");
@@ -430,6 +454,9 @@ void lmc_destroy(lmc_ctx *c) {
     if (c->initLs) cudaFree(c->initLs);
     if (c->film && c->filmOwned) cudaFree(c->film);
     if (c->statsDev) cudaFree(c->statsDev);
+    if (c->cacheData) cudaFree(c->cacheData);
+    if (c->cacheInts) cudaFree(c->cacheInts);
+    if (c->cacheBlockCounts) cudaFree(c->cacheBlockCounts);
     if (c->listMem) cudaFree(c->listMem);
     if (c->sides) cudaFree(c->sides);
     if (c->queueMem) cudaFree(c->queueMem);
@@ -499,11 +526,18 @@ int lmc_get_stats(lmc_ctx *c, lmc_stats *out) {
     if (c->begun) {
         const int rc = chain_stats(c);
         if (rc) return rc;
-        unsigned long long h[11];
+        unsigned long long h[13];
         CK(cudaMemcpyAsync(h, c->statsDev, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         for (int k = 0; k < 4; k++) { out->proposed[k] = h[k]; out->accepted[k] = h[4 + k]; }
         out->gradient_evals = h[8]; out->gradient_nonfinite = h[9]; out->outlier_resets = h[10];
+        out->cache_queries = h[11]; out->cache_hits = h[12];
+        if (c->sc.opt.cacheEnabled) {
+            int ci[2 * LMC_CACHE_SLOTS];
+            CK(cudaMemcpyAsync(ci, c->cacheInts, sizeof(ci), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            for (int s = 0; s < LMC_CACHE_SLOTS; s++) out->cache_count[s] = (uint32_t)ci[s];
+        }
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->lastMs = ms;
         else cudaGetLastError();

@@ -15,6 +15,7 @@
 // Embree's BVH build (src/trianglemesh.cpp:107-143) is replaced by the binned-SAH BVH2 below.
 #include "host_scene.h"
 #include "mini_xml.h"
+#include "image_decode.h"
 #include "../core/bsdf.h"
 #include "../core/bvh.h"
 
@@ -231,12 +232,17 @@ static M44 parse_transform(const XmlNode &node) {
 }
 
 // ------------------------------------------------------------------------------------------
-// images (.rawf written by tools/stage_scenes.py)
+// images: "<file>.rawf" (pre-decoded by tools/stage_scenes.py) when it exists, else PNG / EXR decoded here
+// (image_decode.h; what the reference does through OpenImageIO, src/bitmaptexture.h:73-146, src/image.cpp:5-45)
 // ------------------------------------------------------------------------------------------
-struct RawImage { int w = 0, h = 0, is8 = 0; std::vector<float> rgb; };
+typedef DecodedImage RawImage;
 static RawImage load_rawf(const std::string &path) {
     std::ifstream f(path + ".rawf", std::ios::binary);
-    if (!f) throw std::runtime_error("cannot open image '" + path + ".rawf' (run tools/stage_scenes.py)");
+    if (!f) {
+        RawImage native;
+        if (decode_image_native(path, native)) return native;
+        throw std::runtime_error("cannot open image '" + path + ".rawf' (JPEG textures are pre-decoded: run tools/stage_scenes.py)");
+    }
     char magic[4]; int hdr[3];
     f.read(magic, 4); f.read((char *)hdr, 12);
     if (memcmp(magic, "RAWF", 4) != 0) throw std::runtime_error("bad rawf magic: " + path);
@@ -568,7 +574,7 @@ const OptField kOptFields[] = {
     LMC_OI("h2mc", h2mc), LMC_OI("mala", mala), LMC_OI("numchains", numChains), LMC_OI("seedoffset", seedOffset),
     LMC_OI("uselightcoordinatesampling", useLightCoordinateSampling), LMC_OI("largestepmultiplexed", largeStepMultiplexed),
     LMC_OI("maxdervdepth", maxDervDepth), LMC_OI("pssminlength", pssMinLength), LMC_OI("pssmaxlength", pssMaxLength),
-    LMC_OI("adjointcompat", adjointCompat), LMC_OI("outlierweakrejectcnt", outlierWeakRejectCnt),
+    LMC_OI("adjointcompat", adjointCompat), LMC_OI("globalcache", cacheEnabled), LMC_OI("outlierweakrejectcnt", outlierWeakRejectCnt),
     LMC_OI("outlierstrongrejectcnt", outlierStrongRejectCnt), LMC_OF("outlierratiothreshold", outlierRatioThreshold),
     LMC_OF("perturbstddev", perturbStdDev), LMC_OF("roughnessthreshold", roughnessThreshold),
     LMC_OF("largestepprob", largeStepProbability), LMC_OF("largestepscale", largeStepProbScale),
@@ -1095,7 +1101,7 @@ template <class T> static void rd_vec(std::ifstream &f, std::vector<T> &v) {
     v.resize(n);
     if (n) f.read((char *)v.data(), n * sizeof(T));
 }
-static const uint32_t kPackVersion = 1;
+static const uint32_t kPackVersion = 2;
 
 void save_scene_pack(const std::string &path, const SceneStore &s) {
     std::ofstream f(path, std::ios::binary);

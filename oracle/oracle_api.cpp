@@ -27,6 +27,7 @@
 #include "../langevin-mcmc_b200/csrc/core/chain.h"
 #include "../langevin-mcmc_b200/csrc/host/host_scene.h"
 #include "../langevin-mcmc_b200/csrc/host/mlt_init.h"
+#include "../langevin-mcmc_b200/csrc/host/image_decode.h"
 
 using namespace lmc;
 
@@ -70,7 +71,7 @@ void run_chains_t(const Scene &sc, int numChains, int chainBase, int totalChains
     const int W = sc.cam.width, H = sc.cam.height;
     if (threads < 1) threads = 1;
     std::vector<std::vector<float>> films(threads);
-    std::vector<std::vector<unsigned long long>> tstats(threads, std::vector<unsigned long long>(11, 0ULL));
+    std::vector<std::vector<unsigned long long>> tstats(threads, std::vector<unsigned long long>(18, 0ULL));
     std::atomic<int> next(0);
     auto work = [&](int w) {
         ref_grad_hook() = (g_useRef && g_refLoaded) ? ref_gradient : nullptr;
@@ -100,7 +101,58 @@ void run_chains_t(const Scene &sc, int numChains, int chainBase, int totalChains
     for (int w = 0; w < threads; w++) pool.emplace_back(work, w);
     for (auto &t : pool) t.join();
     if (film) for (int w = 0; w < threads; w++) for (size_t k = 0; k < (size_t)W * H * 3; k++) film[k] += films[w][k];
-    if (stats) for (int k = 0; k < 11; k++) { stats[k] = 0; for (int w = 0; w < threads; w++) stats[k] += tstats[w][k]; }
+    if (stats) for (int k = 0; k < 18; k++) { stats[k] = 0; for (int w = 0; w < threads; w++) stats[k] += tstats[w][k]; }
+}
+
+// Global cache on (option globalcache = 1): chains interact through the cache, so they advance in LOCKSTEP -- every chain
+// does iteration k, then the push requests of that iteration are committed in chain order (cache_commit_host) -- which is
+// exactly what the device does between its finish and begin kernels.
+template <int MAXD>
+void run_chains_cache_t(Scene sc, int numChains, int chainBase, int totalChains, long long numSteps,
+                        long long numSamplesThisChain, float normalization, const float *initLs, float *film,
+                        unsigned char *trace, float *aTrace, int threads, unsigned long long *stats) {
+    RunParams rp; rp.normalization = normalization; rp.numChains = totalChains;
+    rp.numSamplesThisChain = numSamplesThisChain; rp.initLsScore = initLs;
+    std::vector<float> data(LMC_CACHE_FLOATS, 0.0f);
+    int count[LMC_CACHE_SLOTS] = {0}, ready[LMC_CACHE_SLOTS] = {0};
+    sc.gc.data = data.data(); sc.gc.count = count; sc.gc.ready = ready;
+    const int W = sc.cam.width, H = sc.cam.height;
+    if (threads < 1) threads = 1;
+    std::vector<ChainState<MAXD> *> cs(numChains);
+    for (int i = 0; i < numChains; i++) { cs[i] = new ChainState<MAXD>(); chain_state_init(*cs[i], initLs ? initLs[chainBase + i] : 0.0f); }
+    std::vector<std::vector<float>> films(threads);
+    for (auto &f : films) f.assign((size_t)W * H * 3, 0.0f);
+    for (long long k = 0; k < numSteps; k++) {
+        std::atomic<int> next(0);
+        auto work = [&](int w) {
+            ref_grad_hook() = (g_useRef && g_refLoaded) ? ref_gradient : nullptr;
+            HostFilm hf; hf.p = films[w].data();
+            H2mcSide *side = new H2mcSide(); memset(side, 0, sizeof(*side));
+            uint32_t tab[64];
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= numChains) break;
+                chain_run(sc, rp, chainBase + i, *cs[i], 1, tab, 1, hf, trace ? trace + (size_t)i * numSteps + k : nullptr,
+                          aTrace ? aTrace + (size_t)i * numSteps + k : nullptr, 1, side, (StagedWork<MAXD> *)nullptr);
+            }
+            delete side;
+        };
+        std::vector<std::thread> pool;
+        for (int w = 0; w < threads; w++) pool.emplace_back(work, w);
+        for (auto &t : pool) t.join();
+        cache_commit_host<MAXD>(sc, cs.data(), numChains);
+    }
+    if (film) for (int w = 0; w < threads; w++) for (size_t p = 0; p < (size_t)W * H * 3; p++) film[p] += films[w][p];
+    if (stats) {
+        for (int k = 0; k < 13; k++) stats[k] = 0;
+        for (int i = 0; i < numChains; i++) {
+            for (int k = 0; k < 4; k++) { stats[k] += cs[i]->nPropose[k]; stats[4 + k] += cs[i]->nAccept[k]; }
+            stats[8] += cs[i]->gradStats[0]; stats[9] += cs[i]->gradStats[1]; stats[10] += (unsigned long long)cs[i]->ch.outlierResets;
+            stats[11] += (unsigned long long)cs[i]->ch.cacheQueries; stats[12] += (unsigned long long)cs[i]->ch.cacheHits;
+        }
+        for (int s = 0; s < LMC_CACHE_SLOTS; s++) stats[13 + s] = (unsigned long long)count[s];
+    }
+    for (auto *p : cs) delete p;
 }
 
 template <int MAXD>
@@ -182,12 +234,19 @@ int lmco_mlt_init(void *h, long long numInitSamples, int numChains, int logicalT
     LMCO_CATCH
 }
 
-// stats[11]: nPropose[4], nAccept[4], gradEvals, gradNonFinite, outlierResets
+// stats[18]: nPropose[4], nAccept[4], gradEvals, gradNonFinite, outlierResets, cacheQueries, cacheHits, cacheCount[5]
 int lmco_run_chains(void *h, int numChains, int chainBase, int totalChains, long long numSteps,
                     long long numSamplesThisChain, float normalization, const float *initLs, float *film,
                     unsigned char *trace, float *aTrace, int threads, unsigned long long *stats) {
     LMCO_TRY
     const Scene sc = ((OScene *)h)->store.view();
+    if (sc.opt.cacheEnabled) {      // lockstep runner; H2MC has no cache (src/mutation_h2mc.h)
+        if (sc.opt.h2mc) throw std::runtime_error("globalcache applies to the MALA mutation only");
+        if (sc.opt.maxDepth <= 4) run_chains_cache_t<4>(sc, numChains, chainBase, totalChains, numSteps, numSamplesThisChain, normalization, initLs, film, trace, aTrace, threads, stats);
+        else if (sc.opt.maxDepth <= 8) run_chains_cache_t<8>(sc, numChains, chainBase, totalChains, numSteps, numSamplesThisChain, normalization, initLs, film, trace, aTrace, threads, stats);
+        else run_chains_cache_t<12>(sc, numChains, chainBase, totalChains, numSteps, numSamplesThisChain, normalization, initLs, film, trace, aTrace, threads, stats);
+        return 0;
+    }
     if (sc.opt.maxDepth <= 4) run_chains_t<4>(sc, numChains, chainBase, totalChains, numSteps, numSamplesThisChain, normalization, initLs, film, trace, aTrace, threads, stats);
     else if (sc.opt.maxDepth <= 8) run_chains_t<8>(sc, numChains, chainBase, totalChains, numSteps, numSamplesThisChain, normalization, initLs, film, trace, aTrace, threads, stats);
     else if (sc.opt.maxDepth <= 12) run_chains_t<12>(sc, numChains, chainBase, totalChains, numSteps, numSamplesThisChain, normalization, initLs, film, trace, aTrace, threads, stats);
@@ -376,6 +435,27 @@ int lmco_jacobi(int n, const float *A, float *V, float *w) {
     memcpy(tmp, A, sizeof(float) * n * n);
     jacobi_eigen(n, tmp, V, w);
     return 0;
+}
+// native image decoders probe (csrc/host/image_decode.h): returns w, h, is8 and the RGB floats
+int lmco_decode_image(const char *path, int *whi, float *rgb, long long cap) {
+    LMCO_TRY
+    lmc_host::DecodedImage im;
+    if (!lmc_host::decode_image_native(path, im)) throw std::runtime_error("no native decoder for this extension");
+    whi[0] = im.w; whi[1] = im.h; whi[2] = im.is8;
+    if (rgb && (long long)im.rgb.size() <= cap) memcpy(rgb, im.rgb.data(), im.rgb.size() * sizeof(float));
+    LMCO_CATCH
+}
+// global_cache_t::query probe: `entries` = PSS_MAX_SIZE x 3 dim floats (pss, v1, v2) of a READY slot
+int lmco_cache_query(int dim, const float *entries, const float *pss, float *v1, float *v2) {
+    const int s = cache_slot(dim);
+    if (s < 0) return -1;
+    std::vector<float> data(LMC_CACHE_FLOATS, 0.0f);
+    memcpy(data.data() + cache_slot_offset(s), entries, sizeof(float) * (size_t)LMC_CACHE_MAX_SIZE * 3 * dim);
+    int count[LMC_CACHE_SLOTS] = {0}, ready[LMC_CACHE_SLOTS] = {0};
+    count[s] = LMC_CACHE_MAX_SIZE; ready[s] = 1;
+    Scene sc; memset(&sc, 0, sizeof(sc));
+    sc.opt.cacheEnabled = 1; sc.gc.data = data.data(); sc.gc.count = count; sc.gc.ready = ready;
+    return cache_query(sc, dim, pss, v1, v2) ? 1 : 0;
 }
 int lmco_scene_serialized(void *h, float *out38) { memcpy(out38, ((OScene *)h)->store.head.sceneSer, 38 * sizeof(float)); return 0; }
 

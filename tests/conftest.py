@@ -87,7 +87,7 @@ class Oracle:
         film = np.zeros((info["height"], info["width"], 3), np.float32)
         trace = np.zeros((num_chains, steps), np.uint8) if want_trace else None
         a = np.zeros((num_chains, steps), np.float32) if want_trace else None
-        stats = np.zeros(11, np.uint64)
+        stats = np.zeros(18, np.uint64)
         spc = samples_per_chain if samples_per_chain is not None else steps
         rc = self.L.lmco_run_chains(h, num_chains, chain_base, total, ctypes.c_longlong(steps), ctypes.c_longlong(spc),
                                     ctypes.c_float(norm), self.p(init_ls), self.p(film), self.p(trace), self.p(a),

@@ -2,9 +2,12 @@
 closest-hit with the same Moeller-Trumbore leaf test returns (oracle-defined semantics,
 SURVEY.md s8c: Embree's own tie-breaking is unpinned)."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
+
+from conftest import SCENES
 
 
 def make_rays(n, seed, center, radius):
@@ -76,3 +79,47 @@ def test_cuda_bvh_probe_matches_oracle(lmc, oracle, torus_xml, door_xml, scene):
     assert np.array_equal(occ.astype(bool), hit)
     empty_tid, _, _ = ctx.bvh_probe(np.zeros((0, 6), np.float32), 0.0, 1.0)
     assert empty_tid.shape == (0,)
+
+
+def _read_rawf(path):
+    with open(path, "rb") as f:
+        assert f.read(4) == b"RAWF"
+        w, h, is8 = np.frombuffer(f.read(12), "<i4")
+        if is8:
+            rgb = np.frombuffer(f.read(), np.uint8).astype(np.float32) / np.float32(255.0)
+        else:
+            rgb = np.frombuffer(f.read(), "<f4")
+    return int(w), int(h), int(is8), rgb
+
+
+@pytest.mark.parametrize("name", ["checker.png", "sunsky.exr"])
+def test_native_image_decoders_match_staged_rawf(oracle, name):
+    """The loader's own PNG / OpenEXR decoders (csrc/host/image_decode.h, what the reference gets from OpenImageIO,
+    src/image.cpp:5-45, src/bitmaptexture.h:73-146) give the bits tools/stage_scenes.py decoded with OpenCV."""
+    import ctypes
+    path = os.path.join(SCENES, "torus", "data", name)
+    w, h, is8, ref = _read_rawf(path + ".rawf")
+    whi = np.zeros(3, np.int32)
+    out = np.zeros(w * h * 3, np.float32)
+    oracle.L.lmco_decode_image.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong]
+    assert oracle.L.lmco_decode_image(path.encode(), oracle.p(whi), oracle.p(out), out.size) == 0
+    assert (int(whi[0]), int(whi[1]), int(whi[2])) == (w, h, is8)
+    assert np.array_equal(out.view(np.uint32), np.ascontiguousarray(ref).view(np.uint32))
+
+
+def test_scene_loads_without_rawf_containers(oracle, tmp_path):
+    """lmc_scene_load on a directory that holds only the reference's own files (no .rawf): same serialized scene,
+    same first mutations."""
+    import shutil
+    dst = tmp_path / "torus"
+    shutil.copytree(os.path.join(SCENES, "torus"), dst, ignore=shutil.ignore_patterns("*.rawf"))
+    h0 = oracle.load(os.path.join(SCENES, "torus", "lmc.xml"))
+    h1 = oracle.load(str(dst / "lmc.xml"))
+    for h in (h0, h1):
+        oracle.set_option(h, "maxdepth", 4)
+    n0, l0 = oracle.mlt_init(h0, 20000, 256, 8)
+    n1, l1 = oracle.mlt_init(h1, 20000, 256, 8)
+    assert n0 == n1 and np.array_equal(l0, l1)
+    r0 = oracle.run_chains(h0, 256, 12, n0, l0, samples_per_chain=12)
+    r1 = oracle.run_chains(h1, 256, 12, n1, l1, samples_per_chain=12)
+    assert np.array_equal(r0[1], r1[1]) and np.array_equal(r0[0], r1[0])

@@ -51,6 +51,8 @@ for scene in ("torus", "veachdoor"):
         ext = fn.rsplit(".", 1)[-1].lower()
         if ext in ("exr", "png", "jpg", "jpeg"):
             write_rawf(src, os.path.join(odir, "data", fn + ".rawf"))
+            if ext in ("exr", "png"):     # lossless formats are also decoded by the loader itself (csrc/host/image_decode.h)
+                shutil.copyfile(src, os.path.join(odir, "data", fn))
         else:
             shutil.copyfile(src, os.path.join(odir, "data", fn))
     print("staged", scene)
