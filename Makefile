@@ -27,7 +27,7 @@ oracle/liblmc_oracle_fast.so: oracle/oracle_api.cpp $(PKG)/csrc/host/host_scene.
 CUDA_SRC := $(PKG)/csrc/cuda
 CUDA_OBJ := $(PKG)/build/lmc_abi.o $(PKG)/build/chain_inst_4.o $(PKG)/build/chain_inst_8.o $(PKG)/build/chain_inst_12.o
 lib: $(PKG)/liblmc_b200.so
-$(PKG)/build/%.o: $(CUDA_SRC)/%.cu $(CORE_H) $(CORE_INC) $(CUDA_SRC)/chain_kernels.cuh $(CUDA_SRC)/trace_kernels.cuh include/lmc/lmc_abi.h
+$(PKG)/build/%.o: $(CUDA_SRC)/%.cu $(CORE_H) $(CORE_INC) $(wildcard $(CUDA_SRC)/*.cuh) $(wildcard $(CUDA_SRC)/*.h) include/lmc/lmc_abi.h
 	@mkdir -p $(PKG)/build
 	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $(PKG)/build/$*.ptxas.log || (cat $(PKG)/build/$*.ptxas.log; false)
 $(PKG)/build/host_scene.o: $(PKG)/csrc/host/host_scene.cpp $(CORE_H)

@@ -165,56 +165,118 @@ struct H2mcSide {
     int dense[2];                                      // slot holds a dense Gaussian (else the diagonal fields are used)
 };
 
-// Cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major, destroyed).
-// Replaces Eigen::SelfAdjointEigenSolver (src/h2mc.cpp:9-10; Eigen is not vendored: parity
-// unpinned, the convention below is the oracle's): eigenvalues ascending, eigenvectors = columns
-// of V, each normalised so that its first non-zero component is positive.
+// Jacobi eigen-decomposition of a symmetric n x n matrix (n even, <= 16; row-major with row stride `ld`, destroyed).
+// Replaces Eigen::SelfAdjointEigenSolver (src/h2mc.cpp:9-10; Eigen is not vendored: parity unpinned, the convention
+// below is the oracle's): eigenvalues ascending, eigenvectors = columns of V, each normalised so that its first
+// non-zero component is positive.
+//
+// The rotation order is the PARALLEL one (round-robin tournament): a sweep is n - 1 rounds, round r rotates the n / 2
+// disjoint index pairs jacobi_pair(n, r, 0 .. n/2-1) at once -- all angles are taken from the matrix as it enters the
+// round, then every pair's column rotation is applied, then every pair's row rotation (A <- J^T (A J), J the product
+// of the round's commuting rotations).  This is the statement list both forms follow: the serial one below (host
+// twin / oracle, small jobs) and the warp-cooperative one of csrc/cuda/h2mc_kernels.cuh, where 16 lanes share a
+// matrix held in shared memory and the sums below are shuffle trees.  Sums over 16 lanes are defined as the xor
+// butterfly tree16(): level by level x[l] += x[l ^ 8], ^ 4, ^ 2, ^ 1 (lanes beyond the data hold 0).
+LMC_HD float tree16(float *x) {
+    for (int off = 8; off > 0; off >>= 1) {
+        float y[16];
+        for (int l = 0; l < 16; l++) y[l] = x[l] + x[l ^ off];
+        for (int l = 0; l < 16; l++) x[l] = y[l];
+    }
+    return x[0];
+}
+// pair i (0 <= i < n / 2) of round r (0 <= r < n - 1), p < q: circle method with n - 1 fixed
+LMC_HD void jacobi_pair(int n, int r, int i, int &p, int &q) {
+    const int m = n - 1;
+    int a, b;
+    if (i == 0) { a = m; b = r; }
+    else { a = (r + i) % m; b = (r + m - i) % m; }
+    p = a < b ? a : b; q = a < b ? b : a;
+}
+// rotation that annihilates A[p][q]; returns false when there is nothing to rotate
+LMC_HD bool jacobi_angle(float app, float aqq, float apq, float &c, float &sn) {
+    if (apq == 0.0f) { c = 1.0f; sn = 0.0f; return false; }
+    const float theta = (aqq - app) / (2.0f * apq);
+    const float t = ((theta >= 0.0f) ? 1.0f : -1.0f) / (dm_abs(theta) + dm_sqrt(theta * theta + 1.0f));
+    c = 1.0f / dm_sqrt(t * t + 1.0f);
+    sn = t * c;
+    return true;
+}
+#define LMC_JACOBI_SWEEPS 16
+LMC_HD bool jacobi_converged(float off, float diag) { return off <= 1e-14f * (diag + off) || off == 0.0f; }
+
 LMC_HD_NOINLINE void jacobi_eigen(int n, float *A, float *V, float *w) {
     for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = (i == j) ? 1.0f : 0.0f;
-    for (int sweep = 0; sweep < 16; sweep++) {
-        float off = 0.0f, diag = 0.0f;
-        for (int p = 0; p < n; p++) { diag += A[p * n + p] * A[p * n + p]; for (int q = p + 1; q < n; q++) off += A[p * n + q] * A[p * n + q]; }
-        if (off <= 1e-14f * (diag + off) || off == 0.0f) break;
-        for (int p = 0; p < n - 1; p++) {
-            for (int q = p + 1; q < n; q++) {
-                const float apq = A[p * n + q];
-                if (apq == 0.0f) continue;
-                const float theta = (A[q * n + q] - A[p * n + p]) / (2.0f * apq);
-                const float t = ((theta >= 0.0f) ? 1.0f : -1.0f) / (dm_abs(theta) + dm_sqrt(theta * theta + 1.0f));
-                const float c = 1.0f / dm_sqrt(t * t + 1.0f);
-                const float sn = t * c;
-                for (int k = 0; k < n; k++) {      // columns p, q
+    const int ne = n + (n & 1);                  // an odd n plays with a phantom index whose pairs sit out (the chains only have even n)
+    for (int sweep = 0; sweep < LMC_JACOBI_SWEEPS; sweep++) {
+        float offp[16], diagp[16];
+        for (int l = 0; l < 16; l++) {           // lane l = row l
+            offp[l] = 0.0f; diagp[l] = 0.0f;
+            if (l < n) { diagp[l] = A[l * n + l] * A[l * n + l]; for (int q = l + 1; q < n; q++) offp[l] += A[l * n + q] * A[l * n + q]; }
+        }
+        const float off = tree16(offp), diag = tree16(diagp);
+        if (jacobi_converged(off, diag)) break;
+        for (int r = 0; r < ne - 1; r++) {
+            int P[8], Q[8]; float C[8], S[8]; bool rot[8];
+            for (int i = 0; i < ne / 2; i++) {
+                jacobi_pair(ne, r, i, P[i], Q[i]);
+                rot[i] = Q[i] < n && jacobi_angle(A[P[i] * n + P[i]], A[Q[i] * n + Q[i]], A[P[i] * n + Q[i]], C[i], S[i]);
+            }
+            for (int i = 0; i < ne / 2; i++) {
+                if (!rot[i]) continue;
+                const int p = P[i], q = Q[i]; const float c = C[i], sn = S[i];
+                for (int k = 0; k < n; k++) {      // columns p, q of A and of V
                     const float akp = A[k * n + p], akq = A[k * n + q];
                     A[k * n + p] = c * akp - sn * akq;
                     A[k * n + q] = sn * akp + c * akq;
-                }
-                for (int k = 0; k < n; k++) {      // rows p, q
-                    const float apk = A[p * n + k], aqk = A[q * n + k];
-                    A[p * n + k] = c * apk - sn * aqk;
-                    A[q * n + k] = sn * apk + c * aqk;
-                }
-                for (int k = 0; k < n; k++) {
                     const float vkp = V[k * n + p], vkq = V[k * n + q];
                     V[k * n + p] = c * vkp - sn * vkq;
                     V[k * n + q] = sn * vkp + c * vkq;
                 }
             }
+            for (int i = 0; i < ne / 2; i++) {
+                if (!rot[i]) continue;
+                const int p = P[i], q = Q[i]; const float c = C[i], sn = S[i];
+                for (int k = 0; k < n; k++) {      // rows p, q
+                    const float apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = c * apk - sn * aqk;
+                    A[q * n + k] = sn * apk + c * aqk;
+                }
+            }
         }
     }
-    for (int i = 0; i < n; i++) w[i] = A[i * n + i];
-    for (int i = 0; i < n - 1; i++) {              // ascending selection sort, columns follow
-        int m = i;
-        for (int j = i + 1; j < n; j++) if (w[j] < w[m]) m = j;
-        if (m != i) {
-            const float tw = w[i]; w[i] = w[m]; w[m] = tw;
-            for (int k = 0; k < n; k++) { const float tv = V[k * n + i]; V[k * n + i] = V[k * n + m]; V[k * n + m] = tv; }
-        }
+    // ascending by rank (ties keep index order), columns follow; A's storage receives the sorted vectors
+    float d[16];
+    for (int i = 0; i < n; i++) d[i] = A[i * n + i];
+    for (int i = 0; i < n; i++) {
+        int rank = 0;
+        for (int j = 0; j < n; j++) if (d[j] < d[i] || (d[j] == d[i] && j < i)) rank++;
+        w[rank] = d[i];
+        for (int k = 0; k < n; k++) A[k * n + rank] = V[k * n + i];
     }
     for (int j = 0; j < n; j++) {
         float lead = 0.0f;
-        for (int k = 0; k < n; k++) if (V[k * n + j] != 0.0f) { lead = V[k * n + j]; break; }
-        if (lead < 0.0f) for (int k = 0; k < n; k++) V[k * n + j] = -V[k * n + j];
+        for (int k = 0; k < n; k++) if (A[k * n + j] != 0.0f) { lead = A[k * n + j]; break; }
+        for (int k = 0; k < n; k++) V[k * n + j] = (lead < 0.0f) ? -A[k * n + j] : A[k * n + j];
     }
+}
+
+// per eigen-direction part of ComputeGaussian (src/h2mc.cpp:88-118): `vtg` = (eigenvector . gradient)
+LMC_HD void h2mc_eigen_scale(const Options &opt, float invSigmaSq, float w, float vtg, float &eigenBuff, float &offsetBuff, float &post) {
+    float e = (dm_abs(w) > 1e-10f) ? 1.0f / dm_abs(w) : 0.0f;
+    const float ob = e * vtg;
+    float s2 = 1.0f, o = 0.0f;
+    if (dm_abs(w) > 1e-10f) {
+        o = ob;
+        if (w > 0.0f) { s2 = opt.h2mcPosScale; o *= opt.h2mcPosOffset; }
+        else { s2 = opt.h2mcNegScale; o *= opt.h2mcNegOffset; }
+    } else {
+        s2 = opt.h2mcL * opt.h2mcL;
+        o = 0.5f * ob * opt.h2mcL * opt.h2mcL;
+    }
+    e *= s2;
+    e = (e > 1e-10f) ? 1.0f / e : 0.0f;
+    eigenBuff = e; offsetBuff = o; post = e + invSigmaSq;
 }
 
 // ComputeGaussian(h2mcParam, sc, vGrad, vHess, gaussian)  (src/h2mc.cpp:70-142 and :3-68).
@@ -225,9 +287,9 @@ LMC_HD_NOINLINE int h2mc_compute_gaussian(const Options &opt, float sc, int dim,
     const float sigma = opt.perturbStdDev;
     const float invSigmaSq = 1.0f / (sigma * sigma);
     g.dim = dim;
-    float frob = 0.0f;
-    for (int i = 0; i < dim * dim; i++) frob += hess[i] * hess[i];
-    frob = dm_sqrt(frob);
+    float fp[16];                // Frobenius norm: lane l of 16 sums the entries l, l + 16, ..., then the tree
+    for (int l = 0; l < 16; l++) { fp[l] = 0.0f; for (int i = l; i < dim * dim; i += 16) fp[l] += hess[i] * hess[i]; }
+    const float frob = dm_sqrt(tree16(fp));
     if (sc <= 1e-15f || frob < 0.5f / (sigma * sigma)) {
         for (int i = 0; i < dim; i++) { g.mean[i] = 0.0f; g.covL_d[i] = sigma; g.invCov_d[i] = invSigmaSq; }
         g.logDet = 0.0f;
@@ -238,27 +300,11 @@ LMC_HD_NOINLINE int h2mc_compute_gaussian(const Options &opt, float sc, int dim,
     // SelfAdjointEigenSolver reads the lower triangle of the column-major map H(r, c) = vHess[c * dim + r]
     for (int r = 0; r < dim; r++) for (int c = 0; c < r; c++) hess[c * dim + r] = hess[r * dim + c];
     jacobi_eigen(dim, hess, V, w);
-    for (int i = 0; i < dim; i++) eigenBuff[i] = (dm_abs(w[i]) > 1e-10f) ? 1.0f / dm_abs(w[i]) : 0.0f;
     for (int i = 0; i < dim; i++) {
         float vtg = 0.0f;
         for (int k = 0; k < dim; k++) vtg += V[k * dim + i] * grad[k];
-        offsetBuff[i] = eigenBuff[i] * vtg;
+        h2mc_eigen_scale(opt, invSigmaSq, w[i], vtg, eigenBuff[i], offsetBuff[i], post[i]);
     }
-    for (int i = 0; i < dim; i++) {
-        float s2 = 1.0f, o = 0.0f;
-        if (dm_abs(w[i]) > 1e-10f) {
-            o = offsetBuff[i];
-            if (w[i] > 0.0f) { s2 = opt.h2mcPosScale; o *= opt.h2mcPosOffset; }
-            else { s2 = opt.h2mcNegScale; o *= opt.h2mcNegOffset; }
-        } else {
-            s2 = opt.h2mcL * opt.h2mcL;
-            o = 0.5f * offsetBuff[i] * opt.h2mcL * opt.h2mcL;
-        }
-        eigenBuff[i] *= s2;
-        eigenBuff[i] = (eigenBuff[i] > 1e-10f) ? 1.0f / eigenBuff[i] : 0.0f;
-        offsetBuff[i] = o;
-    }
-    for (int i = 0; i < dim; i++) post[i] = eigenBuff[i] + invSigmaSq;
     for (int r = 0; r < dim; r++) {
         for (int c = 0; c < dim; c++) {
             float acc = 0.0f;
@@ -315,9 +361,13 @@ LMC_HD int h2mc_grad_mode(const Scene &sc, const MarkovState<MAXD> &st) {
 
 // initGaussian(state) of H2MCSmallStep::Mutate
 template <int MAXD>
-LMC_HD void h2mc_init_gaussian(const Scene &sc, MarkovState<MAXD> &st, int slot, int mode, const float *grad, H2mcSide *side) {
+LMC_HD void h2mc_init_gaussian(const Scene &sc, MarkovState<MAXD> &st, int slot, int mode, const float *grad, H2mcSide *side,
+                               bool built = false) {
     const int dim = path_dimension(st.path);
-    if (mode == 0) {
+    if (built) {
+        // the device's cooperative kernel (k_h2mc_gaussian) has already turned this state's gradient + Hessian into
+        // its Gaussian -- same statements as h2mc_compute_gaussian, 16 lanes per matrix
+    } else if (mode == 0) {
         isotropic_gaussian(dim, sc.opt.perturbStdDev, st.gaussian);
         side->dense[slot] = 0;
     } else {
@@ -334,6 +384,7 @@ struct StepScratch {
     int kind;            // StepKind of the iteration in flight
     int needCurGrad;     // gradient of the CURRENT state wanted before the proposal (MALA, lazily)
     int needPropGrad;    // gradient of the PROPOSAL wanted before the acceptance test (MALA)
+                         // (both: 2 = evaluated AND the H2MC Gaussian built from it, device only: k_h2mc_gaussian)
     int hasContrib;      // the proposal produced a contribution
     float a;             // acceptance probability (final after phase_finish)
     float offset[Limits<MAXD>::DIM];
@@ -577,7 +628,7 @@ LMC_HD void propose_pre_small(const Scene &sc, MarkovState<MAXD> &cur, MarkovSta
     }
     if (ss.kind == STEP_H2MC) {
         ch.lastMutationType = MUT_H2MC_SMALL;
-        if (!cur.gaussianInitialized) h2mc_init_gaussian(sc, cur, curSlot, h2mc_grad_mode(sc, cur), ss.grad, side);
+        if (!cur.gaussianInitialized) h2mc_init_gaussian(sc, cur, curSlot, h2mc_grad_mode(sc, cur), ss.grad, side, ss.needCurGrad == 2);
         if (side->dense[curSlot]) generate_sample_dense(cur.gaussian, side->covL[curSlot], ss.offset, rng);
         else generate_sample(cur.gaussian, ss.offset, rng);
         if (COPY_PATH) path_copy(prop.path, cur.path);
@@ -706,7 +757,7 @@ LMC_HD StepInfo phase_finish(const Scene &sc, const RunParams &rp, int chainId, 
     MarkovState<MAXD> &prop = states[curIdx ^ 1];
     if (ss.kind == STEP_H2MC && ss.hasContrib) {
         const int cs_ = curIdx, ps_ = curIdx ^ 1;
-        h2mc_init_gaussian(sc, prop, ps_, h2mc_grad_mode(sc, prop), ss.grad, side);
+        h2mc_init_gaussian(sc, prop, ps_, h2mc_grad_mode(sc, prop), ss.grad, side, ss.needPropGrad == 2);
         const float py = side->dense[cs_] ? gaussian_log_pdf_dense(ss.offset, 1.0f, cur.gaussian, side->invCov[cs_])
                                           : gaussian_log_pdf(ss.offset, 1.0f, cur.gaussian);
         const float px = side->dense[ps_] ? gaussian_log_pdf_dense(ss.offset, -1.0f, prop.gaussian, side->invCov[ps_])

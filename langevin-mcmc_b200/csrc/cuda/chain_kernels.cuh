@@ -222,6 +222,10 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_begin(const __grid_con
     list_append(wl.large, wl.largeCount, active && kind == STEP_LARGE, i);
 }
 
+}  // namespace lmc_cuda
+#include "h2mc_kernels.cuh"
+namespace lmc_cuda {
+
 // gradient of the current state (which = 0) or of the proposal (which = 1) for a sorted list
 // occupancy of the gradient kernel in units of 128 threads per SM.  The reverse-sweep evaluator is bound by the
 // latency of its local-memory traffic (checkpoints, spills): 4 (two 256-thread blocks, 128 registers) measured
@@ -1010,6 +1014,8 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
     const bool useWavefront = wc.wavefront < 0 ? (n >= LMC_WAVEFRONT_MIN_CHAINS) : (wc.wavefront != 0);
     const int GALIGN = LMC_GRAD_BLOCK;          // gradient lists: class-pure blocks
     const int GG = (n + LMC_NKEYS * (GALIGN - 1) + LMC_GRAD_BLOCK - 1) / LMC_GRAD_BLOCK;   // gradient grid over the (padded) list
+    const int GHmax = (n + LMC_NKEYS * (GALIGN - 1)) / (LMC_H2MC_BLOCK / 16) + 1;
+    const int GH = GHmax < sms * 8 ? GHmax : sms * 8;                                   // H2MC Gaussians: 16 lanes per list entry, grid-stride
     cudaError_t e = cudaMemsetAsync(wl.largeCount, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     k_wave_begin<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl);
@@ -1024,8 +1030,11 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             if (e != cudaSuccess) return e;
         }
         k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.small_, wl.curGrad, 2);
-        if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide);
-        else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide);
+        if (sc.opt.h2mc) {
+            k_wave_grad<MAXD, 2><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide);
+            k_h2mc_gaussian<MAXD><<<GH, LMC_H2MC_BLOCK, 0, st>>>(sc, states, wl.curGrad.list, wl.curGrad.count, 0, sides);
+            *launches += 1;
+        } else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide);
         *launches += 3;
         pt.mark("sort + grad(cur)");
         if (!useWavefront) {
@@ -1098,8 +1107,11 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             if (e != cudaSuccess) return e;
         }
         k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.propGrad, wl.propGrad, 1);
-        if (sc.opt.h2mc) k_wave_grad<MAXD, 2><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide);
-        else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide);
+        if (sc.opt.h2mc) {
+            k_wave_grad<MAXD, 2><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide);
+            k_h2mc_gaussian<MAXD><<<GH, LMC_H2MC_BLOCK, 0, st>>>(sc, states, wl.propGrad.list, wl.propGrad.count, 1, sides);
+            *launches += 1;
+        } else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide);
         pt.mark("sort + grad(prop)");
         // the large-step list of this iteration is consumed: refill it for the next one in the fused finish + begin
         e = cudaMemsetAsync(wl.largeCount, 0, sizeof(int), st);

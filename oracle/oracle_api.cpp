@@ -424,7 +424,7 @@ int lmco_eval_batch_hess(void *h, int camDepth, int lightDepth, int n, const flo
     const int dim = primary_param_size(camDepth, lightDepth) - 1;
     if (dim > LMC_HESS_MAXDIM) return -1;
     for (int i = 0; i < n; i++)
-        logLum[i] = (st.head.opt.adjointCompat == 3 ? path_loglum_hess_rev : path_loglum_hess)(camDepth, lightDepth, sceneSer, primary + (size_t)i * primaryStride,
+        logLum[i] = (st.head.opt.adjointCompat == 3 ? path_loglum_hess_rev<4> : path_loglum_hess)(camDepth, lightDepth, sceneSer, primary + (size_t)i * primaryStride,
                                      vertParams + (size_t)i * vertStride, grad + (size_t)i * dim, hess + (size_t)i * dim * dim);
     return 0;
 }
