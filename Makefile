@@ -25,7 +25,8 @@ oracle/liblmc_oracle_fast.so: oracle/oracle_api.cpp $(PKG)/csrc/host/host_scene.
 	$(CXX) -Ofast -march=$(FAST_ARCH) -std=c++17 -fPIC -pthread -DLMC_TIMING_LIBM -w -shared -o $@ oracle/oracle_api.cpp $(PKG)/csrc/host/host_scene.cpp -lz -ldl
 
 CUDA_SRC := $(PKG)/csrc/cuda
-CUDA_OBJ := $(PKG)/build/lmc_abi.o $(PKG)/build/chain_inst_4.o $(PKG)/build/chain_inst_8.o $(PKG)/build/chain_inst_12.o
+CUDA_OBJ := $(PKG)/build/lmc_abi.o $(PKG)/build/chain_hess_12.o $(PKG)/build/chain_hess_8.o $(PKG)/build/chain_hess_4.o \
+            $(PKG)/build/chain_inst_12.o $(PKG)/build/chain_inst_8.o $(PKG)/build/chain_inst_4.o
 lib: $(PKG)/liblmc_b200.so
 $(PKG)/build/%.o: $(CUDA_SRC)/%.cu $(CORE_H) $(CORE_INC) $(wildcard $(CUDA_SRC)/*.cuh) $(wildcard $(CUDA_SRC)/*.h) include/lmc/lmc_abi.h
 	@mkdir -p $(PKG)/build

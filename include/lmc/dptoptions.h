@@ -28,7 +28,7 @@ struct DptOptions {
     Float malaGN = Float(100.0);                     // MALA truncated gradient magnitude
     Float malaStepsize = Float(0.005);               // MALA stepsize
     Float malaStdDev = Float(0.005);                 // MALA shrink prior to prevent noisy gradient issue
-    bool sampleFromGlobalCache = false;              // (not supported: rejected at load time)
+    bool sampleFromGlobalCache = false;              // LargeStepCache, src/mutation_large_cache.h (not supported: rejected at load time)
 
     int numChains = 128;
     int seedOffset = 0;
@@ -39,6 +39,8 @@ struct DptOptions {
     bool largeStepMultiplexed = false;               // (not supported: rejected at create time)
 
     // compile-time constants of the reference, run-time options here (same defaults)
+    bool globalCache = false;                        // src/global_cache.h: always on in the reference (timing-dependent fill); here an
+                                                     // option with a defined fill order, off = every MALA step evaluates its gradient
     int adjointCompat = 1;                           // 1: the reference's reverse sweep (src/chad.cpp:284-287); 0 / 2: true gradient
     int maxDervDepth = 8;                            // src/main.cpp:46
     int pssMinLength = 2, pssMaxLength = 12;         // PSS_MIN_LENGTH / PSS_MAX_LENGTH, src/global_cache.h:8-9
@@ -59,6 +61,7 @@ struct DptOptions {
             {"uniformmixprob", uniformMixingProbability},
             {"uselightcoordinatesampling", useLightCoordinateSampling ? 1.0 : 0.0},
             {"largestepmultiplexed", largeStepMultiplexed ? 1.0 : 0.0},
+            {"globalcache", globalCache ? 1.0 : 0.0},
             {"adjointcompat", (double)adjointCompat}, {"maxdervdepth", (double)maxDervDepth},
             {"pssminlength", (double)pssMinLength}, {"pssmaxlength", (double)pssMaxLength},
             {"outlierweakrejectcnt", (double)outlierWeakRejectCnt}, {"outlierstrongrejectcnt", (double)outlierStrongRejectCnt},
@@ -81,6 +84,7 @@ struct DptOptions {
         discreteStdDev = (Float)get("discretestddev", 0.01); uniformMixingProbability = (Float)get("uniformmixprob", 0.1);
         useLightCoordinateSampling = get("uselightcoordinatesampling", 0) != 0;
         largeStepMultiplexed = get("largestepmultiplexed", 0) != 0;
+        globalCache = get("globalcache", 0) != 0;
         adjointCompat = (int)get("adjointcompat", 1); maxDervDepth = (int)get("maxdervdepth", 8);
         pssMinLength = (int)get("pssminlength", 2); pssMaxLength = (int)get("pssmaxlength", 12);
         outlierWeakRejectCnt = (int)get("outlierweakrejectcnt", 10000); outlierStrongRejectCnt = (int)get("outlierstrongrejectcnt", 1000);

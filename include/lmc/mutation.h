@@ -42,7 +42,7 @@ struct MutationRecord {
 // ChainVars) and never crosses the ABI; this struct documents the correspondence for readers of the reference:
 //   Chain::v1, v2, curr_new_*, prop_new_*   ChainVars::v1, v2, curr_new_v1/2, prop_new_v1/2   (2 * maxDepth floats each)
 //   Chain::buffered, t                      ChainVars::buffered, t
-//   Chain::pss, last_pss, M, g, queried, globalCache      only used by the global cache (not built)
+//   Chain::pss, last_pss, queried           ChainVars::pss, last_pss, queried: the global cache (DptOptions::globalCache)
 struct Chain {
     int chainId = 0;
     int t = 0;

@@ -61,9 +61,12 @@ LMC_HD BsdfParams bsdf_params(const Scene &sc, int geom, V2 st) {
     BsdfParams p;
     p.type = m.type; p.twoSided = m.twoSided;
     p.Kd = (m.type == BSDF_ROUGHDIELECTRIC) ? mk3s(0.0f) : mat_kd(sc, m, st);
-    p.Ks = ld3(m.Ks); p.Kt = ld3(m.Kt);
-    p.exponent = m.exponent; p.KsWeight = m.KsWeight;
-    p.eta = m.eta; p.invEta = m.invEta; p.alpha = m.alpha;
+    p.Ks = (m.ksTex >= 0) ? texture_eval(sc, m.ksTex, st) : ld3(m.Ks);
+    p.Kt = (m.ktTex >= 0) ? texture_eval(sc, m.ktTex, st) : ld3(m.Kt);
+    p.exponent = (m.expTex >= 0) ? texture_eval(sc, m.expTex, st).x : m.exponent;
+    p.KsWeight = m.KsWeight;
+    p.eta = m.eta; p.invEta = m.invEta;
+    p.alpha = (m.alphaTex >= 0) ? texture_eval(sc, m.alphaTex, st).x : m.alpha;
     return p;
 }
 

@@ -964,6 +964,13 @@ LMC_HD_NOINLINE float path_loglum_grad(int camDepth, int lightDepth, const float
 // the symmetric matrix.  Replaces the forward-over-reverse code `evaluate_path_bidir_<c>_<l>_static_derv`
 // (src/chad.cpp:333-545); hess is row-major D x D (hess[i * D + j] = d2 f / dx_i dx_j, symmetric).
 #define LMC_HESS_CHUNK 2
+// Which Hessian the H2MC mutation runs: > 0 = forward-over-reverse (pathgrad_rev.h path_loglum_hess_rev) with that many
+// directions per reverse sweep, 0 = the second-order forward evaluator below.  Measured on B200 (torus, maxdepth 8,
+// 2^20 chains, Hessian kernels per iteration): second-order forward 62 ms, forward-over-reverse 1 direction 30 ms,
+// 2 directions 24 ms (ptxas: 75 s / 153 s for the kernel).
+#ifndef LMC_HESS_REV_CHUNK
+#define LMC_HESS_REV_CHUNK 2
+#endif
 #define LMC_HESS_MAXDIM 16
 // seeds of one second-order sweep: outer directions ba.., inner directions bb..
 struct HessSeed {

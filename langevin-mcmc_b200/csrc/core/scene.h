@@ -49,6 +49,10 @@ struct Material {
     int hasST;         // mesh has texture coordinates (else st = barycentric uv)
     float invTotalArea;
     int firstTid;      // not used by traversal; kept for diagnostics
+    // bitmap-textured parameters (src/parsescene.cpp:341-412 Parse3DMap / Parse1DMap), -1 = the constant above:
+    // Phong specularReflectance / exponent, RoughDielectric specularReflectance / specularTransmittance / alpha.
+    // One-channel maps read the texture's first channel (BitmapTexture<1>, src/bitmaptexture.h:73-97).
+    int ksTex, ktTex, expTex, alphaTex;
 };
 
 struct Texture {

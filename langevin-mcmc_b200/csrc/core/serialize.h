@@ -213,7 +213,7 @@ LMC_HD_NOINLINE void path_hessian(const Scene &sc, const Path<MAXD> &path, float
         return;
     }
     serialize_path<MAXD, true>(sc, path, primary, vertParams);
-#if defined(LMC_HESS_REV_CHUNK)
+#if LMC_HESS_REV_CHUNK > 0
     path_loglum_hess_rev<LMC_HESS_REV_CHUNK>(path.camDepth, path.lgtDepth, sc.sceneSer, primary, vertParams, grad, hess);
 #else
     path_loglum_hess(path.camDepth, path.lgtDepth, sc.sceneSer, primary, vertParams, grad, hess);

@@ -1,0 +1,4 @@
+// chain_hess_4.cu -- the H2MC kernels for maxdepth <= 4: k_wave_grad<4, 2> (gradient + Hessian, forward-over-reverse)
+// and k_h2mc_gaussian<4> (warp-cooperative ComputeGaussian), see chain_kernels.cuh LMC_INSTANTIATE_HESS.
+#include "chain_kernels.cuh"
+namespace lmc_cuda { LMC_INSTANTIATE_HESS(4) }

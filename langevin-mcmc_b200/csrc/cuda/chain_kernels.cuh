@@ -994,6 +994,23 @@ struct PhaseTimer {
     }
 };
 
+// H2MC: Hessian kernel (k_wave_grad<MAXD, 2>) + cooperative Gaussian kernel over one gradient list.  Defined in
+// chain_hess_<MAXD>.cu (LMC_INSTANTIATE_HESS): the dual-number reverse sweep is the longest ptxas job of the library, so it
+// gets translation units of its own that build next to chain_inst_<MAXD>.cu.
+template <int MAXD>
+cudaError_t launch_wave_hess(cudaStream_t st, const Scene &sc, ChainRec<MAXD> *states, int n, const int *list, const int *count,
+                             int which, H2mcSide *sides, H2mcSide *padSide, int GG, int GH);
+template <> cudaError_t launch_wave_hess<4>(cudaStream_t, const Scene &, ChainRec<4> *, int, const int *, const int *, int, H2mcSide *, H2mcSide *, int, int);
+template <> cudaError_t launch_wave_hess<8>(cudaStream_t, const Scene &, ChainRec<8> *, int, const int *, const int *, int, H2mcSide *, H2mcSide *, int, int);
+template <> cudaError_t launch_wave_hess<12>(cudaStream_t, const Scene &, ChainRec<12> *, int, const int *, const int *, int, H2mcSide *, H2mcSide *, int, int);
+#define LMC_INSTANTIATE_HESS(MAXD) \
+    template <> cudaError_t launch_wave_hess<MAXD>(cudaStream_t st, const Scene &sc, ChainRec<MAXD> *states, int n, const int *list, \
+                                                   const int *count, int which, H2mcSide *sides, H2mcSide *padSide, int GG, int GH) { \
+        k_wave_grad<MAXD, 2><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, list, count, which, sides, padSide); \
+        k_h2mc_gaussian<MAXD><<<GH, LMC_H2MC_BLOCK, 0, st>>>(sc, states, list, count, which, sides); \
+        return cudaGetLastError(); \
+    }
+
 // One iteration of the chain loop for all chains = the launch sequence below.
 template <int MAXD>
 cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams &rp, int chainBase, void *states_,
@@ -1031,8 +1048,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         }
         k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.small_, wl.curGrad, 2);
         if (sc.opt.h2mc) {
-            k_wave_grad<MAXD, 2><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide);
-            k_h2mc_gaussian<MAXD><<<GH, LMC_H2MC_BLOCK, 0, st>>>(sc, states, wl.curGrad.list, wl.curGrad.count, 0, sides);
+            launch_wave_hess<MAXD>(st, sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide, GG, GH);
             *launches += 1;
         } else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide);
         *launches += 3;
@@ -1108,8 +1124,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         }
         k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.propGrad, wl.propGrad, 1);
         if (sc.opt.h2mc) {
-            k_wave_grad<MAXD, 2><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide);
-            k_h2mc_gaussian<MAXD><<<GH, LMC_H2MC_BLOCK, 0, st>>>(sc, states, wl.propGrad.list, wl.propGrad.count, 1, sides);
+            launch_wave_hess<MAXD>(st, sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide, GG, GH);
             *launches += 1;
         } else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide);
         pt.mark("sort + grad(prop)");

@@ -598,9 +598,11 @@ bool get_option(const Options &o, const std::string &name, double &value) {
     return false;
 }
 
+struct MatTex { std::string file; float s = 1, t = 1; };    // a bitmap-textured parameter (empty file = constant)
 struct MatDesc {
     Material m;
     std::string kdTexFile; float sScale = 1, tScale = 1;   // Kd bitmap, if any
+    MatTex ks, kt, exponent, alpha;
 };
 
 struct Loader {
@@ -662,10 +664,21 @@ struct Loader {
             constant[0] = v.x; constant[1] = v.y; constant[2] = v.z;
         }
     }
+    // Parse1DMap: a float constant or a bitmap whose first channel is used
+    void parse_1d_map(const XmlNode &n, float &constant, MatTex &mt) {
+        float dummy[3]; bool isTex; TexDesc tex;
+        if (n.name == "texture" || n.name == "ref") {
+            parse_rgb_map(n, dummy, isTex, tex);
+            mt.file = tex.file; mt.s = tex.s; mt.t = tex.t;
+        } else {
+            constant = std::stof(n.attr("value"));
+        }
+    }
     MatDesc parse_bsdf(const XmlNode &n, bool twoSided) {
         const std::string type = n.attr("type");
         MatDesc d; memset(&d.m, 0, sizeof(d.m));
         d.m.twoSided = twoSided ? 1 : 0; d.m.kdTex = -1; d.m.areaLight = -1;
+        d.m.ksTex = d.m.ktTex = d.m.expTex = d.m.alphaTex = -1;
         bool isTex; TexDesc tex;
         if (type == "diffuse") {
             d.m.type = BSDF_LAMBERTIAN;
@@ -687,15 +700,15 @@ struct Loader {
                     if (isTex) { d.kdTexFile = tex.file; d.sScale = tex.s; d.tScale = tex.t; }
                 } else if (name == "specularReflectance") {
                     parse_rgb_map(*c, d.m.Ks, isTex, tex);
-                    if (isTex) throw std::runtime_error("textured specularReflectance is not supported");
+                    if (isTex) { d.ks.file = tex.file; d.ks.s = tex.s; d.ks.t = tex.t; }
                 } else if (name == "exponent") {
-                    if (c->name == "texture" || c->name == "ref") throw std::runtime_error("textured exponent is not supported");
-                    d.m.exponent = std::stof(c->attr("value"));
+                    parse_1d_map(*c, d.m.exponent, d.exponent);
                 }
             }
-            // GetKsWeight
+            // GetKsWeight (src/phong.cpp:159-169): texture AVERAGES of Ks and Kd
             const V3 kdAvgV = d.kdTexFile.empty() ? ld3(d.m.Kd) : texture_avg(d.kdTexFile);
-            const float ksAvg = luminance(ld3(d.m.Ks)), kdAvg = luminance(kdAvgV);
+            const V3 ksAvgV = d.ks.file.empty() ? ld3(d.m.Ks) : texture_avg(d.ks.file);
+            const float ksAvg = luminance(ksAvgV), kdAvg = luminance(kdAvgV);
             const float sum = ksAvg + kdAvg;
             d.m.KsWeight = (sum > 0.0f) ? ksAvg / sum : 0.0f;
             return d;
@@ -709,14 +722,13 @@ struct Loader {
                 if (name == "intIOR") intIOR = std::stof(c->attr("value"));
                 else if (name == "extIOR") extIOR = std::stof(c->attr("value"));
                 else if (name == "alpha") {
-                    if (c->name == "texture" || c->name == "ref") throw std::runtime_error("textured alpha is not supported");
-                    d.m.alpha = std::stof(c->attr("value"));
+                    parse_1d_map(*c, d.m.alpha, d.alpha);
                 } else if (name == "specularReflectance") {
                     parse_rgb_map(*c, d.m.Ks, isTex, tex);
-                    if (isTex) throw std::runtime_error("textured specularReflectance is not supported");
+                    if (isTex) { d.ks.file = tex.file; d.ks.s = tex.s; d.ks.t = tex.t; }
                 } else if (name == "specularTransmittance") {
                     parse_rgb_map(*c, d.m.Kt, isTex, tex);
-                    if (isTex) throw std::runtime_error("textured specularTransmittance is not supported");
+                    if (isTex) { d.kt.file = tex.file; d.kt.s = tex.s; d.kt.t = tex.t; }
                 }
             }
             d.m.eta = intIOR / extIOR;           // src/roughdielectric.h ctor
@@ -892,6 +904,8 @@ void load_scene_xml(const std::string &xmlPath, SceneStore &out) {
         MatDesc &md = shapes[g].mat;
         Material mat = md.m;
         if (!md.kdTexFile.empty()) { Loader::TexDesc t; t.file = md.kdTexFile; t.s = md.sScale; t.t = md.tScale; mat.kdTex = L.texture_id(t); }
+        auto texId = [&L](const MatTex &mt) { if (mt.file.empty()) return -1; Loader::TexDesc t; t.file = mt.file; t.s = mt.s; t.t = mt.t; return L.texture_id(t); };
+        mat.ksTex = texId(md.ks); mat.ktTex = texId(md.kt); mat.expTex = texId(md.exponent); mat.alphaTex = texId(md.alpha);
         mat.hasST = m.st.empty() ? 0 : 1;
         mat.areaLight = -1; mat.invTotalArea = 0.0f; mat.firstTid = 0;
         out.mats[g] = mat;
@@ -1101,7 +1115,7 @@ template <class T> static void rd_vec(std::ifstream &f, std::vector<T> &v) {
     v.resize(n);
     if (n) f.read((char *)v.data(), n * sizeof(T));
 }
-static const uint32_t kPackVersion = 2;
+static const uint32_t kPackVersion = 3;
 
 void save_scene_pack(const std::string &path, const SceneStore &s) {
     std::ofstream f(path, std::ios::binary);

@@ -254,6 +254,82 @@ int lmco_run_chains(void *h, int numChains, int chainBase, int totalChains, long
     LMCO_CATCH
 }
 
+// Step-by-step view of ONE chain for the independent restatement of the chain-level arithmetic in
+// tests/test_chain_logic.py (numpy, written from src/mutation_mala.h:83-278, src/mala.cpp:7-51, src/gaussian.cpp:5-36,
+// src/mutation_large.h:70-127, src/mlt.cpp:113-170 -- NOT from csrc/core): the chain advances one iteration per record and
+// the record holds what the step read and what it left behind.  maxdepth <= 8.  rec[numSteps][LMCO_DBG_STRIDE]:
+//   header  0 kind (0 large, 1 isotropic, 2 MALA, 3 H2MC)  1 accepted  2 a  3 dim(cur)  4 dim(prop)  5 cur.ssScore
+//           6 prop.ssScore  7 cur.lsScore  8 prop.lsScore  9 cur.scoreSum  10 prop.scoreSum  11 lastScore (before)
+//           12 lastScoreSum (before)  13 cur.gaussianInitialized (before)  14 chain.buffered (before)  15 hasContrib
+//           16 cur.valid (before)  17 gradient mode of cur (before)  18 gradient mode of prop  19 cur.logDet  20 prop.logDet
+//           21 lastScore (after)  22 lastScoreSum (after)  23 chain.t (before)  24 chain.t (after)  25 chain.buffered (after)
+//           26 adjacentReject (before)  27 adjacentReject (after)  28 outlier resets during the step
+//   arrays (16 floats each, from 32): offset, grad(prop), grad(cur), v1 before, v2 before, v1 after, v2 after,
+//           curr_new_v2 before, prop_new_v2 before, cur.mean, cur.invCov_d, cur.covL_d, prop.mean, prop.invCov_d, prop.covL_d
+#define LMCO_DBG_STRIDE (32 + 15 * 16)
+int lmco_chain_debug(void *h, int chainId, int totalChains, int numSteps, long long numSamplesThisChain, float normalization,
+                     const float *initLs, float *rec) {
+    LMCO_TRY
+    const Scene sc = ((OScene *)h)->store.view();
+    if (sc.opt.maxDepth > 8 || sc.opt.cacheEnabled) throw std::runtime_error("lmco_chain_debug: maxdepth <= 8, cache off");
+    const int MAXD = 8, DIM = 16;
+    RunParams rp; rp.normalization = normalization; rp.numChains = totalChains;
+    rp.numSamplesThisChain = numSamplesThisChain; rp.initLsScore = initLs;
+    ref_grad_hook() = (g_useRef && g_refLoaded) ? ref_gradient : nullptr;
+    std::vector<float> film((size_t)sc.cam.width * sc.cam.height * 3, 0.0f);
+    HostFilm hf; hf.p = film.data();
+    std::unique_ptr<ChainState<MAXD>> csp(new ChainState<MAXD>());
+    std::unique_ptr<H2mcSide> side(new H2mcSide());
+    ChainState<MAXD> &cs = *csp;
+    chain_state_init(cs, initLs ? initLs[chainId] : 0.0f);
+    memset(side.get(), 0, sizeof(H2mcSide));
+    uint32_t tab[64];
+    for (int k = 0; k < numSteps; k++) {
+        float *r = rec + (size_t)k * LMCO_DBG_STRIDE;
+        for (int i = 0; i < LMCO_DBG_STRIDE; i++) r[i] = 0.0f;
+        float *arr = r + 32;
+        const int c0 = cs.curIdx;
+        const MarkovState<MAXD> &cur = cs.st[c0], &prop = cs.st[c0 ^ 1];
+        r[3] = cur.valid ? (float)path_dimension(cur.path) : 0.0f;
+        r[5] = cur.sp.ssScore; r[7] = cur.sp.lsScore; r[9] = cur.scoreSum;
+        r[11] = cs.ch.lastScore; r[12] = cs.ch.lastScoreSum; r[13] = (float)cur.gaussianInitialized; r[14] = (float)cs.ch.buffered;
+        r[16] = (float)cur.valid; r[17] = cur.valid ? (float)mala_grad_mode(sc, cur) : -1.0f;
+        r[23] = (float)cs.ch.t; r[26] = (float)cs.ch.adjacentReject;
+        const int resets0 = cs.ch.outlierResets;
+        for (int i = 0; i < DIM; i++) {
+            arr[3 * 16 + i] = cs.ch.v1[i]; arr[4 * 16 + i] = cs.ch.v2[i];
+            arr[7 * 16 + i] = cs.ch.curr_new_v2[i]; arr[8 * 16 + i] = cs.ch.prop_new_v2[i];
+        }
+        if (cur.valid && !cur.gaussianInitialized && mala_grad_mode(sc, cur) == 2) {
+            float g[DIM]; for (int i = 0; i < DIM; i++) g[i] = 0.0f;
+            mala_eval_gradient(sc, cur, g, nullptr);
+            for (int i = 0; i < DIM; i++) arr[2 * 16 + i] = g[i];
+        }
+        unsigned char tr = 0; float a = 0.0f;
+        chain_run(sc, rp, chainId, cs, 1, tab, 1, hf, &tr, &a, 1, side.get(), (StagedWork<MAXD> *)nullptr);
+        r[0] = (float)cs.ss.kind; r[1] = (float)((tr >> 2) & 1); r[2] = a; r[15] = (float)cs.ss.hasContrib;
+        r[21] = cs.ch.lastScore; r[22] = cs.ch.lastScoreSum; r[24] = (float)cs.ch.t; r[25] = (float)cs.ch.buffered;
+        r[27] = (float)cs.ch.adjacentReject; r[28] = (float)(cs.ch.outlierResets - resets0);
+        if (cs.ss.hasContrib || cs.ss.kind == STEP_LARGE || a > 0.0f) {
+            r[4] = (float)path_dimension(prop.path); r[6] = prop.sp.ssScore; r[8] = prop.sp.lsScore; r[10] = prop.scoreSum;
+            r[18] = (float)mala_grad_mode(sc, prop);
+        }
+        r[19] = cur.gaussian.logDet; r[20] = prop.gaussian.logDet;
+        if (cs.ss.kind == STEP_MALA && cs.ss.hasContrib && mala_grad_mode(sc, prop) == 2) {
+            float g[DIM]; for (int i = 0; i < DIM; i++) g[i] = 0.0f;
+            mala_eval_gradient(sc, prop, g, nullptr);
+            for (int i = 0; i < DIM; i++) arr[1 * 16 + i] = g[i];
+        }
+        for (int i = 0; i < DIM; i++) {
+            arr[0 * 16 + i] = cs.ss.offset[i];
+            arr[5 * 16 + i] = cs.ch.v1[i]; arr[6 * 16 + i] = cs.ch.v2[i];
+            arr[9 * 16 + i] = cur.gaussian.mean[i]; arr[10 * 16 + i] = cur.gaussian.invCov_d[i]; arr[11 * 16 + i] = cur.gaussian.covL_d[i];
+            arr[12 * 16 + i] = prop.gaussian.mean[i]; arr[13 * 16 + i] = prop.gaussian.invCov_d[i]; arr[14 * 16 + i] = prop.gaussian.covL_d[i];
+        }
+    }
+    LMCO_CATCH
+}
+
 // Oracle-R switch: load oracle/_ref/libpathref_mala.so and route every MALA gradient of subsequent
 // lmco_run_chains calls through the reference's generated reverse-mode code (enable = 0 switches back
 // to the twin evaluator).  Returns the number of (c, l) functions resolved, or -1.
@@ -416,7 +492,8 @@ int lmco_eval_batch(void *h, int camDepth, int lightDepth, int n, const float *p
     }
     return 0;
 }
-// gradient + Hessian (second-order forward mode); hess n x dim x dim row-major
+// gradient + Hessian; hess n x dim x dim row-major.  adjointcompat = 3 selects the forward-over-reverse evaluator (what
+// the H2MC mutation runs, LMC_HESS_REV_CHUNK directions per sweep), anything else the second-order forward one
 int lmco_eval_batch_hess(void *h, int camDepth, int lightDepth, int n, const float *primary, int primaryStride,
                          const float *vertParams, int vertStride, float *logLum, float *grad, float *hess) {
     const lmc_host::SceneStore &st = ((OScene *)h)->store;
@@ -424,7 +501,7 @@ int lmco_eval_batch_hess(void *h, int camDepth, int lightDepth, int n, const flo
     const int dim = primary_param_size(camDepth, lightDepth) - 1;
     if (dim > LMC_HESS_MAXDIM) return -1;
     for (int i = 0; i < n; i++)
-        logLum[i] = (st.head.opt.adjointCompat == 3 ? path_loglum_hess_rev<4> : path_loglum_hess)(camDepth, lightDepth, sceneSer, primary + (size_t)i * primaryStride,
+        logLum[i] = (st.head.opt.adjointCompat == 3 ? path_loglum_hess_rev<(LMC_HESS_REV_CHUNK > 0 ? LMC_HESS_REV_CHUNK : 4)> : path_loglum_hess)(camDepth, lightDepth, sceneSer, primary + (size_t)i * primaryStride,
                                      vertParams + (size_t)i * vertStride, grad + (size_t)i * dim, hess + (size_t)i * dim * dim);
     return 0;
 }

@@ -73,6 +73,11 @@ class Oracle:
         self.L.lmco_scene_serialized(h, self.p(s))
         return s
 
+    def get_option(self, h, name):
+        v = ctypes.c_double()
+        assert self.L.lmco_get_option(h, name.encode(), ctypes.byref(v)) == 0, name
+        return v.value
+
     def mlt_init(self, h, num_init, num_chains, logical_threads=32):
         norm = ctypes.c_float()
         ls = np.zeros(num_chains, np.float32)

@@ -3,8 +3,12 @@
 BASELINE.json configs[0]: torus, LMC, path length 4, 1024 chains x 100 mutations, fixed PCG
 seeds (chain id + seedoffset): accept/reject + step-type sequence and acceptance probabilities
 must be BIT-identical; the film equal up to fp32 atomic summation order."""
+import os
+
 import numpy as np
 import pytest
+
+from conftest import SCENES
 
 
 def oracle_run(oracle, xml, opts, chains, steps, norm, init_ls, **kw):
@@ -333,3 +337,21 @@ def test_cuda_outlier_reset_bit_identical_to_oracle(lmc, oracle, torus_xml):
     assert np.array_equal(a.view(np.uint32), oa.view(np.uint32))
     assert np.allclose(film, ofilm, rtol=1e-4, atol=1e-5)
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_cuda_textured_parameter_scene_bit_identical(lmc, oracle):
+    """scenes/torus/textured.xml: bitmap-textured Phong Ks / exponent and RoughDielectric alpha / Kt:
+    the device evaluates the parameter maps per hit exactly like the host twin."""
+    xml = os.path.join(SCENES, "torus", "textured.xml")
+    sc = lmc.ParseScene(xml)
+    sc.options["maxdepth"] = 6
+    chains, steps = 512, 40
+    norm, init_ls = lmc.MLTInit(sc, 100000, chains, 32)
+    ctx = lmc.ChainContext(sc, 0)
+    ctx.begin(chains, norm, init_ls, samples_per_chain=steps)
+    trace, a = ctx.run(steps, trace=True, a_trace=True)
+    film = ctx.film()
+    ofilm, otrace, oa, ostats = oracle_run(oracle, xml, {"maxdepth": 6}, chains, steps, norm, init_ls, samples_per_chain=steps)
+    assert np.array_equal(trace, otrace) and np.array_equal(a.view(np.uint32), oa.view(np.uint32))
+    assert np.allclose(film, ofilm, rtol=1e-4, atol=1e-5 * max(1.0, float(ofilm.max())))

@@ -1,5 +1,6 @@
-"""H2MC mutation (BASELINE configs[3]): Hessian by second-order forward mode,
-Jacobi eigen-solver (replacing Eigen::SelfAdjointEigenSolver, unpinned), dense Gaussian proposal."""
+"""H2MC mutation (BASELINE configs[3]): Hessian by forward-over-reverse (second-order forward mode
+as the cross-check), parallel-order Jacobi eigen-solver (replacing Eigen::SelfAdjointEigenSolver, unpinned; warp-cooperative
+on the device), dense Gaussian proposal."""
 import os
 
 import numpy as np
@@ -30,9 +31,10 @@ def test_jacobi_eigensolver_matches_lapack(oracle):
 def test_hessian_matches_reference_generated_code(oracle, torus_xml, door_xml, mode):
     """Our Hessians vs the reference's (evaluate_path_bidir_<c>_<l>_static_derv, vectors in
     tests/golden/path_golden.npz, every path length up to 8):
-      mode 1  second-order forward mode (csrc/core/pathgrad.h path_loglum_hess) -- what the H2MC mutation runs
-      mode 3  forward-over-reverse: the generated reverse sweep on dual numbers (pathgrad_rev.h, host only) -- an
-              independent derivation used as a cross-check."""
+      mode 3  forward-over-reverse: the generated reverse sweep on dual numbers (pathgrad_rev.h path_loglum_hess_rev)
+              -- what the H2MC mutation runs, on the device and in the host twin
+      mode 1  second-order forward mode (csrc/core/pathgrad.h path_loglum_hess) -- an independent derivation kept as
+              a cross-check (it was the device path of round 1)."""
     g = np.load(os.path.join(GOLDEN, "path_golden.npz"))
     handles = {0: oracle.load(torus_xml), 1: oracle.load(door_xml), 2: oracle.load(os.path.join(SCENES, "torus", "point.xml"))}
     for h in handles.values():

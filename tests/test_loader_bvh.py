@@ -123,3 +123,57 @@ def test_scene_loads_without_rawf_containers(oracle, tmp_path):
     r0 = oracle.run_chains(h0, 256, 12, n0, l0, samples_per_chain=12)
     r1 = oracle.run_chains(h1, 256, 12, n1, l1, samples_per_chain=12)
     assert np.array_equal(r0[1], r1[1]) and np.array_equal(r0[0], r1[0])
+
+
+def _bsdf_records(c, l, v):
+    """The 10-float BSDF records along a serialized path (layout: SURVEY.md App. A.4)."""
+    o, out = 3, []
+    if l > 1:
+        o += 1 + 56
+        for k in range(l - 1):
+            out.append(v[o + 48:o + 58])
+            o += 46 + 2 + 10 + (0 if k == l - 2 else 1)
+    for k in range(c - 1):
+        if k == c - 2:
+            if l == 1:
+                out.append(v[o + 46 + 56:o + 46 + 66])
+            elif l >= 2:
+                out.append(v[o + 46:o + 56])
+        else:
+            out.append(v[o + 48:o + 58])
+            o += 59
+    return out
+
+
+def test_textured_bsdf_parameters(oracle):
+    """Parse3DMap / Parse1DMap of ParseBSDF (src/parsescene.cpp:341-412): Phong specularReflectance / exponent and
+    RoughDielectric alpha / specularTransmittance read from bitmaps (scenes/torus/textured.xml = lmc.xml with those four
+    parameters textured).  The serialized BSDF records (BSDF::Serialize evaluates the textures at the hit point,
+    src/phong.cpp:14-20, src/roughdielectric.cpp:13-20) must carry per-hit values; the constant scene must not."""
+    def records(xml):
+        h = oracle.load(os.path.join(SCENES, "torus", xml))
+        oracle.set_option(h, "maxdepth", 6)
+        rec = oracle.sample_paths(h, 7, 2500, perturb=False, max_len=6)
+        phong, glass = [], []
+        for r in rec:
+            c, l = int(r[0]), int(r[1])
+            for b in _bsdf_records(c, l, r[oracle.REC_HEAD + 25:]):
+                (phong if int(b[0]) == 1 else glass if int(b[0]) == 2 else []).append(b)
+        return np.array(phong), np.array(glass)
+    p0, g0 = records("lmc.xml")
+    p1, g1 = records("textured.xml")
+    assert len(p1) > 200 and len(g1) > 200
+    # constant scene: two Phong materials, one glass
+    assert len(np.unique(p0[:, 7])) == 2 and len(np.unique(g0[:, 9])) == 1 and np.allclose(g0[:, 4:7], 1.0)
+    # textured scene.  Phong record: type, Kd(3), Ks(3), exponent, KsWeight; glass: type, Ks(3), Kt(3), eta, invEta, alpha
+    floor = p1[p1[:, 7] <= 1.0]                               # the 8-bit exponent map decodes to (0, 1] (gamma 2.2)
+    assert len(floor) > 100 and len(np.unique(floor[:, 7])) > 20 and floor[:, 7].min() > 0.0
+    assert len(np.unique(floor[:, 4])) >= 2 and floor[:, 4:7].min() >= 0.0 and floor[:, 4:7].max() <= 1.001   # fastpow(1, 2.2) = 1.0000076
+    assert np.array_equal(floor[:, 4], floor[:, 5])           # grey checker: Ks channels equal
+    alpha = g1[:, 9]
+    lo, hi = (40 / 255.0) ** 2.2, (140 / 255.0) ** 2.2        # range of the alpha map's five grey levels
+    assert len(np.unique(alpha)) > 20 and alpha.min() >= lo * 0.9 and alpha.max() <= hi * 1.1
+    assert (alpha < 0.05).any() and (alpha > 0.05).any()      # both parametrisations of the glass vertex occur
+    assert g1[:, 4:7].min() >= 0.0 and g1[:, 4:7].max() <= 1.001 and len(np.unique(g1[:, 4])) >= 2
+    # KsWeight uses the texture AVERAGES (src/phong.cpp:159-169): one value per material, not per hit
+    assert len(np.unique(floor[:, 8])) == 1

@@ -10,5 +10,5 @@ nvcc -ccbin /usr/bin/g++ -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a 
      -Xcompiler -fPIC,-mfma,-ffp-contract=off,-pthread -Xptxas -v $@ \
      -c -o $PKG/build/var_$NAME/chain_inst_8.o $PKG/csrc/cuda/chain_inst_8.cu 2> $PKG/build/var_$NAME/ptxas.log
 nvcc -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -shared -o $PKG/liblmc_b200_$NAME.so \
-     $PKG/build/lmc_abi.o $PKG/build/chain_inst_4.o $PKG/build/var_$NAME/chain_inst_8.o $PKG/build/chain_inst_12.o $PKG/build/host_scene.o -lz -lpthread
+     $PKG/build/lmc_abi.o $PKG/build/chain_hess_4.o $PKG/build/chain_hess_8.o $PKG/build/chain_hess_12.o $PKG/build/chain_inst_4.o $PKG/build/var_$NAME/chain_inst_8.o $PKG/build/chain_inst_12.o $PKG/build/host_scene.o -lz -lpthread
 echo built $NAME
