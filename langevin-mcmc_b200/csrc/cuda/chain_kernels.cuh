@@ -243,15 +243,26 @@ namespace lmc_cuda {
 // of ONE (camDepth, lightDepth) class: the evaluator's vertex loops have the same trip counts in all of
 // its threads, which is what the barriers of core/pathgrad.h (LMC_VERTEX_SYNC) require.  Padding
 // entries (-1) redo the block's first chain into scratch so that they take part in every barrier.
+// (the Hessian instantiation, ORDER = 2, carries dual numbers through the sweep and has its own occupancy setting)
+#ifndef LMC_HESS_MINB
+#define LMC_HESS_MINB 4
+#endif
+#ifndef LMC_HESS_BLOCK
+#define LMC_HESS_BLOCK LMC_GRAD_BLOCK      // must divide LMC_GRAD_BLOCK (the class alignment of the gradient lists)
+#endif
 template <int MAXD, int ORDER>
-__global__ void __launch_bounds__(LMC_GRAD_BLOCK, (LMC_GRAD_MINB * 128) / LMC_GRAD_BLOCK) k_wave_grad(const __grid_constant__ Scene sc, ChainRec<MAXD> *states, int n,
+__global__ void __launch_bounds__(ORDER == 2 ? LMC_HESS_BLOCK : LMC_GRAD_BLOCK,
+                                  ORDER == 2 ? (LMC_HESS_MINB * 128) / LMC_HESS_BLOCK : (LMC_GRAD_MINB * 128) / LMC_GRAD_BLOCK) k_wave_grad(const __grid_constant__ Scene sc, ChainRec<MAXD> *states, int n,
                                                                 const int *list, const int *count, int which, H2mcSide *sides,
                                                                 H2mcSide *padSide) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= *count) return;                    // *count is a multiple of the block size: whole blocks leave
     int i = list[t];
     const bool pad = i < 0;
-    if (pad) i = list[blockIdx.x * blockDim.x]; // class segments start on block boundaries and are filled from the front
+    if (pad) {
+        i = list[blockIdx.x * blockDim.x];      // class segments start on alignment boundaries and are filled from the front
+        if (i < 0) return;                      // (a block smaller than the alignment can be all padding: uniform exit)
+    }
     ChainState<MAXD> &cs = states[i].cs;
     if (pad) {
         StepScratch<MAXD> scratch; scratch.kind = cs.ss.kind;
@@ -1006,7 +1017,7 @@ template <> cudaError_t launch_wave_hess<12>(cudaStream_t, const Scene &, ChainR
 #define LMC_INSTANTIATE_HESS(MAXD) \
     template <> cudaError_t launch_wave_hess<MAXD>(cudaStream_t st, const Scene &sc, ChainRec<MAXD> *states, int n, const int *list, \
                                                    const int *count, int which, H2mcSide *sides, H2mcSide *padSide, int GG, int GH) { \
-        k_wave_grad<MAXD, 2><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, list, count, which, sides, padSide); \
+        k_wave_grad<MAXD, 2><<<GG * (LMC_GRAD_BLOCK / LMC_HESS_BLOCK), LMC_HESS_BLOCK, 0, st>>>(sc, states, n, list, count, which, sides, padSide); \
         k_h2mc_gaussian<MAXD><<<GH, LMC_H2MC_BLOCK, 0, st>>>(sc, states, list, count, which, sides); \
         return cudaGetLastError(); \
     }

@@ -1,7 +1,8 @@
 """Key metrics + stall breakdown of one ncu report (first kernel)."""
 import csv, subprocess, sys
 rep = sys.argv[1]
-out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+# a .ncu-rep report, or the csv of its raw page (`ncu -i rep --page raw --csv`, what tools/ncu_hot.sh brings back)
+out = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
 m = dict(zip(hdr, vals))
