@@ -3,7 +3,8 @@
 # /root/reference; outputs are git-ignored but travel to the GPU box).
 PKG      := langevin-mcmc_b200
 CORE_INC := $(wildcard $(PKG)/csrc/core/*.inc)
-CORE_H   := $(wildcard $(PKG)/csrc/core/*.h) $(wildcard $(PKG)/csrc/host/*.h) $(CORE_INC)
+DEV_H    := $(wildcard $(PKG)/csrc/core/*.h) $(CORE_INC)
+CORE_H   := $(DEV_H) $(wildcard $(PKG)/csrc/host/*.h)
 CXX      := $(shell which g++)
 CXXFLAGS := -O2 -std=c++17 -fPIC -mfma -ffp-contract=off -fno-fast-math -Wall -Wno-unused-function -pthread
 NVCC     := nvcc
@@ -28,7 +29,9 @@ CUDA_SRC := $(PKG)/csrc/cuda
 CUDA_OBJ := $(PKG)/build/lmc_abi.o $(PKG)/build/chain_hess_12.o $(PKG)/build/chain_hess_8.o $(PKG)/build/chain_hess_4.o \
             $(PKG)/build/chain_inst_12.o $(PKG)/build/chain_inst_8.o $(PKG)/build/chain_inst_4.o
 lib: $(PKG)/liblmc_b200.so
-$(PKG)/build/%.o: $(CUDA_SRC)/%.cu $(CORE_H) $(CORE_INC) $(wildcard $(CUDA_SRC)/*.cuh) $(wildcard $(CUDA_SRC)/*.h) include/lmc/lmc_abi.h
+# the chain kernels see the device headers only; the C ABI translation unit also includes the host side (loader, MLTInit, image io)
+$(PKG)/build/lmc_abi.o: $(CORE_H)
+$(PKG)/build/%.o: $(CUDA_SRC)/%.cu $(DEV_H) $(wildcard $(CUDA_SRC)/*.cuh) $(wildcard $(CUDA_SRC)/*.h) include/lmc/lmc_abi.h
 	@mkdir -p $(PKG)/build
 	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $(PKG)/build/$*.ptxas.log || (cat $(PKG)/build/$*.ptxas.log; false)
 $(PKG)/build/host_scene.o: $(PKG)/csrc/host/host_scene.cpp $(CORE_H)

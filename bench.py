@@ -58,9 +58,9 @@ WORKLOADS = {
                           text="torus, H2MC (Hessian preconditioner), maxdepth 8, 2^20 chains per GPU (BASELINE configs[3])"),
 }
 HEADLINE = "torus_lmc_L8"
-# dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one iteration over 2^20 chains
-# (ncu, profiles/r02_launches_2p20_summary.txt), per mutation; None until measured for this build
-DRAM_BYTES_PER_MUTATION_NCU = None
+# dram__bytes_read.sum + dram__bytes_write.sum of all kernels of one steady-state chain-loop iteration over 2^20 chains
+# (ncu launch list of this very command, profiles/r02_bench_launches.csv: 13.4 GB per 48-launch iteration), per mutation
+DRAM_BYTES_PER_MUTATION_NCU = 12800
 
 
 def load_package():

@@ -320,8 +320,9 @@ def MLT(scene, numChains=None, mutationsPerChain=None, device=0, logicalThreads=
     """MLT() (src/mlt.cpp:20-215) on one GPU: DirectLighting pre-pass, MLTInit on the host, the chain loop on the
     GPU, MergeBuffer(direct / directSpp, indirect / spp) -> film, optional WriteImage.  Returns (film H x W x 3,
     stats).  Known deviations from the reference's MLT(): every chain runs mutationsPerChain iterations (the
-    reference adds one to chainId < numSamplesPerChain % numChains, src/mlt.cpp:40,64-65); the global cache is not
-    built, so LMC keeps evaluating gradients where the reference switches to cached moments (src/mutation_mala.h:131-161);
+    reference adds one to chainId < numSamplesPerChain % numChains, src/mlt.cpp:40,64-65); the global cache
+    (src/mutation_mala.h:131-161) is an option here (`globalcache`, default 0 = every eligible MALA step evaluates its gradient;
+    1 = cached moments once a dimension holds 3000 entries, filled in a defined order instead of the reference's thread order);
     a gradient that is not evaluated because ssScore <= 1e-10 is zero instead of the stale vector the reference
     reuses.  The C++ form with multi-GPU sharding and progressive dumps is include/lmc/mlt.h."""
     if numChains is None:

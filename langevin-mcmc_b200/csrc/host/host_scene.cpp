@@ -232,17 +232,20 @@ static M44 parse_transform(const XmlNode &node) {
 }
 
 // ------------------------------------------------------------------------------------------
-// images: "<file>.rawf" (pre-decoded by tools/stage_scenes.py) when it exists, else PNG / EXR decoded here
-// (image_decode.h; what the reference does through OpenImageIO, src/bitmaptexture.h:73-146, src/image.cpp:5-45)
+// images: PNG / JPEG / OpenEXR are decoded here (image_decode.h, jpeg_decode.h; what the reference does through
+// OpenImageIO, src/bitmaptexture.h:73-146, src/image.cpp:5-45).  Any other format can be handed over pre-decoded as
+// "<file>.rawf" (tools/stage_scenes.py; the containers of the bundled images are kept under tests/golden/decoded/ as the
+// OpenCV-decoded ground truth the native decoders are tested against).
 // ------------------------------------------------------------------------------------------
 typedef DecodedImage RawImage;
 static RawImage load_rawf(const std::string &path) {
-    std::ifstream f(path + ".rawf", std::ios::binary);
-    if (!f) {
+    {
+        std::ifstream probe(path, std::ios::binary);
         RawImage native;
-        if (decode_image_native(path, native)) return native;
-        throw std::runtime_error("cannot open image '" + path + ".rawf' (JPEG textures are pre-decoded: run tools/stage_scenes.py)");
+        if (probe && decode_image_native(path, native)) return native;
     }
+    std::ifstream f(path + ".rawf", std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open image '" + path + "' (PNG / JPEG / OpenEXR are decoded natively; other formats: '" + path + ".rawf', see tools/stage_scenes.py)");
     char magic[4]; int hdr[3];
     f.read(magic, 4); f.read((char *)hdr, 12);
     if (memcmp(magic, "RAWF", 4) != 0) throw std::runtime_error("bad rawf magic: " + path);

@@ -39,8 +39,9 @@ struct SceneStore {
 // Default options == src/dptoptions.h:7-34 (+ the #define constants the reference compiles in).
 lmc::Options default_options();
 
-// Parse a reference-format scene xml.  Images are read from "<file>.rawf" siblings written by
-// tools/stage_scenes.py (float32 RGB + an 8-bit-source flag).  Throws std::runtime_error.
+// Parse a reference-format scene xml from the reference's own scene directory: PNG / JPEG / OpenEXR images are decoded
+// here (image_decode.h); any other encoding can be handed over as a "<file>.rawf" sibling (tools/stage_scenes.py:
+// float32 or 8-bit RGB + an 8-bit-source flag).  Throws std::runtime_error.
 void load_scene_xml(const std::string &xmlPath, SceneStore &out);
 
 // Set / get one option by its reference name (the <dpt> names of src/parsescene.cpp:535-590

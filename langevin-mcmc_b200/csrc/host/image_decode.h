@@ -1,14 +1,13 @@
-// image_decode.h -- in-loader decoding of the image formats the reference's scenes use for lossless data:
-// PNG textures and OpenEXR environment maps.
+// image_decode.h -- in-loader decoding of the image formats the reference's scenes use: PNG and JPEG textures
+// (JPEG: jpeg_decode.h) and OpenEXR environment maps.
 //
 // The reference reads images through OpenImageIO (src/image.cpp:5-45, src/bitmaptexture.h:73-146), which is vendored
 // only as unbuilt source.  These two decoders follow the published file formats directly (PNG: RFC 2083; OpenEXR:
 // "OpenEXR File Layout") on top of zlib's inflate, which the loader links anyway for .serialized meshes:
 //   PNG   8-bit grey / grey+alpha / RGB / RGBA / palette, non-interlaced
 //   EXR   single-part scan-line files, compression NONE / ZIPS / ZIP, HALF or FLOAT channels R G B (or Y)
-// Both are lossless, so the result is bit-identical to what tools/stage_scenes.py stores in the .rawf containers
-// (tests/test_loader_bvh.py).  JPEG (lossy: results depend on the decoder's IDCT and chroma upsampling) stays on the
-// pre-decoded .rawf path so that textures are reproducible.
+// Both are lossless, so the result is bit-identical to the OpenCV decode kept in tests/golden/decoded/*.rawf
+// (tests/test_loader_bvh.py); the JPEG decoder reproduces the libjpeg family's default arithmetic and matches them too.
 #pragma once
 #include <zlib.h>
 #include <stdint.h>
@@ -17,6 +16,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include "jpeg_decode.h"
 
 namespace lmc_host {
 
@@ -180,13 +180,21 @@ inline DecodedImage decode_exr(const std::string &path) {
     return im;
 }
 
-// PNG / EXR by extension; anything else (JPEG) must have been pre-decoded to <file>.rawf
+inline DecodedImage decode_jpeg(const std::string &path) {
+    const JpegImage j = decode_jpeg_bytes(imgdetail::read_file(path), path);
+    DecodedImage im; im.w = j.w; im.h = j.h; im.is8 = 1; im.rgb.resize(j.rgb.size());
+    for (size_t i = 0; i < j.rgb.size(); i++) im.rgb[i] = (float)j.rgb[i] / 255.0f;
+    return im;
+}
+
+// PNG / EXR / JPEG by extension
 inline bool decode_image_native(const std::string &path, DecodedImage &out) {
     const size_t dot = path.rfind('.');
     std::string ext = dot == std::string::npos ? "" : path.substr(dot + 1);
     for (auto &c : ext) c = (char)tolower(c);
     if (ext == "png") { out = decode_png(path); return true; }
     if (ext == "exr") { out = decode_exr(path); return true; }
+    if (ext == "jpg" || ext == "jpeg") { out = decode_jpeg(path); return true; }
     return false;
 }
 

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import SCENES
+from conftest import GOLDEN, SCENES
 
 
 def make_rays(n, seed, center, radius):
@@ -92,27 +92,35 @@ def _read_rawf(path):
     return int(w), int(h), int(is8), rgb
 
 
-@pytest.mark.parametrize("name", ["checker.png", "sunsky.exr"])
-def test_native_image_decoders_match_staged_rawf(oracle, name):
-    """The loader's own PNG / OpenEXR decoders (csrc/host/image_decode.h, what the reference gets from OpenImageIO,
-    src/image.cpp:5-45, src/bitmaptexture.h:73-146) give the bits tools/stage_scenes.py decoded with OpenCV."""
+IMAGES = [("torus", "checker.png"), ("torus", "sunsky.exr"), ("veachdoor", "72cf.jpg"), ("veachdoor", "72rdf.jpg"),
+          ("veachdoor", "checker.jpg"), ("veachdoor", "marble.jpg"), ("veachdoor", "perlin.jpg"), ("veachdoor", "pic.jpg")]
+
+
+@pytest.mark.parametrize("scene,name", IMAGES)
+def test_native_image_decoders_match_opencv_decode(oracle, scene, name):
+    """The loader's own PNG / OpenEXR / JPEG decoders (csrc/host/image_decode.h, jpeg_decode.h -- what the reference gets
+    from OpenImageIO, src/image.cpp:5-45, src/bitmaptexture.h:73-146) against the OpenCV decode of the same files kept in
+    tests/golden/decoded/<file>.rawf (written by tools/stage_scenes.py): every image of the two bundled scenes, bit for
+    bit -- incl. the JPEGs (four baseline 4:2:0 files with odd sizes, two progressive 4:4:4 ones)."""
     import ctypes
-    path = os.path.join(SCENES, "torus", "data", name)
-    w, h, is8, ref = _read_rawf(path + ".rawf")
+    path = os.path.join(SCENES, scene, "data", name)
+    w, h, is8, ref = _read_rawf(os.path.join(GOLDEN, "decoded", name + ".rawf"))
     whi = np.zeros(3, np.int32)
     out = np.zeros(w * h * 3, np.float32)
     oracle.L.lmco_decode_image.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong]
-    assert oracle.L.lmco_decode_image(path.encode(), oracle.p(whi), oracle.p(out), out.size) == 0
+    assert oracle.L.lmco_decode_image(path.encode(), oracle.p(whi), oracle.p(out), out.size) == 0, oracle.L.lmco_last_error()
     assert (int(whi[0]), int(whi[1]), int(whi[2])) == (w, h, is8)
     assert np.array_equal(out.view(np.uint32), np.ascontiguousarray(ref).view(np.uint32))
 
 
-def test_scene_loads_without_rawf_containers(oracle, tmp_path):
-    """lmc_scene_load on a directory that holds only the reference's own files (no .rawf): same serialized scene,
-    same first mutations."""
+def test_scene_loads_from_predecoded_containers(oracle, tmp_path):
+    """The .rawf hand-over path (formats the loader does not decode): a copy of the torus scene whose images exist ONLY
+    as .rawf containers loads to the same scene and runs the same first mutations as the natively decoded one."""
     import shutil
     dst = tmp_path / "torus"
-    shutil.copytree(os.path.join(SCENES, "torus"), dst, ignore=shutil.ignore_patterns("*.rawf"))
+    shutil.copytree(os.path.join(SCENES, "torus"), dst, ignore=shutil.ignore_patterns("*.png", "*.exr", "textured.xml"))
+    for name in ("checker.png", "sunsky.exr"):
+        shutil.copyfile(os.path.join(GOLDEN, "decoded", name + ".rawf"), dst / "data" / (name + ".rawf"))
     h0 = oracle.load(os.path.join(SCENES, "torus", "lmc.xml"))
     h1 = oracle.load(str(dst / "lmc.xml"))
     for h in (h0, h1):

@@ -1,14 +1,14 @@
 #!/usr/bin/env python3
 """Stage the reference's bundled scenes into scenes/<name>/ of this repo.
 
-Copies the scene XML + mesh files verbatim (they are input DATA, not source) and decodes
-every image (EXR envmap, PNG/JPG textures) into a tiny raw float container "<file>.rawf":
+Copies the scene XML + mesh + image files verbatim (they are input DATA, not source; the loader decodes PNG / JPEG /
+OpenEXR itself) and, as the ground truth the native decoders are tested against, decodes every image with OpenCV into a
+tiny raw container tests/golden/decoded/<file>.rawf -- also the hand-over format for images in any other encoding:
 
     magic 'RAWF' | int32 width | int32 height | int32 is8bit | RGB[h][w][3] (row 0 = top)
     payload is uint8 when is8bit (the loader divides by 255.0f), float32 otherwise
 
-so the C++ host loader needs no image library (the reference links OpenImageIO for this,
-src/image.cpp:5-45, src/bitmaptexture.h:99-146).  `is8bit` drives the 2.2 gamma rule of
+(the reference links OpenImageIO for this, src/image.cpp:5-45, src/bitmaptexture.h:99-146).  `is8bit` drives the 2.2 gamma rule of
 src/bitmaptexture.h:136-144.  Run once in the build container:  python tools/stage_scenes.py
 """
 import os, shutil, struct, sys
@@ -18,6 +18,7 @@ import numpy as np
 
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/scenes"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "scenes")
+DECODED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "decoded")
 
 
 def write_rawf(src, dst):
@@ -50,9 +51,9 @@ for scene in ("torus", "veachdoor"):
         src = os.path.join(sdir, "data", fn)
         ext = fn.rsplit(".", 1)[-1].lower()
         if ext in ("exr", "png", "jpg", "jpeg"):
-            write_rawf(src, os.path.join(odir, "data", fn + ".rawf"))
-            if ext in ("exr", "png"):     # lossless formats are also decoded by the loader itself (csrc/host/image_decode.h)
-                shutil.copyfile(src, os.path.join(odir, "data", fn))
+            os.makedirs(DECODED, exist_ok=True)
+            write_rawf(src, os.path.join(DECODED, fn + ".rawf"))
+            shutil.copyfile(src, os.path.join(odir, "data", fn))     # the loader decodes PNG / EXR / JPEG itself (csrc/host/image_decode.h)
         else:
             shutil.copyfile(src, os.path.join(odir, "data", fn))
     print("staged", scene)
