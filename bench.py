@@ -210,7 +210,7 @@ def device_run(lmc, torch, dist, workload, n_local, M, K, W, rank, world, local,
         scene.options[k] = v
     total = n_local * world
     stream = torch.cuda.current_stream()
-    # ---- setup (untimed): MLTInit, every rank generates the init paths of its own logical threads ----
+    # ---- setup (untimed): MLTInit with the init paths generated on rank 0's GPU (lmc_mlt_init_device), broadcast ----
     t_setup = time.time()
     ctx = lmc.ChainContext(scene, local, stream=stream.cuda_stream)
     init_t = torch.zeros(total + 1, dtype=torch.float32, device="cuda")
@@ -350,6 +350,13 @@ def main():
                            "steps": 2, "warmup": 1, "mutations_per_step": m2, "ms_per_step": r2["ms"] / 2,
                            "gpu_launches": r2["launches"], "roofline": roofline(r2, name, n_local, m2, 2, peak, peak_src, world),
                            "accepted": r2["stats"]["accepted"], "proposed": r2["stats"]["proposed"]}
+
+        # the operating point of an actual render of this scene (profiles/r01_render_check.txt: 65 536 long chains keep the
+        # start-up bias of the always-accepted first large step small): far fewer chains than the SMs can hold threads for
+        rp = device_run(lmc, torch, dist, HEADLINE, 65536, 64, 2, 1, rank, world, local, want_e2e=False)
+        extra["torus_lmc_L8_render_point"] = {"workload": "torus, LMC, maxdepth 8, 65 536 chains per GPU (chain count of a converged render)",
+                                              "value": rp["value"], "unit": "mutations/s", "n_gpus": world, "steps": 2, "warmup": 1,
+                                              "mutations_per_step": 64, "ms_per_step": rp["ms"] / 2, "gpu_launches": rp["launches"]}
 
     if rank == 0:
         st = res["stats"]
