@@ -24,6 +24,19 @@ namespace lmc {
 enum TraceStage { TS_DONE = 0, TS_P_LGT = 1, TS_P_CAM = 2, TS_G_LGT = 3, TS_G_CAM = 4 };
 enum CandFlag { CAND_VISIBLE = 0, CAND_PENDING = 1, CAND_OCCLUDED = 2, CAND_CLEAR = 4 };
 
+// Capacity invariant.  The list holds, per path function call, the contributions the reference's vector would hold
+// (bounded by Limits<MAXD>::MAXC - 2, mutation.h), the slots reserved for deferred connections (they ARE such
+// contributions) and at most ONE clear entry: every `contribs.clear()` of the path functions is followed by `return`
+// (src/path.cpp:704-708,1384-1387,2075-2078).  So n <= MAXC - 1 and the `n < cap` guards below never fire; if the bound
+// were ever wrong an entry would be dropped (and an unconditional clear would fall back to rewinding the list), which the
+// host build counts -- the staged-path tests assert the counter stays 0 (lmco_deferred_overflows).
+#if !defined(__CUDACC__)
+inline long &deferred_overflow_count() { static long c = 0; return c; }
+#define LMC_DEFERRED_OVERFLOW() (++deferred_overflow_count())
+#else
+#define LMC_DEFERRED_OVERFLOW() ((void)0)
+#endif
+
 // SINK: void emit(const Ray &ray, float dist, int slot, int *flag)
 template <class SINK>
 struct DeferredList {
@@ -46,7 +59,7 @@ struct DeferredList {
             flag[n] = pend ? CAND_PENDING : CAND_VISIBLE;
             *np = n + 1;
             if (pend) sink->emit(pray, pdist, n, flag + n);
-        }
+        } else LMC_DEFERRED_OVERFLOW();
         pend = false;
     }
     // ConnectVertex of GeneratePathBidir: evaluated on the spot, or -- when the sink wants it
@@ -61,7 +74,7 @@ struct DeferredList {
                 flag[n] = CAND_OCCLUDED;
                 *np = n + 1;
                 sink->emit_connection(sc, camDepth, lgtDepth, n, ls, lgtVerts, cps, camVertex, screenPos, c + n, flag + n);
-            }
+            } else LMC_DEFERRED_OVERFLOW();
         } else {
             const SurfaceVertex lv = lgtVerts[lgtDepth];
             connect_vertex(sc, camDepth, lgtDepth, ls[lgtDepth], lv, cps, camVertex, screenPos, *this);
@@ -75,14 +88,14 @@ struct DeferredList {
                 flag[n] = CAND_PENDING | CAND_CLEAR;
                 *np = n + 1;
                 sink->emit(pray, pdist, n, flag + n);
-            }
+            } else LMC_DEFERRED_OVERFLOW();
             pend = false;
         } else {
             // unconditional clear: recorded as an already-visible CLEAR entry rather than by rewinding the
             // list, so that slots whose shadow rays are still in flight are never reused
             const int n = *np;
             if (n < cap) { flag[n] = CAND_VISIBLE | CAND_CLEAR; *np = n + 1; }
-            else *np = 0;
+            else { *np = 0; LMC_DEFERRED_OVERFLOW(); }
         }
     }
 };

@@ -62,6 +62,9 @@ __global__ void k_chain_init(ChainRec<MAXD> *states, int n, int chainBase, const
 #ifndef LMC_CHAIN_BLOCK
 #define LMC_CHAIN_BLOCK 128
 #endif
+#ifndef LMC_FINISH_MINB
+#define LMC_FINISH_MINB 1          // resident blocks per SM asked of k_wave_finish (1 = ptxas picks: 96 registers, 5 blocks)
+#endif
 
 // ---- wavefront execution of one chain-loop iteration -----------------------------------------
 // The iteration of src/mlt.cpp:91-170 is cut into the phases of core/mutation.h; every phase
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_PROP_MINB) k_wave_propose
 
 // Phase 4 of iteration k and, when THEN_BEGIN, phase 0 of iteration k + 1 in the same pass over the records
 template <int MAXD, int THEN_BEGIN>
-__global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_wave_finish(const __grid_constant__ Scene sc, RunParams rp, int chainBase,
+__global__ void __launch_bounds__(LMC_CHAIN_BLOCK, LMC_FINISH_MINB) k_wave_finish(const __grid_constant__ Scene sc, RunParams rp, int chainBase,
                                                                   ChainRec<MAXD> *states, int n, float *film, unsigned char *trace,
                                                                   float *aTrace, long long numSteps, long long stepInLaunch, H2mcSide *sides,
                                                                   WaveLists wl) {
@@ -500,11 +503,14 @@ __device__ __forceinline__ void rng_to_payload(const Rng &rng, TraceState &ts) {
 #ifndef LMC_SHADE_MINB
 #define LMC_SHADE_MINB 2
 #endif
+#ifndef LMC_START_MINB
+#define LMC_START_MINB LMC_SHADE_MINB
+#endif
 template <int MAXD> struct GenWorkT { typedef GenWork<MAXD, Limits<MAXD>::MAXC> type; };
 
 // first stage of every proposal: PRE part of the mutation + the statements up to the first ray
 template <int MAXD, int LARGE>
-__global__ void __launch_bounds__(LMC_SHADE_BLOCK, LMC_SHADE_MINB) k_prop_start(const __grid_constant__ Scene sc, int chainBase, ChainRec<MAXD> *states,
+__global__ void __launch_bounds__(LMC_SHADE_BLOCK, LMC_START_MINB) k_prop_start(const __grid_constant__ Scene sc, int chainBase, ChainRec<MAXD> *states,
                                                                  typename GenWorkT<MAXD>::type *genWork, const int *list, const int *countp,
                                                                  WaveQueues wq, H2mcSide *sides) {
     const int count = *countp;
@@ -637,7 +643,9 @@ __global__ void __launch_bounds__(LMC_SHADE_BLOCK, LMC_SHADE_MINB) k_shade(const
     const int stride = gridDim.x * blockDim.x;
     const int nextSet = curSet ^ 1;
     for (int base = blockIdx.x * blockDim.x; base < count; base += stride) {
+#ifndef LMC_SHADE_NOSYNC
         __syncthreads();          // keep the block's warps in the same stretch of code (instruction fetch)
+#endif
         const int t = base + threadIdx.x;
         bool more = false; int i = -1;
         Payload p;
@@ -1036,6 +1044,7 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
     const int sms = wc.smCount > 0 ? wc.smCount : 148;
     const int GSmax = (n + LMC_SHADE_BLOCK - 1) / LMC_SHADE_BLOCK;
     const int GS = GSmax < sms * LMC_SHADE_MINB ? GSmax : sms * LMC_SHADE_MINB;     // grid-stride kernels: one resident wave of CTAs
+    const int GSS = GSmax < sms * LMC_START_MINB ? GSmax : sms * LMC_START_MINB;
     const int GTmax = (n + LMC_TRACE_BLOCK - 1) / LMC_TRACE_BLOCK;
     const int GT = GTmax < sms * LMC_TRACE_MINB ? GTmax : sms * LMC_TRACE_MINB;     // persistent traversal warps
     const int maxDepth = sc.opt.maxDepth;
@@ -1059,7 +1068,8 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         }
         k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.small_, wl.curGrad, 2);
         if (sc.opt.h2mc) {
-            launch_wave_hess<MAXD>(st, sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide, GG, GH);
+            e = launch_wave_hess<MAXD>(st, sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide, GG, GH);
+            if (e != cudaSuccess) return e;
             *launches += 1;
         } else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.curGrad.list, wl.curGrad.count, 0, sides, wc.padSide);
         *launches += 3;
@@ -1073,9 +1083,9 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             if (e != cudaSuccess) return e;
             cudaStream_t sa = wc.aux ? wc.aux : st;
             if (wc.aux) { cudaEventRecord(wc.evFork, st); cudaStreamWaitEvent(wc.aux, wc.evFork, 0); }
-            k_prop_start<MAXD, 1><<<GS, LMC_SHADE_BLOCK, 0, sa>>>(sc, chainBase, states, genWork, wl.large, wl.largeCount, wq, sides);
+            k_prop_start<MAXD, 1><<<GSS, LMC_SHADE_BLOCK, 0, sa>>>(sc, chainBase, states, genWork, wl.large, wl.largeCount, wq, sides);
             if (wc.aux) cudaEventRecord(wc.evJoin, wc.aux);
-            k_prop_start<MAXD, 0><<<GS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wl.small_.list, wl.small_.count, wq, sides);
+            k_prop_start<MAXD, 0><<<GSS, LMC_SHADE_BLOCK, 0, st>>>(sc, chainBase, states, genWork, wl.small_.list, wl.small_.count, wq, sides);
             if (wc.aux) cudaStreamWaitEvent(st, wc.evJoin, 0);
             *launches += 2;
             pt.mark("prop_start");
@@ -1135,7 +1145,8 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         }
         k_sort_scatter<<<(n + 255) / 256, 256, 0, st>>>(n, wl.propGrad, wl.propGrad, 1);
         if (sc.opt.h2mc) {
-            launch_wave_hess<MAXD>(st, sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide, GG, GH);
+            e = launch_wave_hess<MAXD>(st, sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide, GG, GH);
+            if (e != cudaSuccess) return e;
             *launches += 1;
         } else k_wave_grad<MAXD, 1><<<GG, LMC_GRAD_BLOCK, 0, st>>>(sc, states, n, wl.propGrad.list, wl.propGrad.count, 1, sides, wc.padSide);
         pt.mark("sort + grad(prop)");

@@ -415,6 +415,8 @@ int lmco_deferred_probe(int nEvents, const int *type, const int *occl, float *ou
 
 // 1: lmco_run_chains runs every proposal through the staged (wavefront) path functions
 int lmco_use_staged(int enable) { g_staged = enable != 0; return 0; }
+// dropped DeferredList entries since load (core/stages.h capacity invariant): must stay 0
+long lmco_deferred_overflows() { return deferred_overflow_count(); }
 
 // plain bidirectional path tracing estimate of the image (sanity reference for the MLT film)
 int lmco_bdpt(void *h, int spp, int minDepth, float *film, int threads) {

@@ -28,8 +28,13 @@ def _run(oracle, xml, opts, chains, steps, staged, n_init=60000):
 ])
 def test_staged_equals_monolithic(oracle, torus_xml, door_xml, scene, opts, chains, steps):
     xml = torus_xml if scene == "torus" else door_xml
+    import ctypes
+    oracle.L.lmco_deferred_overflows.restype = ctypes.c_long
+    dropped0 = oracle.L.lmco_deferred_overflows()
     film0, tr0, a0, st0 = _run(oracle, xml, opts, chains, steps, False)
     film1, tr1, a1, st1 = _run(oracle, xml, opts, chains, steps, True)
+    # capacity invariant of DeferredList (core/stages.h): no candidate was ever dropped for lack of a slot
+    assert oracle.L.lmco_deferred_overflows() == dropped0
     assert np.array_equal(tr0, tr1)
     assert np.array_equal(a0.view(np.uint32), a1.view(np.uint32))
     assert np.array_equal(st0, st1)
