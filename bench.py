@@ -57,6 +57,9 @@ WORKLOADS = {
     "torus_h2mc_L8": dict(xml=os.path.join("torus", "h2mc.xml"), opts={"maxdepth": 8}, L=8, kind="h2mc",
                           text="torus, H2MC (Hessian preconditioner), maxdepth 8, 2^20 chains per GPU (BASELINE configs[3])"),
 }
+WORKLOADS["torus_lmc_L8_cache"] = dict(xml=os.path.join("torus", "lmc.xml"), opts={"maxdepth": 8, "globalcache": 1}, L=8, kind="lmc",
+                                       text="torus, LMC, maxdepth 8, 2^20 chains per GPU, global cache ON (the reference's own operating mode: "
+                                            "once a PSS dimension holds 3000 entries its chains query the cache instead of evaluating gradients)")
 HEADLINE = "torus_lmc_L8"
 # dram__bytes_read.sum + dram__bytes_write.sum of all kernels of one steady-state chain-loop iteration over 2^20 chains
 # (ncu launch list of this very command, profiles/r02_bench_launches.csv: 13.4 GB per 48-launch iteration), per mutation
@@ -343,13 +346,16 @@ def main():
     res = device_run(lmc, torch, dist, HEADLINE, n_local, M, K, W, rank, world, local, want_e2e=True)
     extra = {}
     if not args.no_extra_configs:
-        for name in ("door_lmc_L12", "torus_h2mc_L8"):
+        for name in ("door_lmc_L12", "torus_h2mc_L8", "torus_lmc_L8_cache"):
             m2 = max(4, M // 2)
             r2 = device_run(lmc, torch, dist, name, n_local, m2, 2, 1, rank, world, local, want_e2e=False)
             extra[name] = {"workload": WORKLOADS[name]["text"], "value": r2["value"], "unit": "mutations/s", "n_gpus": world,
                            "steps": 2, "warmup": 1, "mutations_per_step": m2, "ms_per_step": r2["ms"] / 2,
                            "gpu_launches": r2["launches"], "roofline": roofline(r2, name, n_local, m2, 2, peak, peak_src, world),
-                           "accepted": r2["stats"]["accepted"], "proposed": r2["stats"]["proposed"]}
+                           "accepted": r2["stats"]["accepted"], "proposed": r2["stats"]["proposed"],
+                           "gradient_evals": r2["stats"]["gradient_evals"]}
+            if WORKLOADS[name]["opts"].get("globalcache"):
+                extra[name].update({k: r2["stats"][k] for k in ("cache_queries", "cache_hits", "cache_count")})
 
         # the operating point of an actual render of this scene (profiles/r01_render_check.txt: 65 536 long chains keep the
         # start-up bias of the always-accepted first large step small): far fewer chains than the SMs can hold threads for

@@ -78,6 +78,18 @@ LMC_HD void chain_run(const Scene &sc, const RunParams &rp, int globalChainId, C
     cs.rngEpoch = rng.epoch;
 }
 
+// Bin the entries of a ready slot into the query grid (scene.h); the device form is k_cache_grid.
+inline void cache_grid_build_host(const GlobalCacheView &gc, int s) {
+    const int dim = 4 + 2 * s;
+    int *cellStart = gc.grid + (size_t)s * LMC_CACHE_GRID_INTS, *cursor = cellStart + LMC_CACHE_CELLS + 1, *entry = cursor + LMC_CACHE_CELLS;
+    const float *base = gc.data + cache_slot_offset(s);
+    for (int c = 0; c <= LMC_CACHE_CELLS; c++) cellStart[c] = 0;
+    for (int e = 0; e < LMC_CACHE_MAX_SIZE; e++) cellStart[cache_cell(base + (size_t)e * 3 * dim) + 1]++;
+    for (int c = 0; c < LMC_CACHE_CELLS; c++) { cellStart[c + 1] += cellStart[c]; cursor[c] = 0; }
+    for (int e = 0; e < LMC_CACHE_MAX_SIZE; e++) { const int c = cache_cell(base + (size_t)e * 3 * dim); entry[cellStart[c] + cursor[c]++] = e; }
+    gc.gridReady[s] = 1;
+}
+
 // Global cache: apply the push requests of ONE iteration in chain order (src/mlt.cpp:121-127 pushes under a mutex in
 // whatever order the threads arrive; here the order is defined: by chain id, all requests of an iteration after the
 // iteration).  Entries beyond PSS_MAX_SIZE are dropped (global_cache_t::push returns false once is_ready), a slot becomes
@@ -95,7 +107,10 @@ inline void cache_commit_host(const Scene &sc, ChainState<MAXD> *const *states, 
         for (int k = 0; k < dim; k++) { e[k] = ch.pss[k]; e[dim + k] = ch.v1[k]; e[2 * dim + k] = ch.v2[k]; }
         sc.gc.count[s] += 1;
     }
-    for (int s = 0; s < LMC_CACHE_SLOTS; s++) if (sc.gc.count[s] >= LMC_CACHE_MAX_SIZE) sc.gc.ready[s] = 1;
+    for (int s = 0; s < LMC_CACHE_SLOTS; s++) {
+        if (sc.gc.count[s] >= LMC_CACHE_MAX_SIZE) sc.gc.ready[s] = 1;
+        if (sc.gc.ready[s] && sc.gc.grid && !sc.gc.gridReady[s]) cache_grid_build_host(sc.gc, s);
+    }
 }
 
 }  // namespace lmc

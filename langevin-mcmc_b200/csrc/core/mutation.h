@@ -422,11 +422,37 @@ LMC_HD bool cache_query(const Scene &sc, int dim, const float *pss, float *v1, f
     const int stride = 3 * dim;
     const float radius = (float)dim * (LMC_CACHE_QUERY_DIST * LMC_CACHE_QUERY_DIST);
     int idx[LMC_CACHE_KNN]; float dist[LMC_CACHE_KNN]; int found = 0;
-    for (int e = 0; e < LMC_CACHE_MAX_SIZE && found < LMC_CACHE_KNN; e++) {
-        const float *q = base + (size_t)e * stride;
-        float d = 0.0f;
-        for (int j = 0; j < dim; j++) { const float t = pss[j] - q[j]; d += t * t; }
-        if (d < radius) { idx[found] = e; dist[found] = d; found++; }
+    if (sc.gc.grid && sc.gc.gridReady[s]) {
+        // the 27 cells around the query; keep the LMC_CACHE_KNN in-radius entries with the smallest insertion index,
+        // in ascending order -- exactly what the linear scan below finds
+        const int *cellStart = sc.gc.grid + (size_t)s * LMC_CACHE_GRID_INTS;
+        const int *entry = cellStart + 2 * LMC_CACHE_CELLS + 1;
+        const int c0 = cache_cell_coord(pss[0]), c1 = cache_cell_coord(pss[1]), c2 = cache_cell_coord(pss[2]);
+        const int G = LMC_CACHE_GRID;
+        for (int a = (c0 > 0 ? c0 - 1 : 0); a <= (c0 < G - 1 ? c0 + 1 : G - 1); a++)
+            for (int b = (c1 > 0 ? c1 - 1 : 0); b <= (c1 < G - 1 ? c1 + 1 : G - 1); b++) {
+                const int row = (a * G + b) * G;
+                const int p0 = cellStart[row + (c2 > 0 ? c2 - 1 : 0)], p1 = cellStart[row + (c2 < G - 1 ? c2 + 1 : G - 1) + 1];
+                for (int p = p0; p < p1; p++) {         // the three cells along the last axis are contiguous
+                    const int e = entry[p];
+                    const float *q = base + (size_t)e * stride;
+                    float d = 0.0f;
+                    for (int j = 0; j < dim; j++) { const float t = pss[j] - q[j]; d += t * t; }
+                    if (!(d < radius)) continue;
+                    int k = found < LMC_CACHE_KNN ? found : LMC_CACHE_KNN - 1;
+                    if (found == LMC_CACHE_KNN && e > idx[k]) continue;
+                    while (k > 0 && idx[k - 1] > e) { idx[k] = idx[k - 1]; dist[k] = dist[k - 1]; k--; }
+                    idx[k] = e; dist[k] = d;
+                    if (found < LMC_CACHE_KNN) found++;
+                }
+            }
+    } else {
+        for (int e = 0; e < LMC_CACHE_MAX_SIZE && found < LMC_CACHE_KNN; e++) {
+            const float *q = base + (size_t)e * stride;
+            float d = 0.0f;
+            for (int j = 0; j < dim; j++) { const float t = pss[j] - q[j]; d += t * t; }
+            if (d < radius) { idx[found] = e; dist[found] = d; found++; }
+        }
     }
     if (!found) return false;
     double sum_w = 0.0;

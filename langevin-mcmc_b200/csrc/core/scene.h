@@ -140,11 +140,27 @@ struct Options {                 // src/dptoptions.h:7-34 + compile-time constan
 #define LMC_CACHE_QUERY_DIST 0.01f       // PSS_QUERY_DIST
 #define LMC_CACHE_REUSE_DIST 0.10f       // PSS_REUSE_DIST
 #define LMC_CACHE_KNN 5
+// A ready slot is read-only (global_cache_t::push refuses once is_ready), so its 3000 entries are binned ONCE into a
+// uniform grid over the first three PSS coordinates: cell size 1/24 >= the largest query radius 0.01 * sqrt(12), hence
+// every entry within the radius of a query lies in the 3 x 3 x 3 cells around the query's cell and a query tests ~6
+// entries instead of 3000 (the reference walks a KD-tree, nanoflann).  Same result as the linear scan by construction.
+#define LMC_CACHE_GRID 24
+#define LMC_CACHE_CELLS (LMC_CACHE_GRID * LMC_CACHE_GRID * LMC_CACHE_GRID)
+#define LMC_CACHE_GRID_INTS (2 * LMC_CACHE_CELLS + 1 + LMC_CACHE_MAX_SIZE)     // cellStart[CELLS + 1], cursor[CELLS], entry[MAX_SIZE]
 struct GlobalCacheView {
     float *data;     // slot s (D = 4 + 2 s) starts at cache_slot_offset(s); entry e = 3 D floats: pss, v1, v2
     int *count;      // [LMC_CACHE_SLOTS] entries stored
     int *ready;      // [LMC_CACHE_SLOTS] is_ready
+    int *grid;       // [LMC_CACHE_SLOTS][LMC_CACHE_GRID_INTS] (may be null: linear scan)
+    int *gridReady;  // [LMC_CACHE_SLOTS] the slot's grid has been built
 };
+LMC_HD int cache_cell_coord(float x) {
+    const int c = (int)(x * (float)LMC_CACHE_GRID);
+    return c < 0 ? 0 : (c > LMC_CACHE_GRID - 1 ? LMC_CACHE_GRID - 1 : c);
+}
+LMC_HD int cache_cell(const float *pss) {
+    return (cache_cell_coord(pss[0]) * LMC_CACHE_GRID + cache_cell_coord(pss[1])) * LMC_CACHE_GRID + cache_cell_coord(pss[2]);
+}
 LMC_HD int cache_slot(int dim) { return (dim >= 4 && dim <= 12 && (dim & 1) == 0) ? (dim - 4) / 2 : -1; }
 LMC_HD int cache_slot_offset(int s) {        // floats before slot s: 3000 * 3 * sum_{k<s} (4 + 2k)
     return LMC_CACHE_MAX_SIZE * 3 * (4 * s + s * (s - 1));

@@ -955,6 +955,30 @@ __global__ void __launch_bounds__(LMC_CACHE_BLOCK) k_cache_write(const __grid_co
     }
 }
 
+// k_cache_grid    block s: once slot s is ready (and its last entries are written), bin its entries into the query grid
+//                 of scene.h (counts by atomics, serial prefix sum over the 13 824 cells, fill by atomic cursors; the
+//                 query does not depend on the order inside a cell).  Runs once per slot and job; otherwise returns at once.
+static __global__ void __launch_bounds__(256) k_cache_grid(GlobalCacheView gc) {
+    const int s = blockIdx.x;
+    if (!gc.grid || !gc.ready[s] || gc.gridReady[s]) return;
+    const int dim = 4 + 2 * s;
+    int *cellStart = gc.grid + (size_t)s * LMC_CACHE_GRID_INTS, *cursor = cellStart + LMC_CACHE_CELLS + 1, *entry = cursor + LMC_CACHE_CELLS;
+    const float *base = gc.data + cache_slot_offset(s);
+    for (int c = threadIdx.x; c <= LMC_CACHE_CELLS; c += blockDim.x) cellStart[c] = 0;
+    for (int c = threadIdx.x; c < LMC_CACHE_CELLS; c += blockDim.x) cursor[c] = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < LMC_CACHE_MAX_SIZE; e += blockDim.x) atomicAdd(&cellStart[cache_cell(base + (size_t)e * 3 * dim) + 1], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) for (int c = 0; c < LMC_CACHE_CELLS; c++) cellStart[c + 1] += cellStart[c];
+    __syncthreads();
+    for (int e = threadIdx.x; e < LMC_CACHE_MAX_SIZE; e += blockDim.x) {
+        const int c = cache_cell(base + (size_t)e * 3 * dim);
+        entry[cellStart[c] + atomicAdd(&cursor[c], 1)] = e;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); gc.gridReady[s] = 1; }
+}
+
 // launchers (defined by LMC_INSTANTIATE_CHAIN in chain_inst_*.cu)
 #ifndef LMC_WAVEFRONT_MIN_CHAINS
 #define LMC_WAVEFRONT_MIN_CHAINS 393216     // measured crossover on B200 (torus, maxdepth 8): 2^18 -> monolithic, 2^19 -> wavefront
@@ -1162,6 +1186,8 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             k_cache_count<MAXD><<<CB, LMC_CACHE_BLOCK, 0, st>>>(sc, states, n, wc.cacheBlockCounts);
             k_cache_scan<<<1, 1024, 0, st>>>(sc.gc, wc.cacheBlockCounts, CB, active);
             k_cache_write<MAXD><<<CB, LMC_CACHE_BLOCK, 0, st>>>(sc, states, n, wc.cacheBlockCounts, active);
+            k_cache_grid<<<LMC_CACHE_SLOTS, 256, 0, st>>>(sc.gc);
+            *launches += 1;
             if (k + 1 < numSteps) k_wave_begin<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl);
             *launches += 4;
         } else if (k + 1 < numSteps) k_wave_finish<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides, wl);

@@ -124,7 +124,8 @@ struct lmc_ctx {
     uint64_t launches = 0;
     double lastMs = 0.0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float *cacheData = nullptr; int *cacheInts = nullptr;       // global cache (option globalcache): entries; count[5] + ready[5]
+    float *cacheData = nullptr; int *cacheInts = nullptr;       // global cache (option globalcache): entries; count[5] + ready[5] + gridReady[5]
+    int *cacheGrid = nullptr;                                   // query grids of the ready slots (scene.h LMC_CACHE_GRID_INTS per slot)
     int *cacheBlockCounts = nullptr; int cacheBlockCap = 0;
     ncclComm_t comm = nullptr;      // film all-reduce (lmc_create_multi / lmc_comm_init_rank); NULL for a lone ctx
 };
@@ -207,7 +208,7 @@ int chains_begin(lmc_ctx *c) {
     if (c->sc.opt.cacheEnabled) {
         // a fresh cache for every job (GlobalCache globalCache; src/mlt.cpp:53)
         CK(cudaMemsetAsync(c->cacheData, 0, sizeof(float) * (size_t)LMC_CACHE_FLOATS, c->stream));
-        CK(cudaMemsetAsync(c->cacheInts, 0, sizeof(int) * 2 * LMC_CACHE_SLOTS, c->stream));
+        CK(cudaMemsetAsync(c->cacheInts, 0, sizeof(int) * 3 * LMC_CACHE_SLOTS, c->stream));
         const int need = LMC_CACHE_SLOTS * ((n + LMC_CACHE_BLOCK - 1) / LMC_CACHE_BLOCK) + 1;
         if (c->cacheBlockCap < need) {
             if (c->cacheBlockCounts) { cudaFree(c->cacheBlockCounts); c->cacheBlockCounts = nullptr; }
@@ -409,14 +410,16 @@ int lmc_create(const lmc_scene *scene, int32_t device, lmc_ctx **out) {
     UP(d.env.image, s.envImage, float); UP(d.env.cdfRows, s.envCdfRows, float); UP(d.env.cdfCols, s.envCdfCols, float);
     UP(d.env.rowWeights, s.envRowWeights, float);
 #undef UP
-    d.gc.data = nullptr; d.gc.count = nullptr; d.gc.ready = nullptr;
+    d.gc.data = nullptr; d.gc.count = nullptr; d.gc.ready = nullptr; d.gc.grid = nullptr; d.gc.gridReady = nullptr;
     if (d.opt.cacheEnabled) {
         if (cudaMalloc((void **)&c->cacheData, sizeof(float) * (size_t)LMC_CACHE_FLOATS) != cudaSuccess ||
-            cudaMalloc((void **)&c->cacheInts, sizeof(int) * 2 * LMC_CACHE_SLOTS) != cudaSuccess) {
+            cudaMalloc((void **)&c->cacheInts, sizeof(int) * 3 * LMC_CACHE_SLOTS) != cudaSuccess ||
+            cudaMalloc((void **)&c->cacheGrid, sizeof(int) * (size_t)LMC_CACHE_SLOTS * LMC_CACHE_GRID_INTS) != cudaSuccess) {
             lmc_destroy(c);
             return fail(LMC_ERR_CUDA, "device allocation failed (global cache)");
         }
         d.gc.data = c->cacheData; d.gc.count = c->cacheInts; d.gc.ready = c->cacheInts + LMC_CACHE_SLOTS;
+        d.gc.gridReady = c->cacheInts + 2 * LMC_CACHE_SLOTS; d.gc.grid = c->cacheGrid;
     }
     const size_t filmBytes = (size_t)d.cam.width * d.cam.height * 3 * sizeof(float);
     if (cudaMalloc((void **)&c->film, filmBytes) != cudaSuccess || cudaMemset(c->film, 0, filmBytes) != cudaSuccess ||
@@ -456,6 +459,7 @@ void lmc_destroy(lmc_ctx *c) {
     if (c->statsDev) cudaFree(c->statsDev);
     if (c->cacheData) cudaFree(c->cacheData);
     if (c->cacheInts) cudaFree(c->cacheInts);
+    if (c->cacheGrid) cudaFree(c->cacheGrid);
     if (c->cacheBlockCounts) cudaFree(c->cacheBlockCounts);
     if (c->listMem) cudaFree(c->listMem);
     if (c->sides) cudaFree(c->sides);

@@ -61,6 +61,7 @@ struct HostFilm {
 };
 
 bool g_useRef = false;
+bool g_cacheGrid = true;   // global-cache queries through the grid (what the device does); false = the linear scan it must equal
 bool g_staged = false;     // run the proposal phase through the staged path functions (core/stages.h)
 template <int MAXD>
 void run_chains_t(const Scene &sc, int numChains, int chainBase, int totalChains, long long numSteps,
@@ -114,8 +115,10 @@ void run_chains_cache_t(Scene sc, int numChains, int chainBase, int totalChains,
     RunParams rp; rp.normalization = normalization; rp.numChains = totalChains;
     rp.numSamplesThisChain = numSamplesThisChain; rp.initLsScore = initLs;
     std::vector<float> data(LMC_CACHE_FLOATS, 0.0f);
-    int count[LMC_CACHE_SLOTS] = {0}, ready[LMC_CACHE_SLOTS] = {0};
+    int count[LMC_CACHE_SLOTS] = {0}, ready[LMC_CACHE_SLOTS] = {0}, gridReady[LMC_CACHE_SLOTS] = {0};
+    std::vector<int> grid((size_t)LMC_CACHE_SLOTS * LMC_CACHE_GRID_INTS, 0);
     sc.gc.data = data.data(); sc.gc.count = count; sc.gc.ready = ready;
+    sc.gc.grid = g_cacheGrid ? grid.data() : nullptr; sc.gc.gridReady = gridReady;     // lmco_cache_use_grid(0): linear scan
     const int W = sc.cam.width, H = sc.cam.height;
     if (threads < 1) threads = 1;
     std::vector<ChainState<MAXD> *> cs(numChains);
@@ -534,8 +537,17 @@ int lmco_cache_query(int dim, const float *entries, const float *pss, float *v1,
     count[s] = LMC_CACHE_MAX_SIZE; ready[s] = 1;
     Scene sc; memset(&sc, 0, sizeof(sc));
     sc.opt.cacheEnabled = 1; sc.gc.data = data.data(); sc.gc.count = count; sc.gc.ready = ready;
+    std::vector<int> grid; int gridReady[LMC_CACHE_SLOTS] = {0};
+    sc.gc.gridReady = gridReady;
+    if (g_cacheGrid) {
+        grid.assign((size_t)LMC_CACHE_SLOTS * LMC_CACHE_GRID_INTS, 0);
+        sc.gc.grid = grid.data();
+        cache_grid_build_host(sc.gc, s);
+    }
     return cache_query(sc, dim, pss, v1, v2) ? 1 : 0;
 }
+// 1 (default): global-cache queries go through the uniform grid of core/scene.h, as on the device; 0: the linear scan
+int lmco_cache_use_grid(int enable) { g_cacheGrid = enable != 0; return 0; }
 int lmco_scene_serialized(void *h, float *out38) { memcpy(out38, ((OScene *)h)->store.head.sceneSer, 38 * sizeof(float)); return 0; }
 
 // RNG streams from a fresh RNG(seed) each: raw 32-bit draws, uniform_real_distribution<float>(0,1),

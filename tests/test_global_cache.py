@@ -24,6 +24,37 @@ def numpy_query(entries, dim, pss):
     return v1, v2
 
 
+def test_grid_query_equals_linear_scan(oracle):
+    """The query grid over the first three PSS coordinates (core/scene.h; the reference walks a KD-tree) returns exactly
+    what the linear scan returns: clustered entries so that many queries have 1 .. > 5 neighbours, queries on cell borders
+    and outside [0, 1)."""
+    rng = np.random.default_rng(5)
+    for dim in (6, 10, 12):
+        centres = rng.uniform(0.0, 1.0, size=(40, dim)).astype(np.float32)
+        entries = rng.uniform(0, 1, size=(3000, 3, dim)).astype(np.float32)
+        for i in range(1500):                                     # half of the entries in tight clusters
+            entries[i, 0, :] = centres[i % 40] + rng.normal(size=dim).astype(np.float32) * np.float32(0.006)
+        flat = np.ascontiguousarray(entries.reshape(-1))
+        hits = 0
+        queries = [centres[k % 40] + rng.normal(size=dim).astype(np.float32) * np.float32(0.005) for k in range(200)]
+        queries += [np.round(centres[k] * 24).astype(np.float32) / np.float32(24) for k in range(20)]      # on cell borders
+        queries += [np.full(dim, -0.01, np.float32), np.full(dim, 1.01, np.float32)]
+        for q in queries:
+            q = np.ascontiguousarray(q, np.float32)
+            out = {}
+            for grid in (1, 0):
+                oracle.L.lmco_cache_use_grid(grid)
+                v1 = np.zeros(dim, np.float32); v2 = np.zeros(dim, np.float32)
+                rc = oracle.L.lmco_cache_query(dim, oracle.p(flat), oracle.p(q), oracle.p(v1), oracle.p(v2))
+                out[grid] = (rc, v1, v2)
+            oracle.L.lmco_cache_use_grid(1)
+            assert out[0][0] == out[1][0]
+            assert np.array_equal(out[0][1].view(np.uint32), out[1][1].view(np.uint32))
+            assert np.array_equal(out[0][2].view(np.uint32), out[1][2].view(np.uint32))
+            hits += out[1][0]
+        assert hits > 100
+
+
 @pytest.mark.parametrize("dim", [6, 8, 12])
 def test_cache_query_semantics(oracle, dim):
     rng = np.random.default_rng(dim)
@@ -78,6 +109,13 @@ def test_oracle_cache_fills_and_replaces_gradients(oracle):
     first_diff = int((tr == tr0).all(axis=0).argmin())
     assert first_diff > 10 and np.array_equal(tr[:, :first_diff], tr0[:, :first_diff])
     assert abs(float(f.sum()) - float(f0.sum())) < 0.02 * float(f0.sum())
+    # ready slots are queried through the grid; the linear scan gives the same chains
+    oracle.L.lmco_cache_use_grid(0)
+    try:
+        (f3, tr3, a3, st3), _ = _cache_run(oracle, chains, steps, 8)
+    finally:
+        oracle.L.lmco_cache_use_grid(1)
+    assert np.array_equal(tr, tr3) and np.array_equal(a.view(np.uint32), a3.view(np.uint32)) and np.array_equal(st, st3)
     # the fill order is defined (chain order per iteration): independent of the number of worker threads
     (f2, tr2, a2, st2), _ = _cache_run(oracle, chains, steps, 3)
     assert np.array_equal(tr, tr2) and np.array_equal(a.view(np.uint32), a2.view(np.uint32))

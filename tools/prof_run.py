@@ -11,6 +11,9 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 launches = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 sc = m.ParseScene(os.path.join(ROOT, "scenes", os.environ.get("LMC_SCENE", "torus/lmc.xml")))
 sc.options["maxdepth"] = int(os.environ.get("LMC_MAXDEPTH", "8"))
+for kv in filter(None, os.environ.get("LMC_OPTS", "").split(",")):      # e.g. LMC_OPTS=globalcache=1,adjointcompat=0
+    k, v = kv.split("=")
+    sc.options[k] = float(v)
 chains = 1 << lg
 norm, init_small = m.MLTInit(sc, 300000, min(chains, 8192), 32)
 init_ls = np.resize(init_small, chains)
