@@ -9,8 +9,8 @@
 //     (k_wave_grad<2>) has just served, so this kernel walks the same list -- 16 lanes per entry;
 //   * A and V sit in shared memory with row stride 17 (rows and columns are both conflict-free);
 //   * the Jacobi rotations run in the parallel (round-robin) order of core/mutation.h: the n / 2 disjoint pairs of a
-//     round get their angles from lanes 0 .. n/2-1, then the 16 lanes share the (pair, row) work items of the column
-//     phase and of the row phase;
+//     round get their angles from lanes 0 .. n/2-1, then lane l applies all of them to row l (column phase, A and V)
+//     and to column l (row phase) -- no index arithmetic in the hot loops, no bank conflicts;
 //   * norms, convergence tests and dot products are xor-shuffle trees over the 16 lanes (group_tree16 == tree16).
 // Statement for statement this is h2mc_compute_gaussian + jacobi_eigen of core/mutation.h, so the result is bit-identical
 // to the host twin (tests/test_h2mc.py); the chain kernels find the Gaussian built (StepScratch::need*Grad == 2).
@@ -100,27 +100,31 @@ __global__ void __launch_bounds__(LMC_H2MC_BLOCK) k_h2mc_gaussian(const __grid_c
                         S.p[l] = rot ? p : -1; S.q[l] = q; S.c[l] = c; S.s[l] = sn;
                     }
                     __syncwarp(mask);
-                    for (int item = l; item < (n / 2) * n; item += 16) {         // columns p, q of A and of V
-                        const int i = item / n, k = item % n;
-                        const int p = S.p[i];
-                        if (p < 0) continue;
-                        const int q = S.q[i]; const float c = S.c[i], sn = S.s[i];
-                        const float akp = S.A[k * LD + p], akq = S.A[k * LD + q];
-                        S.A[k * LD + p] = c * akp - sn * akq;
-                        S.A[k * LD + q] = sn * akp + c * akq;
-                        const float vkp = S.V[k * LD + p], vkq = S.V[k * LD + q];
-                        S.V[k * LD + p] = c * vkp - sn * vkq;
-                        S.V[k * LD + q] = sn * vkp + c * vkq;
+                    // lane l owns row l in the column phase and column l in the row phase (both conflict-free with the
+                    // stride-17 rows) and walks the round's pairs: no index arithmetic in the hot loops
+                    if (l < n) {
+                        for (int i = 0; i < n / 2; i++) {                        // columns p, q of A and of V, row l
+                            const int p = S.p[i];
+                            if (p < 0) continue;
+                            const int q = S.q[i]; const float c = S.c[i], sn = S.s[i];
+                            const float akp = S.A[l * LD + p], akq = S.A[l * LD + q];
+                            S.A[l * LD + p] = c * akp - sn * akq;
+                            S.A[l * LD + q] = sn * akp + c * akq;
+                            const float vkp = S.V[l * LD + p], vkq = S.V[l * LD + q];
+                            S.V[l * LD + p] = c * vkp - sn * vkq;
+                            S.V[l * LD + q] = sn * vkp + c * vkq;
+                        }
                     }
                     __syncwarp(mask);
-                    for (int item = l; item < (n / 2) * n; item += 16) {         // rows p, q
-                        const int i = item / n, k = item % n;
-                        const int p = S.p[i];
-                        if (p < 0) continue;
-                        const int q = S.q[i]; const float c = S.c[i], sn = S.s[i];
-                        const float apk = S.A[p * LD + k], aqk = S.A[q * LD + k];
-                        S.A[p * LD + k] = c * apk - sn * aqk;
-                        S.A[q * LD + k] = sn * apk + c * aqk;
+                    if (l < n) {
+                        for (int i = 0; i < n / 2; i++) {                        // rows p, q, column l
+                            const int p = S.p[i];
+                            if (p < 0) continue;
+                            const int q = S.q[i]; const float c = S.c[i], sn = S.s[i];
+                            const float apk = S.A[p * LD + l], aqk = S.A[q * LD + l];
+                            S.A[p * LD + l] = c * apk - sn * aqk;
+                            S.A[q * LD + l] = sn * apk + c * aqk;
+                        }
                     }
                     __syncwarp(mask);
                 }
