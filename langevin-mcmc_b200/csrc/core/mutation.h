@@ -123,6 +123,8 @@ struct ChainVars {               // Chain (src/mutation.h:28-43) + per-chain loo
     int queried;
     int cacheQueries, cacheHits;      // statistics: global_cache_t::query calls / calls that found a neighbour
     int pushDim;                      // > 0: this chain asks for a push of (pss, v1, v2) into the cache of that dimension
+    int preq;                         // device only: the proposal's cache query of this iteration has been answered by the
+                                      // warp-cooperative k_cache_prequery (1 = no neighbour, 2 = v1 / v2 already averaged in)
 };
 
 template <int MAXD>
@@ -132,7 +134,7 @@ LMC_HD void chain_vars_init(ChainVars<MAXD> &c) {
     }
     c.buffered = 0; c.t = 0; c.lastScoreSum = 1.0f; c.lastScore = 1.0f; c.adjacentReject = 0; c.lastMutationType = MUT_LARGE; c.outlierResets = 0;
     for (int i = 0; i < Limits<MAXD>::DIM; i++) { c.pss[i] = 0; c.last_pss[i] = 0; }
-    c.pathWeight = 0.0f; c.queried = 0; c.pushDim = 0; c.cacheQueries = 0; c.cacheHits = 0;
+    c.pathWeight = 0.0f; c.queried = 0; c.pushDim = 0; c.cacheQueries = 0; c.cacheHits = 0; c.preq = 0;
 }
 
 // Film accumulation (src/image.h:66-77).  FILM is a functor add(pixelIndex, channel, value)
@@ -415,6 +417,25 @@ LMC_HD int mala_grad_mode(const Scene &sc, const MarkovState<MAXD> &st) {
 // most LMC_CACHE_KNN of them: the reference's patched nanoflann stops its KD-tree walk after 5 in-radius points
 // (nanoflann.hpp:256-262), i.e. which 5 it keeps depends on the tree; here they are the first 5 in INSERTION order --
 // averaged with weights 1 / (dist^2 + 1e-6), dist being the SQUARED distance nanoflann reports.
+// the weighted average over the (at most LMC_CACHE_KNN) neighbours, in ascending insertion order
+LMC_HD void cache_average(const float *base, int dim, int found, const int *idx, const float *dist, float *v1, float *v2) {
+    const int stride = 3 * dim;
+    double sum_w = 0.0;
+    for (int i = 0; i < dim; i++) { v1[i] = 0.0f; v2[i] = 0.0f; }
+    for (int k = 0; k < found; k++) {
+        const float *q = base + (size_t)idx[k] * stride;
+        const float w = 1.0f / (dist[k] * dist[k] + 1e-6f);
+        for (int i = 0; i < dim; i++) { v1[i] += q[dim + i] * w; v2[i] += q[2 * dim + i] * w; }
+        sum_w += (double)w;
+    }
+    for (int i = 0; i < dim; i++) { v1[i] = (float)((double)v1[i] / sum_w); v2[i] = (float)((double)v2[i] / sum_w); }
+}
+LMC_HD bool cache_reuse(int dim, int queried, const float *pss, const float *last_pss) {      // src/mutation_mala.h:222-232
+    if (!queried) return false;
+    float dist_sqr = 0.0f;
+    for (int i = 0; i < dim; i++) { const float diff = pss[i] - last_pss[i]; dist_sqr += diff * diff; }
+    return dist_sqr < (float)dim * (LMC_CACHE_REUSE_DIST * LMC_CACHE_REUSE_DIST);
+}
 LMC_HD bool cache_query(const Scene &sc, int dim, const float *pss, float *v1, float *v2) {
     const int s = cache_slot(dim);
     if (s < 0 || !sc.gc.ready[s]) return false;
@@ -455,15 +476,7 @@ LMC_HD bool cache_query(const Scene &sc, int dim, const float *pss, float *v1, f
         }
     }
     if (!found) return false;
-    double sum_w = 0.0;
-    for (int i = 0; i < dim; i++) { v1[i] = 0.0f; v2[i] = 0.0f; }
-    for (int k = 0; k < found; k++) {
-        const float *q = base + (size_t)idx[k] * stride;
-        const float w = 1.0f / (dist[k] * dist[k] + 1e-6f);
-        for (int i = 0; i < dim; i++) { v1[i] += q[dim + i] * w; v2[i] += q[2 * dim + i] * w; }
-        sum_w += (double)w;
-    }
-    for (int i = 0; i < dim; i++) { v1[i] = (float)((double)v1[i] / sum_w); v2[i] = (float)((double)v2[i] / sum_w); }
+    cache_average(base, dim, found, idx, dist, v1, v2);
     return true;
 }
 
@@ -493,15 +506,13 @@ LMC_HD_NOINLINE void mala_finish_gaussian(const Scene &sc, const MarkovState<MAX
     }
     if (mode == 0) { isotropic_gaussian(dim, sc.opt.malaStdDev, out); return; }
     if (mode == 3) {                // src/mutation_mala.h:131-161 / 221-252
-        bool reuse = false;
-        if (ch.queried) {
-            float dist_sqr = 0.0f;
-            for (int i = 0; i < dim; i++) { const float diff = ch.pss[i] - ch.last_pss[i]; dist_sqr += diff * diff; }
-            if (dist_sqr < (float)dim * (LMC_CACHE_REUSE_DIST * LMC_CACHE_REUSE_DIST)) reuse = true;
-        }
+        const bool reuse = cache_reuse(dim, ch.queried, ch.pss, ch.last_pss);
         if (!reuse) {
             ch.cacheQueries += 1;
-            if (!cache_query(sc, dim, ch.pss, ch.v1, ch.v2)) { isotropic_gaussian(dim, sc.opt.malaStdDev, out); return; }
+            bool hit;
+            if (ch.preq) { hit = ch.preq == 2; ch.preq = 0; }       // answered ahead by k_cache_prequery (same statements, 32 lanes per query)
+            else hit = cache_query(sc, dim, ch.pss, ch.v1, ch.v2);
+            if (!hit) { isotropic_gaussian(dim, sc.opt.malaStdDev, out); return; }
             ch.cacheHits += 1;
             ch.queried = 1;
             for (int i = 0; i < dim; i++) ch.last_pss[i] = ch.pss[i];
@@ -542,6 +553,7 @@ template <int MAXD>
 LMC_HD void phase_begin(const Scene &sc, const RunParams &rp, long long sampleIdx, MarkovState<MAXD> &cur,
                         ChainVars<MAXD> &ch, Rng &rng, StepScratch<MAXD> &ss) {
     ss.needCurGrad = 0; ss.needPropGrad = 0; ss.hasContrib = 0; ss.a = 1.0f;
+    ch.preq = 0;
     const float lsScale = ((float)sampleIdx > (float)rp.numSamplesThisChain * sc.opt.lsRatio) ? sc.opt.largeStepProbScale : 1.0f;
     if (!cur.valid || rng_uniform(rng) < sc.opt.largeStepProbability * lsScale) { ss.kind = STEP_LARGE; return; }
     if (!sc.opt.mala && !sc.opt.h2mc) { ss.kind = STEP_ISO; return; }

@@ -979,6 +979,101 @@ static __global__ void __launch_bounds__(256) k_cache_grid(GlobalCacheView gc) {
     if (threadIdx.x == 0) { __threadfence(); gc.gridReady[s] = 1; }
 }
 
+// k_cache_prequery   the cache query of every proposal that k_wave_finish is about to look up (MALA step with a
+//                 contribution, dimension ready, no reuse: the conditions of core/mutation.h mala_finish_gaussian), answered
+//                 by a WARP per query: a thread-per-chain query runs as long as the densest cell neighbourhood among its 32
+//                 lanes (the PSS entries cluster: 50 .. 500 candidates), here the 32 lanes test 32 candidates at a time.
+//                 In-radius entries go to a per-warp shared list; the owner lane keeps the LMC_CACHE_KNN smallest insertion
+//                 indices, averages (cache_average) into chain.v1 / v2 and leaves ChainVars::preq = 2 (hit) or 1 (miss) for
+//                 the finish kernel -- bit-identical to the inline query.  A list overflow leaves preq = 0 (inline query).
+#define LMC_PREQ_CAP 64
+template <int MAXD>
+__global__ void __launch_bounds__(256) k_cache_prequery(const __grid_constant__ Scene sc, ChainRec<MAXD> *states, int n) {
+    const int DIM = Limits<MAXD>::DIM;
+    __shared__ int sIdx[8][LMC_PREQ_CAP];
+    __shared__ float sDist[8][LMC_PREQ_CAP];
+    __shared__ int sCnt[8];
+    if (!sc.gc.grid) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool need = false; int dim = 0, slot = -1;
+    float pss[DIM];
+    for (int j = 0; j < DIM; j++) pss[j] = 0.0f;
+    if (i < n) {
+        const ChainState<MAXD> &cs = states[i].cs;
+        if (cs.ss.kind == STEP_MALA && cs.ss.hasContrib) {
+            const MarkovState<MAXD> &prop = cs.st[cs.curIdx ^ 1];
+            if (mala_grad_mode(sc, prop) == 3) {
+                dim = path_dimension(prop.path);
+                slot = cache_slot(dim);
+                get_path_pss(prop.path, pss);
+                need = slot >= 0 && sc.gc.gridReady[slot] && !cache_reuse(dim, cs.ch.queried, pss, cs.ch.last_pss);
+            }
+        }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, need);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int d = __shfl_sync(0xffffffffu, dim, src), s = __shfl_sync(0xffffffffu, slot, src);
+        float q[DIM];
+#pragma unroll
+        for (int j = 0; j < DIM; j++) q[j] = __shfl_sync(0xffffffffu, pss[j], src);
+        const float *base = sc.gc.data + cache_slot_offset(s);
+        const int stride = 3 * d;
+        const float radius = (float)d * (LMC_CACHE_QUERY_DIST * LMC_CACHE_QUERY_DIST);
+        const int *cellStart = sc.gc.grid + (size_t)s * LMC_CACHE_GRID_INTS;
+        const int *entry = cellStart + 2 * LMC_CACHE_CELLS + 1;
+        const int c0 = cache_cell_coord(q[0]), c1 = cache_cell_coord(q[1]), c2 = cache_cell_coord(q[2]);
+        const int G = LMC_CACHE_GRID;
+        if (lane == 0) sCnt[warp] = 0;
+        __syncwarp();
+        for (int a = (c0 > 0 ? c0 - 1 : 0); a <= (c0 < G - 1 ? c0 + 1 : G - 1); a++)
+            for (int b = (c1 > 0 ? c1 - 1 : 0); b <= (c1 < G - 1 ? c1 + 1 : G - 1); b++) {
+                const int row = (a * G + b) * G;
+                const int p0 = cellStart[row + (c2 > 0 ? c2 - 1 : 0)], p1 = cellStart[row + (c2 < G - 1 ? c2 + 1 : G - 1) + 1];
+                for (int pb = p0; pb < p1; pb += 32) {
+                    const int p = pb + lane;
+                    bool hit = false; int e = 0; float dd = 0.0f;
+                    if (p < p1) {
+                        e = entry[p];
+                        const float *x = base + (size_t)e * stride;
+#pragma unroll
+                        for (int j = 0; j < DIM; j++) if (j < d) { const float t = q[j] - x[j]; dd += t * t; }
+                        hit = dd < radius;
+                    }
+                    const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                    if (hm) {
+                        const int at = sCnt[warp] + __popc(hm & ((1u << lane) - 1u));
+                        if (hit && at < LMC_PREQ_CAP) { sIdx[warp][at] = e; sDist[warp][at] = dd; }
+                        __syncwarp();
+                        if (lane == 0) sCnt[warp] += __popc(hm);
+                        __syncwarp();
+                    }
+                }
+            }
+        if (lane == src) {
+            const int cnt = sCnt[warp];
+            ChainVars<MAXD> &ch = states[i].cs.ch;
+            if (cnt == 0) ch.preq = 1;
+            else if (cnt <= LMC_PREQ_CAP) {
+                int idx[LMC_CACHE_KNN]; float dist[LMC_CACHE_KNN]; int found = 0;
+                for (int k = 0; k < cnt; k++) {              // the KNN smallest insertion indices, ascending
+                    const int e = sIdx[warp][k]; const float dd = sDist[warp][k];
+                    int m = found < LMC_CACHE_KNN ? found : LMC_CACHE_KNN - 1;
+                    if (found == LMC_CACHE_KNN && e > idx[m]) continue;
+                    while (m > 0 && idx[m - 1] > e) { idx[m] = idx[m - 1]; dist[m] = dist[m - 1]; m--; }
+                    idx[m] = e; dist[m] = dd;
+                    if (found < LMC_CACHE_KNN) found++;
+                }
+                cache_average(base, d, found, idx, dist, ch.v1, ch.v2);
+                ch.preq = 2;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // launchers (defined by LMC_INSTANTIATE_CHAIN in chain_inst_*.cu)
 #ifndef LMC_WAVEFRONT_MIN_CHAINS
 #define LMC_WAVEFRONT_MIN_CHAINS 393216     // measured crossover on B200 (torus, maxdepth 8): 2^18 -> monolithic, 2^19 -> wavefront
@@ -1182,12 +1277,13 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
             // its finish and the next iteration's begin, so the two are not fused
             const int CB = (n + LMC_CACHE_BLOCK - 1) / LMC_CACHE_BLOCK;
             int *active = wc.cacheBlockCounts + LMC_CACHE_SLOTS * CB;
+            k_cache_prequery<MAXD><<<(n + 255) / 256, 256, 0, st>>>(sc, states, n);
             k_wave_finish<MAXD, 0><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides, wl);
             k_cache_count<MAXD><<<CB, LMC_CACHE_BLOCK, 0, st>>>(sc, states, n, wc.cacheBlockCounts);
             k_cache_scan<<<1, 1024, 0, st>>>(sc.gc, wc.cacheBlockCounts, CB, active);
             k_cache_write<MAXD><<<CB, LMC_CACHE_BLOCK, 0, st>>>(sc, states, n, wc.cacheBlockCounts, active);
             k_cache_grid<<<LMC_CACHE_SLOTS, 256, 0, st>>>(sc.gc);
-            *launches += 1;
+            *launches += 2;
             if (k + 1 < numSteps) k_wave_begin<MAXD><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, wl);
             *launches += 4;
         } else if (k + 1 < numSteps) k_wave_finish<MAXD, 1><<<G, B, 0, st>>>(sc, rp, chainBase, states, n, film, trace, aTrace, numSteps, k, sides, wl);
