@@ -102,9 +102,26 @@ __device__ __forceinline__ void list_append(int *list, int *counter, bool pred, 
     base = __shfl_sync(mask, base, leader);
     list[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
+// counter++ for every thread that gets here, as ONE atomic per group of converged lanes: the shadow-ray and connection
+// queues take millions of pushes per iteration on a single counter, and an atomic that returns its value costs the
+// pushing warp a full L2 round trip per lane (ncu, veach-door k_shade<G_CAM>: 30 % of all stall samples sat behind the
+// two ATOM instructions of the per-thread form).
+__device__ __forceinline__ int warp_agg_inc(int *counter) {
+    const unsigned mask = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
 __device__ __forceinline__ void sort_key_set(const SortList &sl, int i, int key) {
     sl.keys[i] = key;
-    if (key >= 0) atomicAdd(sl.hist + key, 1);
+    if (key >= 0) {
+        // the gradient lists have a few dozen class keys: lanes with the same key add once
+        const unsigned peers = __match_any_sync(__activemask(), key);
+        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(sl.hist + key, __popc(peers));
+    }
 }
 __device__ __forceinline__ int class_key(int camDepth, int lgtDepth, int kindBit) {
     int k = ((camDepth & 15) * 9 + (lgtDepth < 8 ? lgtDepth : 8)) * 2 + kindBit;
@@ -425,7 +442,7 @@ struct DevShadowSink {
     __device__ __forceinline__ void emit_connection(const Scene &scn, int camDepth, int lgtDepth, int slot, const BidirPathState *ls,
                                                     const SurfaceVertex *lgtVerts, const BidirPathState &cps, const SurfaceVertex &camVertex,
                                                     V2 screenPos, SubpathContrib *c, int *flag) {
-        const int pos = atomicAdd(cq.count, 1);
+        const int pos = warp_agg_inc(cq.count);
         if (pos < cq.cap) {
             CamSnap &sn = snaps[camDepth];
             if (sn.pad[0] != camDepth + 1) {       // first pair of this camera vertex (pad[0] is reset by k_prop_start)
@@ -440,7 +457,7 @@ struct DevShadowSink {
         }
     }
     __device__ __forceinline__ void emit(const Ray &ray, float dist, int, int *flag) {
-        const int pos = atomicAdd(sh.count, 1);
+        const int pos = warp_agg_inc(sh.count);
         if (pos < sh.cap) {
             sh.org[pos] = make_float4(ray.org.x, ray.org.y, ray.org.z, dist);
             sh.dir[pos] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, 0.0f);
