@@ -355,3 +355,25 @@ def test_cuda_textured_parameter_scene_bit_identical(lmc, oracle):
     ofilm, otrace, oa, ostats = oracle_run(oracle, xml, {"maxdepth": 6}, chains, steps, norm, init_ls, samples_per_chain=steps)
     assert np.array_equal(trace, otrace) and np.array_equal(a.view(np.uint32), oa.view(np.uint32))
     assert np.allclose(film, ofilm, rtol=1e-4, atol=1e-5 * max(1.0, float(ofilm.max())))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chains,opts", [
+    (1, {"maxdepth": 8}), (33, {"maxdepth": 8}), (1000, {"maxdepth": 3}), (257, {"maxdepth": 8, "h2mc": 1, "mala": 0}),
+    (1000, {"maxdepth": 6, "globalcache": 1}), (77, {"maxdepth": 12}),
+])
+def test_cuda_ragged_sizes_bit_identical(lmc, oracle, torus_xml, chains, opts):
+    """Chain counts that are no multiple of a warp / block / list alignment, the shallowest depths, every mutation kind:
+    grids, list padding and queue sizing must not depend on round numbers (wavefront path forced by conftest)."""
+    sc = lmc.ParseScene(torus_xml)
+    sc.options.update(opts)
+    steps = 24
+    norm, init_ls = lmc.MLTInit(sc, 30000, chains, 32)
+    ctx = lmc.ChainContext(sc, 0)
+    ctx.begin(chains, norm, init_ls, samples_per_chain=steps)
+    trace, a = ctx.run(steps, trace=True, a_trace=True)
+    st = ctx.stats()
+    ctx.close()
+    ofilm, otrace, oa, ostats = oracle_run(oracle, torus_xml, opts, chains, steps, norm, init_ls, samples_per_chain=steps)
+    assert np.array_equal(trace, otrace) and np.array_equal(a.view(np.uint32), oa.view(np.uint32))
+    assert st["proposed"] == [int(x) for x in ostats[:4]] and st["gradient_evals"] == int(ostats[8])
