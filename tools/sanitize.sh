@@ -13,6 +13,9 @@ ARGS="13 6 1";  run memcheck "torus LMC L8, 8192 chains x 6 (reverse-sweep gradi
 ARGS="12 4 1";  run memcheck "door LMC L12, 4096 chains x 4" LMC_SCENE=veachdoor/lmc.xml LMC_MAXDEPTH=12
 ARGS="11 4 1";  run memcheck "torus H2MC L8, 2048 chains x 4 (FoR Hessian + k_h2mc_gaussian)" LMC_SCENE=torus/h2mc.xml
 ARGS="12 6 1";  run memcheck "torus textured.xml L6, 4096 chains x 6 (textured parameters)" LMC_SCENE=torus/textured.xml LMC_MAXDEPTH=6
+ARGS="12 130 1"; run memcheck "torus LMC L6 global cache on, 4096 chains x 130 (k_cache_*, k_cache_prequery)" LMC_SCENE=torus/lmc.xml LMC_MAXDEPTH=6 LMC_OPTS=globalcache=1
+ARGS="12 130 1"; run racecheck "torus LMC L6 global cache on (shared lists of k_cache_prequery)" LMC_SCENE=torus/lmc.xml LMC_MAXDEPTH=6 LMC_OPTS=globalcache=1
+ARGS="12 130 1"; run synccheck "torus LMC L6 global cache on" LMC_SCENE=torus/lmc.xml LMC_MAXDEPTH=6 LMC_OPTS=globalcache=1
 ARGS="13 6 1";  run synccheck "torus LMC L8" LMC_SCENE=torus/lmc.xml
 ARGS="11 4 1";  run synccheck "torus H2MC L8 (half-warp __syncwarp masks of k_h2mc_gaussian)" LMC_SCENE=torus/h2mc.xml
 ARGS="11 3 1";  run racecheck "torus H2MC L8 (shared-memory Jacobi)" LMC_SCENE=torus/h2mc.xml
