@@ -661,6 +661,9 @@ __global__ void __launch_bounds__(LMC_SHADE_BLOCK, LMC_SHADE_MINB) k_shade(const
     const int nextSet = curSet ^ 1;
     for (int base = blockIdx.x * blockDim.x; base < count; base += stride) {
 #ifndef LMC_SHADE_NOSYNC
+#ifdef LMC_SHADE_SYNC_EVERY
+        if (((base / stride) % LMC_SHADE_SYNC_EVERY) == 0)
+#endif
         __syncthreads();          // keep the block's warps in the same stretch of code (instruction fetch)
 #endif
         const int t = base + threadIdx.x;
