@@ -213,7 +213,10 @@ def device_run(lmc, torch, dist, workload, n_local, M, K, W, rank, world, local,
         scene.options[k] = v
     total = n_local * world
     stream = torch.cuda.current_stream()
-    # ---- setup (untimed): MLTInit with the init paths generated on rank 0's GPU (lmc_mlt_init_device), broadcast ----
+    # ---- setup (untimed): MLTInit with the init paths generated on rank 0's GPU (lmc_mlt_init_device), broadcast.
+    # (The sharded form, lmc_mlt_init_device_part on every rank + all-gather + lmc_mlt_init_finish, gives the same bits but
+    # is slower here -- 2.0 s against 0.7 s at N = 2: the cost is moving and scanning ~2.4 lsScores per init sample on the
+    # host, not generating the paths.) ----
     t_setup = time.time()
     ctx = lmc.ChainContext(scene, local, stream=stream.cuda_stream)
     init_t = torch.zeros(total + 1, dtype=torch.float32, device="cuda")

@@ -117,6 +117,17 @@ int lmc_set_stream(lmc_ctx *ctx, void *cuda_stream);
 int lmc_mlt_init_device(lmc_ctx *ctx, int64_t num_init_samples, int32_t num_chains, int32_t logical_threads,
                         float *normalization, float *init_ls_score);
 
+/* The same, split for several GPUs: every rank generates the init paths of ITS logical threads
+ * [thread_begin, thread_end) and gets their lsScores in (thread, sample, contribution) order; the host concatenates
+ * the parts in thread order (an all-gather) and runs the sequential tail (score sum, CDF, equal-spaced seeding,
+ * src/mlt.h:107-153) with lmc_mlt_init_finish.  Bit-identical to lmc_mlt_init_device / lmc_mlt_init for the same
+ * logical_threads.  Call with scores == NULL first to learn *num_scores (the part is generated then and kept), then
+ * with a buffer of that capacity. */
+int lmc_mlt_init_device_part(lmc_ctx *ctx, int64_t num_init_samples, int32_t logical_threads, int32_t thread_begin, int32_t thread_end,
+                             float *scores, int64_t capacity, int64_t *num_scores);
+int lmc_mlt_init_finish(const float *scores, int64_t num_scores, int64_t num_init_samples, int32_t num_chains,
+                        float *normalization, float *init_ls_score);
+
 /* DirectLighting(scene, buffer) (src/direct.cpp:4-54): the direct-illumination pre-pass of
  * MLT(), direct_spp samples per pixel (the scene's <integer name="directspp">), one RNG per 16 x 16 tile as in
  * the reference.  host_rgb receives the UNWEIGHTED sample buffer (W*H*3 floats); the caller merges it with the

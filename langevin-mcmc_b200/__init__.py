@@ -17,7 +17,7 @@ There is NO CPU fallback: importing works without a GPU (so the loader / ABI can
 but every compute call raises LmcError when the CUDA library or a device is missing.
 """
 from .api import (LmcError, MutationType, Scene, ParseScene, MLTInit, ChainContext, MLT, load_library,
-                  lib_path, decode_trace, MergeBuffer, WriteImage, comm_unique_id)
+                  lib_path, decode_trace, MergeBuffer, WriteImage, comm_unique_id, mlt_init_finish)
 
 __all__ = ["LmcError", "MutationType", "Scene", "ParseScene", "MLTInit", "ChainContext", "MLT", "load_library",
-           "lib_path", "decode_trace", "MergeBuffer", "WriteImage", "comm_unique_id"]
+           "lib_path", "decode_trace", "MergeBuffer", "WriteImage", "comm_unique_id", "mlt_init_finish"]

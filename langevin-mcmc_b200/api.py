@@ -161,6 +161,17 @@ def MLTInit(scene, numInitSamples=None, numChains=None, logicalThreads=32):
     return norm.value, init_ls
 
 
+def mlt_init_finish(scores, numInitSamples, numChains):
+    """The sequential tail of MLTInit (src/mlt.h:107-153) over the concatenated lsScores of all init contributions
+    (ChainContext.mlt_init_part of every rank, in thread order) -> (normalization, initLsScore[numChains])."""
+    scores = np.ascontiguousarray(scores, np.float32)
+    norm = ctypes.c_float()
+    init_ls = np.zeros(int(numChains), np.float32)
+    _check(load_library().lmc_mlt_init_finish(_ptr(scores), ctypes.c_int64(scores.size), ctypes.c_int64(int(numInitSamples)),
+                                              int(numChains), ctypes.byref(norm), _ptr(init_ls)))
+    return norm.value, init_ls
+
+
 def MergeBuffer(buffer1, b1Weight, buffer2, b2Weight):
     """src/image.h:79-98 followed by BufferToFilm (:100-105): film = b1Weight * buffer1 + b2Weight * buffer2
     (lmc_merge_buffer)."""
@@ -209,6 +220,18 @@ class ChainContext:
         _check(load_library().lmc_mlt_init_device(self._c, int(numInitSamples), int(numChains), int(logicalThreads),
                                                   ctypes.byref(norm), _ptr(init_ls)))
         return norm.value, init_ls
+
+    def mlt_init_part(self, numInitSamples, logicalThreads, threadBegin, threadEnd):
+        """lsScores of the init paths of logical threads [threadBegin, threadEnd), generated on this GPU
+        (lmc_mlt_init_device_part): one shard of MLTInit per rank, see mlt_init_finish."""
+        n = ctypes.c_int64()
+        L = load_library()
+        _check(L.lmc_mlt_init_device_part(self._c, ctypes.c_int64(int(numInitSamples)), int(logicalThreads), int(threadBegin),
+                                          int(threadEnd), None, ctypes.c_int64(0), ctypes.byref(n)))
+        out = np.zeros(max(1, n.value), np.float32)
+        _check(L.lmc_mlt_init_device_part(self._c, ctypes.c_int64(int(numInitSamples)), int(logicalThreads), int(threadBegin),
+                                          int(threadEnd), _ptr(out), ctypes.c_int64(out.size), ctypes.byref(n)))
+        return out[:n.value]
 
     def direct_lighting(self, direct_spp=None):
         """DirectLighting(scene, buffer), src/direct.cpp:4-54 -> unweighted H x W x 3 sample buffer."""

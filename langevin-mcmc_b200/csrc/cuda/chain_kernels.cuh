@@ -845,9 +845,12 @@ __global__ void __launch_bounds__(LMC_CHAIN_BLOCK) k_prop_post_large(const __gri
 // normalisation) stay sequential on the host so that both forms agree bit for bit.
 template <int MAXD, int EMIT>
 __global__ void __launch_bounds__(128) k_mlt_init_paths(const __grid_constant__ Scene sc, long long numInitSamples, int logicalThreads,
-                                                        int *counts, const long long *offsets, float *scores) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= logicalThreads) return;
+                                                        int tBegin, int tEnd, int *counts, const long long *offsets, float *scores) {
+    // logical threads [tBegin, tEnd) of logicalThreads: a shard of the init pass (one per GPU); counts / offsets are
+    // indexed relative to tBegin
+    const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = tBegin + tl;
+    if (t >= tEnd) return;
     uint32_t tab[64];
     Rng rng; rng.tab = tab; rng.stride = 1;
     rng_seed_lazy(rng, (uint64_t)(long long)(t + sc.opt.seedOffset));
@@ -857,7 +860,7 @@ __global__ void __launch_bounds__(128) k_mlt_init_paths(const __grid_constant__ 
     Path<MAXD> path;
     ContribList<Limits<MAXD>::MAXC> contribs;
     int count = 0;
-    long long pos = EMIT ? offsets[t] : 0;
+    long long pos = EMIT ? offsets[tl] : 0;
     for (long long s = 0; s < n; s++) {
         contribs.clear();
         path_clear(path);
@@ -865,7 +868,7 @@ __global__ void __launch_bounds__(128) k_mlt_init_paths(const __grid_constant__ 
         if (EMIT) for (int i = 0; i < contribs.n; i++) scores[pos++] = contribs.c[i].lsScore;
         count += contribs.n;
     }
-    if (!EMIT) counts[t] = count;
+    if (!EMIT) counts[tl] = count;
 }
 
 template <int MAXD>
@@ -1126,7 +1129,7 @@ struct WaveCfg {
                                         const WaveLists &wl, const WaveCfg &wc, unsigned long long *launches, H2mcSide *sides); \
     cudaError_t launch_chain_stats_##MAXD(cudaStream_t st, const void *states, int n, unsigned long long *out); \
     cudaError_t launch_mlt_init_paths_##MAXD(cudaStream_t st, const Scene &sc, long long numInitSamples, int logicalThreads, \
-                                             int emit, int *counts, const long long *offsets, float *scores);
+                                             int tBegin, int tEnd, int emit, int *counts, const long long *offsets, float *scores);
 LMC_DECLARE_CHAIN(4)
 LMC_DECLARE_CHAIN(8)
 LMC_DECLARE_CHAIN(12)
@@ -1335,10 +1338,10 @@ cudaError_t launch_chain_run_t(cudaStream_t st, const Scene &sc, const RunParams
         return cudaGetLastError(); \
     } \
     cudaError_t launch_mlt_init_paths_##MAXD(cudaStream_t st, const Scene &sc, long long numInitSamples, int logicalThreads, \
-                                             int emit, int *counts, const long long *offsets, float *scores) { \
-        const int g = (logicalThreads + 127) / 128; \
-        if (emit) k_mlt_init_paths<MAXD, 1><<<g, 128, 0, st>>>(sc, numInitSamples, logicalThreads, counts, offsets, scores); \
-        else k_mlt_init_paths<MAXD, 0><<<g, 128, 0, st>>>(sc, numInitSamples, logicalThreads, counts, offsets, scores); \
+                                             int tBegin, int tEnd, int emit, int *counts, const long long *offsets, float *scores) { \
+        const int g = (tEnd - tBegin + 127) / 128; \
+        if (emit) k_mlt_init_paths<MAXD, 1><<<g, 128, 0, st>>>(sc, numInitSamples, logicalThreads, tBegin, tEnd, counts, offsets, scores); \
+        else k_mlt_init_paths<MAXD, 0><<<g, 128, 0, st>>>(sc, numInitSamples, logicalThreads, tBegin, tEnd, counts, offsets, scores); \
         return cudaGetLastError(); \
     }
 

@@ -125,6 +125,7 @@ struct lmc_ctx {
     double lastMs = 0.0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float *cacheData = nullptr; int *cacheInts = nullptr;       // global cache (option globalcache): entries; count[5] + ready[5] + gridReady[5]
+    std::vector<float> initPart; long long initPartKey[4] = {0, 0, 0, 0}; bool initPartValid = false;   // lmc_mlt_init_device_part
     int *cacheGrid = nullptr;                                   // query grids of the ready slots (scene.h LMC_CACHE_GRID_INTS per slot)
     int *cacheBlockCounts = nullptr; int cacheBlockCap = 0;
     ncclComm_t comm = nullptr;      // film all-reduce (lmc_create_multi / lmc_comm_init_rank); NULL for a lone ctx
@@ -318,24 +319,25 @@ int lmc_mlt_init(const lmc_scene *scene, int64_t num_init_samples, int32_t num_c
     return LMC_OK;
 }
 
-int lmc_mlt_init_device(lmc_ctx *c, int64_t num_init_samples, int32_t num_chains, int32_t logical_threads,
-                        float *normalization, float *init_ls_score) {
-    if (!c || !normalization || num_chains <= 0 || num_init_samples <= 0 || logical_threads <= 0) return fail(LMC_ERR_ARG, "bad argument");
+// Init paths of the logical threads [t0, t1) on this ctx's GPU: lsScores of their contributions in (thread, sample,
+// contribution) order.  Two passes of k_mlt_init_paths (count, then emit at the scanned offsets).
+static int mlt_init_device_scores(lmc_ctx *c, int64_t num_init_samples, int32_t logical_threads, int32_t t0, int32_t t1,
+                                  std::vector<float> &scores) {
     CK(cudaSetDevice(c->device));
     const int d = c->maxdTemplate;
-    const int T = logical_threads;
+    const int T = t1 - t0;
+    scores.clear();
+    if (T <= 0) return LMC_OK;
     DevBuf<int> dCounts; DevBuf<long long> dOffsets; DevBuf<float> dScores;
     CK(dCounts.alloc((size_t)T));
     CK(dOffsets.alloc((size_t)T));
     auto launch = [&](int emit) {
-        return d == 4 ? launch_mlt_init_paths_4(c->stream, c->sc, num_init_samples, T, emit, dCounts, dOffsets, dScores)
-                      : (d == 8 ? launch_mlt_init_paths_8(c->stream, c->sc, num_init_samples, T, emit, dCounts, dOffsets, dScores)
-                                : launch_mlt_init_paths_12(c->stream, c->sc, num_init_samples, T, emit, dCounts, dOffsets, dScores));
+        return d == 4 ? launch_mlt_init_paths_4(c->stream, c->sc, num_init_samples, logical_threads, t0, t1, emit, dCounts, dOffsets, dScores)
+                      : (d == 8 ? launch_mlt_init_paths_8(c->stream, c->sc, num_init_samples, logical_threads, t0, t1, emit, dCounts, dOffsets, dScores)
+                                : launch_mlt_init_paths_12(c->stream, c->sc, num_init_samples, logical_threads, t0, t1, emit, dCounts, dOffsets, dScores));
     };
-    int rc = LMC_OK;
     std::vector<int> counts(T);
     std::vector<long long> offsets(T);
-    std::vector<float> scores;
     cudaError_t e = launch(0);
     c->launches++;
     if (e == cudaSuccess) e = cudaMemcpyAsync(counts.data(), dCounts, sizeof(int) * (size_t)T, cudaMemcpyDeviceToHost, c->stream);
@@ -350,11 +352,46 @@ int lmc_mlt_init_device(lmc_ctx *c, int64_t num_init_samples, int32_t num_chains
     if (e == cudaSuccess) { e = launch(1); c->launches++; }
     if (e == cudaSuccess && total > 0) e = cudaMemcpyAsync(scores.data(), dScores, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) rc = fail(LMC_ERR_CUDA, std::string("lmc_mlt_init_device: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(LMC_ERR_CUDA, std::string("lmc_mlt_init_device: ") + cudaGetErrorString(e));
+    return LMC_OK;
+}
+
+int lmc_mlt_init_device(lmc_ctx *c, int64_t num_init_samples, int32_t num_chains, int32_t logical_threads,
+                        float *normalization, float *init_ls_score) {
+    if (!c || !normalization || num_chains <= 0 || num_init_samples <= 0 || logical_threads <= 0) return fail(LMC_ERR_ARG, "bad argument");
+    std::vector<float> scores;
+    const int rc = mlt_init_device_scores(c, num_init_samples, logical_threads, 0, logical_threads, scores);
     if (rc) return rc;
+    return lmc_mlt_init_finish(scores.data(), (int64_t)scores.size(), num_init_samples, num_chains, normalization, init_ls_score);
+}
+
+int lmc_mlt_init_device_part(lmc_ctx *c, int64_t num_init_samples, int32_t logical_threads, int32_t thread_begin, int32_t thread_end,
+                             float *scores, int64_t capacity, int64_t *num_scores) {
+    if (!c || !num_scores || num_init_samples <= 0 || logical_threads <= 0 || thread_begin < 0 || thread_end > logical_threads ||
+        thread_begin > thread_end) return fail(LMC_ERR_ARG, "bad argument");
+    // the part is generated on the first call (scores == NULL asks for its size) and kept until it has been copied out
+    if (!(c->initPartValid && c->initPartKey[0] == num_init_samples && c->initPartKey[1] == logical_threads &&
+          c->initPartKey[2] == thread_begin && c->initPartKey[3] == thread_end)) {
+        const int rc = mlt_init_device_scores(c, num_init_samples, logical_threads, thread_begin, thread_end, c->initPart);
+        if (rc) return rc;
+        c->initPartKey[0] = num_init_samples; c->initPartKey[1] = logical_threads; c->initPartKey[2] = thread_begin; c->initPartKey[3] = thread_end;
+        c->initPartValid = true;
+    }
+    *num_scores = (int64_t)c->initPart.size();
+    if (!scores) return LMC_OK;
+    if (capacity < *num_scores) return fail(LMC_ERR_ARG, "lmc_mlt_init_device_part: capacity too small");
+    if (!c->initPart.empty()) memcpy(scores, c->initPart.data(), sizeof(float) * c->initPart.size());
+    c->initPart.clear(); c->initPart.shrink_to_fit(); c->initPartValid = false;
+    return LMC_OK;
+}
+
+int lmc_mlt_init_finish(const float *scores, int64_t num_scores, int64_t num_init_samples, int32_t num_chains,
+                        float *normalization, float *init_ls_score) {
+    if ((!scores && num_scores > 0) || num_scores < 0 || !normalization || num_chains <= 0 || num_init_samples <= 0) return fail(LMC_ERR_ARG, "bad argument");
     try {
+        const std::vector<float> v(scores, scores + num_scores);
         lmc_host::InitResult r;
-        lmc_host::mlt_init_finish(scores, num_init_samples, num_chains, r);
+        lmc_host::mlt_init_finish(v, num_init_samples, num_chains, r);
         *normalization = r.normalization;
         if (init_ls_score) memcpy(init_ls_score, r.initLsScore.data(), sizeof(float) * (size_t)num_chains);
     } catch (const std::exception &ex) { return fail(LMC_ERR_STATE, ex.what()); }

@@ -111,3 +111,12 @@ def test_cuda_mlt_init_device_equals_host(lmc, torus_xml, door_xml):
         assert np.float32(norm_h).tobytes() == np.float32(norm_d).tobytes()
         assert np.array_equal(ls_h.view(np.uint32), ls_d.view(np.uint32))
         assert norm_d > 0 and (ls_d > 0).all()
+        # the multi-GPU split: three uneven shards of the logical threads, concatenated in thread order, + the
+        # sequential tail (lmc_mlt_init_device_part / lmc_mlt_init_finish) give the same bits again
+        ctx = lmc.ChainContext(sc, 0)
+        cuts = [0, threads // 3, threads // 3 + 1, threads]
+        parts = [ctx.mlt_init_part(samples, threads, cuts[k], cuts[k + 1]) for k in range(3)]
+        ctx.close()
+        norm_s, ls_s = lmc.mlt_init_finish(np.concatenate(parts), samples, chains)
+        assert np.float32(norm_s).tobytes() == np.float32(norm_d).tobytes()
+        assert np.array_equal(ls_s.view(np.uint32), ls_d.view(np.uint32))
