@@ -20,4 +20,7 @@ ARGS="13 6 1";  run synccheck "torus LMC L8" LMC_SCENE=torus/lmc.xml
 ARGS="11 4 1";  run synccheck "torus H2MC L8 (half-warp __syncwarp masks of k_h2mc_gaussian)" LMC_SCENE=torus/h2mc.xml
 ARGS="11 3 1";  run racecheck "torus H2MC L8 (shared-memory Jacobi)" LMC_SCENE=torus/h2mc.xml
 ARGS="12 3 1";  run racecheck "torus LMC L8" LMC_SCENE=torus/lmc.xml
+unset LMC_WAVEFRONT
+ARGS="12 6 1";  LMC_WAVEFRONT=0 run memcheck "torus LMC L8 monolithic form, 4096 chains x 6 (large-step proposals on the auxiliary stream)" LMC_SCENE=torus/lmc.xml LMC_WAVEFRONT=0
+ARGS="12 6 1";  run synccheck "door LMC L12 (warp-aggregated queue counters)" LMC_SCENE=veachdoor/lmc.xml LMC_MAXDEPTH=12 LMC_WAVEFRONT=1
 cat $OUT
