@@ -44,10 +44,11 @@ LMC_HD void isotropic_gaussian(int dim, float sigma, Gaussian<DIM> &g) {
 
 template <int DIM>
 LMC_HD float gaussian_log_pdf(const float *offset, float sign, const Gaussian<DIM> &g) {
-    float logPdf = (float)g.dim * (-0.9189385332046727f);
+    const int dim = g.dim;
+    float logPdf = (float)dim * (-0.9189385332046727f);
     logPdf += 0.5f * g.logDet;
     float q = 0.0f;
-    for (int i = 0; i < g.dim; i++) {
+    for (int i = 0; i < dim; i++) {
         const float d = sign * offset[i] - g.mean[i];
         q += d * (g.invCov_d[i] * d);
     }
@@ -57,9 +58,12 @@ LMC_HD float gaussian_log_pdf(const float *offset, float sign, const Gaussian<DI
 
 template <int DIM>
 LMC_HD void generate_sample(const Gaussian<DIM> &g, float *x, Rng &rng) {
+    // (g and x both live in the chain record: the dimension is read once and each element is scaled where it is drawn, so
+    // that the loop neither reloads its bound after every store nor makes a second pass through global memory -- same
+    // draws, same arithmetic as `x = normal; x = covL_d * x + mean`, src/gaussian.cpp:44-54)
     NormalDist nd = normal_make(0.0f, 1.0f);
-    for (int i = 0; i < g.dim; i++) x[i] = normal_draw(nd, rng);
-    for (int i = 0; i < g.dim; i++) x[i] = g.covL_d[i] * x[i] + g.mean[i];
+    const int dim = g.dim;
+    for (int i = 0; i < dim; i++) { const float z = normal_draw(nd, rng); x[i] = g.covL_d[i] * z + g.mean[i]; }
 }
 
 // ComputeGaussian (src/mala.cpp:7-51)
@@ -67,12 +71,12 @@ template <int DIM>
 LMC_HD void compute_gaussian_lmc(int dim, const float *v1, const float *M, float ss, float shk, float sc,
                                  Gaussian<DIM> &g) {
     g.dim = dim;
-    g.logDet = 0.0f;
     const float shrk = inverse(shk * shk);
     if (sc <= 1e-10f) {
         for (int i = 0; i < dim; i++) { g.mean[i] = 0.0f; g.invCov_d[i] = shrk; g.covL_d[i] = shk; }
         g.logDet = (float)dim * dm_fastlog(inverse(shk * shk));
     } else {
+        float logDet = 0.0f;            // summed in a register (g is the chain record), stored once
         for (int i = 0; i < dim; i++) {
             const float cov_t = ss * ss * (M[i] + 1.0f);
             const float invcov = inverse(cov_t) + shrk;
@@ -80,8 +84,9 @@ LMC_HD void compute_gaussian_lmc(int dim, const float *v1, const float *M, float
             g.invCov_d[i] = invcov;
             g.covL_d[i] = dm_sqrt(cov);
             g.mean[i] = dm_clamp(v1[i], LMC_MTM_MIN, LMC_MTM_MAX) * cov / 2.0f;
-            g.logDet += dm_fastlog(invcov);
+            logDet += dm_fastlog(invcov);
         }
+        g.logDet = logDet;
     }
 }
 
@@ -529,8 +534,8 @@ LMC_HD_NOINLINE void mala_finish_gaussian(const Scene &sc, const MarkovState<MAX
     for (int i = 0; i < dim; i++) norm += vGrad[i] * vGrad[i];
     norm = dm_sqrt(norm);
     for (int i = 0; i < dim; i++) vGrad[i] *= drift / dm_max(drift, norm);
-    bool first = true;
-    for (int i = 0; i < dim; i++) if (new_v2[i] > 1e-10f) { first = false; break; }
+    bool first = true;                  // (no early exit: the loads of the record's vector stay independent)
+    for (int i = 0; i < dim; i++) first &= !(new_v2[i] > 1e-10f);
     float M[Limits<MAXD>::DIM];
     for (int i = 0; i < dim; i++) {
         const float g = vGrad[i];
@@ -553,7 +558,7 @@ template <int MAXD>
 LMC_HD void phase_begin(const Scene &sc, const RunParams &rp, long long sampleIdx, MarkovState<MAXD> &cur,
                         ChainVars<MAXD> &ch, Rng &rng, StepScratch<MAXD> &ss) {
     ss.needCurGrad = 0; ss.needPropGrad = 0; ss.hasContrib = 0; ss.a = 1.0f;
-    ch.preq = 0;
+    if (sc.opt.cacheEnabled) ch.preq = 0;       // (cache runs only: the flag sits in a sector of the record nothing else touches here)
     const float lsScale = ((float)sampleIdx > (float)rp.numSamplesThisChain * sc.opt.lsRatio) ? sc.opt.largeStepProbScale : 1.0f;
     if (!cur.valid || rng_uniform(rng) < sc.opt.largeStepProbability * lsScale) { ss.kind = STEP_LARGE; return; }
     if (!sc.opt.mala && !sc.opt.h2mc) { ss.kind = STEP_ISO; return; }

@@ -63,7 +63,8 @@ __global__ void k_chain_init(ChainRec<MAXD> *states, int n, int chainBase, const
 #define LMC_CHAIN_BLOCK 128
 #endif
 #ifndef LMC_FINISH_MINB
-#define LMC_FINISH_MINB 1          // resident blocks per SM asked of k_wave_finish (1 = ptxas picks: 96 registers, 5 blocks)
+#define LMC_FINISH_MINB 5          // resident blocks per SM asked of k_wave_finish: <= 102 registers, 20 warps (measured: 4..6 are
+                                   // equivalent, 8 = 64 registers is 3 % slower, and 1 lets ptxas take 168 registers: +0.12 ms)
 #endif
 
 // ---- wavefront execution of one chain-loop iteration -----------------------------------------
@@ -117,11 +118,14 @@ __device__ __forceinline__ int warp_agg_inc(int *counter) {
 }
 __device__ __forceinline__ void sort_key_set(const SortList &sl, int i, int key) {
     sl.keys[i] = key;
-    if (key >= 0) {
-        // the gradient lists have a few dozen class keys: lanes with the same key add once
+    if (key < 0) return;
+    if (sl.nkeys <= LMC_NKEYS) {
+        // the gradient lists have a few dozen class keys: lanes with the same key add once.  (Not for the small-step list:
+        // its 65 536 (class, tile) keys are mostly distinct within a warp and __match_any_sync costs a round per distinct
+        // value -- measured +0.12 ms on k_wave_finish.)
         const unsigned peers = __match_any_sync(__activemask(), key);
         if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(sl.hist + key, __popc(peers));
-    }
+    } else atomicAdd(sl.hist + key, 1);
 }
 __device__ __forceinline__ int class_key(int camDepth, int lgtDepth, int kindBit) {
     int k = ((camDepth & 15) * 9 + (lgtDepth < 8 ? lgtDepth : 8)) * 2 + kindBit;
