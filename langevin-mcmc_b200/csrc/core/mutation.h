@@ -63,7 +63,11 @@ LMC_HD void generate_sample(const Gaussian<DIM> &g, float *x, Rng &rng) {
     // draws, same arithmetic as `x = normal; x = covL_d * x + mean`, src/gaussian.cpp:44-54)
     NormalDist nd = normal_make(0.0f, 1.0f);
     const int dim = g.dim;
-    for (int i = 0; i < dim; i++) { const float z = normal_draw(nd, rng); x[i] = g.covL_d[i] * z + g.mean[i]; }
+    for (int i = 0; i < dim; i++) {
+        const float cl = g.covL_d[i], mu = g.mean[i];       // in flight while the variate is drawn
+        const float z = normal_draw(nd, rng);
+        x[i] = cl * z + mu;
+    }
 }
 
 // ComputeGaussian (src/mala.cpp:7-51)
